@@ -1,0 +1,121 @@
+/*
+ * sfh.h — C ABI of the B200 (sm_100a) implementation of Stonefish's per-triangle hydrodynamic force
+ * integration. Plain pointers and sizes only; the shared library is stonefish_b200/libsfh.so.
+ *
+ * The reference has no FFI layer for this path: the boundary is the C++ call site
+ *   Ocean::ApplyFluidForces -> SolidEntity::ComputeHydrodynamicForces
+ *   (Library/src/entities/forcefields/Ocean.cpp:219-268, Library/src/entities/SolidEntity.cpp:1799-1850)
+ * driven once per ocean-ghost overlap pair by SimulationManager::SimulationTickCallback
+ * (Library/src/core/SimulationManager.cpp:1619-1655). Each entry point below names the reference
+ * interface it replaces; INTEGRATION.md shows the call-site patch.
+ *
+ * Error convention: the reference's integrators are `void` and cannot fail. Here every call returns
+ * SFH_OK (0) or a negative SFH_ERR_*; sfh_last_error() gives the text. There is NO CPU fallback: without a
+ * usable CUDA device sfh_create fails and nothing else can be called.
+ *
+ * Threading: one sfh_ctx per GPU (per process/rank). A context is not re-entrant; calls on different
+ * contexts are independent. sfh_mesh_upload may be called concurrently from several host threads.
+ */
+#ifndef SFH_H
+#define SFH_H
+
+#include "sfh_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFH_ABI_VERSION 1
+
+enum {
+    SFH_OK = 0,
+    SFH_ERR_INVALID = -1, /* bad argument (null pointer, index out of range, too many currents, ...) */
+    SFH_ERR_CUDA = -2,    /* CUDA runtime error; text in sfh_last_error                               */
+    SFH_ERR_NO_DEVICE = -3,
+    SFH_ERR_OOM = -4,
+    SFH_ERR_STATE = -5    /* e.g. has_waves without sfh_waves_upload, sync without step              */
+};
+
+/* sfh_mesh_upload flags */
+enum {
+    SFH_MESH_KEEP_ORDER = 1u << 0 /* do not Morton-sort faces before chunking (default: sort; the sums are
+                                     order-independent within the 1e-9 contract, class counts exactly)  */
+};
+
+typedef struct sfh_ctx sfh_ctx;
+
+typedef struct sfh_mesh_stats {
+    uint32_t n_faces, n_verts;
+    uint32_t n_chunks;          /* device chunks of <=256 faces / <=256 local vertices              */
+    uint32_t n_chunk_verts;     /* vertices stored after per-chunk duplication                     */
+    uint64_t device_bytes;      /* bytes actually read per evaluation of this mesh                 */
+    uint64_t algorithmic_bytes; /* 12*n_faces + 12*n_verts                           */
+} sfh_mesh_stats;
+
+typedef struct sfh_timings {
+    float prologue_ms;  /* per-body prologue + work-list scan                                       */
+    float submerged_ms; /* per-face kernel, INSIDE bodies     (0 when not launched)                  */
+    float surface_ms;   /* per-face kernel, CROSSING bodies   (0 when not launched)                  */
+    float epilogue_ms;  /* per-body reduction + finalisation                                        */
+    float total_ms;     /* first enqueue to last enqueue of the step, incl. copies                   */
+    uint32_t launches;  /* kernels launched by the step                                             */
+    uint32_t reserved;
+    uint64_t faces;     /* triangle-evals of the step                                               */
+} sfh_timings;
+
+int sfh_abi_version(void);
+
+/* Context = one GPU: stream, pinned staging, device arenas.
+ * Replaces: the ThreadPool the reference creates for hydrodynamics (SimulationApp.cpp:132-142). */
+int sfh_create(int cuda_device, sfh_ctx** out);
+/* Same, but enqueue on a caller-owned cudaStream_t (e.g. torch's current stream) instead of a private one. */
+int sfh_create_on_stream(int cuda_device, void* cuda_stream, sfh_ctx** out);
+void sfh_destroy(sfh_ctx* ctx);
+/* Text of the last error on ctx (ctx == NULL: last error of sfh_create on this thread). Never NULL. */
+const char* sfh_last_error(const sfh_ctx* ctx);
+
+/* Static geometry, uploaded once per mesh (SolidEntity::phyMesh is immutable after BuildScenario,
+ * SolidEntity.cpp:108-112,1153-1181). `pos` points at the first vertex position and may be a strided AoS
+ * exactly as Mesh::getVertexDataPointer()/getVertexSize() give it (stride 24 or 44 bytes,
+ * OpenGLDataStructs.h:190-262); `faces` is Mesh::getFaceDataPointer() (3 u32 per face). */
+int sfh_mesh_upload(sfh_ctx* ctx, const void* pos, size_t stride_bytes, uint32_t n_verts, const uint32_t* faces,
+                    uint32_t n_faces, uint32_t flags, uint32_t* mesh_id_out);
+int sfh_mesh_release(sfh_ctx* ctx, uint32_t mesh_id);
+int sfh_mesh_get_stats(sfh_ctx* ctx, uint32_t mesh_id, sfh_mesh_stats* out);
+
+/* Wave height field = OpenGLRealOcean::fftData (OpenGLRealOcean.cpp:191-198, refreshed :333-356).
+ * Copies what the lookup can touch (layer 0 plus one row and one texel) to the device; call again whenever
+ * the field changes. The copy is ordered before the next step on the context's stream. */
+int sfh_waves_upload(sfh_ctx* ctx, const sfh_waves* waves);
+
+/* One recompute of the hydrodynamic forces of n_bodies bodies:
+ * replaces the `for each overlapping pair: ocean->ApplyFluidForces(...)` loop
+ * (SimulationManager.cpp:1625-1651) up to, not including, ApplyHydrodynamicForces.
+ * states/out are HOST buffers (pageable or pinned via sfh_host_alloc); the call enqueues H2D copies,
+ * kernels and the D2H copy of `out` and returns; `out` is valid after sfh_sync. */
+int sfh_step_async(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n_bodies,
+                   sfh_info* out);
+int sfh_sync(sfh_ctx* ctx);
+/* sfh_step_async + sfh_sync */
+int sfh_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n_bodies, sfh_info* out);
+/* As sfh_step, plus one SFH_FACE_* code per face in ORIGINAL face order, bodies concatenated in input
+ * order (sum of their meshes' n_faces bytes). Test/diagnostic entry; mirrors what DEBUG_HYDRO exposes. */
+int sfh_step_debug(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n_bodies,
+                   sfh_info* out, uint8_t* face_codes, size_t face_codes_bytes);
+/* Device-resident variant: d_states / d_out are DEVICE pointers (state already in HBM, results stay in HBM).
+ * Only the ocean parameters (a few KB) are copied. Asynchronous on the context's stream. */
+int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies,
+                    sfh_info* d_out);
+
+/* Pinned host memory for states/out so the per-step copies are truly asynchronous. */
+int sfh_host_alloc(sfh_ctx* ctx, size_t bytes, void** out);
+int sfh_host_free(sfh_ctx* ctx, void* p);
+
+/* CUDA-event timing of the kernels of each step (off by default; adds event records to the stream). */
+int sfh_set_profiling(sfh_ctx* ctx, int enabled);
+int sfh_get_timings(sfh_ctx* ctx, sfh_timings* out); /* synchronises the stream */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFH_H */

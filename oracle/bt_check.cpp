@@ -1,0 +1,200 @@
+/*
+ * bt_check.cpp — the fp64 pieces of the hot path evaluated with the reference's OWN vendored Bullet
+ * LinearMath headers (3rdparty/LinearMath, BT_USE_DOUBLE_PRECISION as in CMakeLists.txt:53).
+ *
+ * TEST INFRASTRUCTURE ONLY. Built into oracle/_ref/libbtcheck.so by oracle/Makefile from the headers where
+ * they lie under /root/reference (never copied). It pins the oracle's hand-written double-precision
+ * operator order (btVector3 dot/cross/norm/safeNormalize, btMatrix3x3::inverse, btTransform::operator(),
+ * getOpenGLMatrix) against the real classes. The statement bodies mirror the reference lines cited below;
+ * only the carrier (sfh_current instead of sf::Jet members) differs, because the reference's
+ * Jet.cpp/Pipe.cpp/Ocean.cpp/SolidEntity.cpp need glm + SDL2 + GL + a cmake-generated version.h and do
+ * not compile in this image.
+ */
+#include "../include/sfh_types.h"
+
+#include "LinearMath/btMatrix3x3.h"
+#include "LinearMath/btQuaternion.h"
+#include "LinearMath/btTransform.h"
+#include "LinearMath/btVector3.h"
+
+typedef btScalar Scalar;
+typedef btVector3 Vector3;
+typedef btMatrix3x3 Matrix3;
+typedef btTransform Transform;
+
+static Transform make_transform(const double T[12])
+{
+    return Transform(Matrix3(T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8]), Vector3(T[9], T[10], T[11]));
+}
+
+extern "C" {
+
+int btc_scalar_size(void) { return (int)sizeof(btScalar); }
+
+/* Uniform.cpp:54-57, Jet.cpp:54-75, Pipe.cpp:57-78 */
+void btc_current_velocity(const sfh_current* cur, const double pp[3], double out[3])
+{
+    Vector3 p(pp[0], pp[1], pp[2]);
+    Vector3 res(0, 0, 0);
+    if (cur->type == SFH_CURRENT_UNIFORM) {
+        res = Vector3(cur->a[0], cur->a[1], cur->a[2]);
+    } else if (cur->type == SFH_CURRENT_JET) {
+        Vector3 c(cur->a[0], cur->a[1], cur->a[2]), n(cur->n[0], cur->n[1], cur->n[2]);
+        Scalar r = cur->r1, vout = cur->vel;
+        Vector3 cp = p - c;
+        Scalar d = cp.cross(n).norm();
+        Scalar t = cp.dot(n);
+        if (t < 0.0) { res = Vector3(0, 0, 0); }
+        else {
+            Scalar r_ = Scalar(1) / Scalar(5) * (t + Scalar(5) * r);
+            if (d >= r_) { res = Vector3(0, 0, 0); }
+            else {
+                Vector3 vmax = Scalar(10) * r / (t + Scalar(5) * r) * vout * n;
+                Scalar f = btExp(-Scalar(50) * d * d / (t * t));
+                res = f * vmax;
+            }
+        }
+    } else {
+        Vector3 p1(cur->a[0], cur->a[1], cur->a[2]), n(cur->n[0], cur->n[1], cur->n[2]);
+        Scalar l = cur->l, r1 = cur->r1, r2 = cur->r2, vin = cur->vel, gamma = cur->gamma;
+        Vector3 p1p = p - p1;
+        Scalar d = p1p.cross(n).norm();
+        Scalar t = p1p.dot(n);
+        if (t < 0.0 || t > l) { res = Vector3(0, 0, 0); }
+        else {
+            Scalar r = r1 + (r2 - r1) * t / l;
+            if (d >= r) { res = Vector3(0, 0, 0); }
+            else {
+                Vector3 v = r1 / r * vin * n;
+                Scalar f = btPow(Scalar(1) - d / r, gamma);
+                res = f * v;
+            }
+        }
+    }
+    out[0] = res.x(); out[1] = res.y(); out[2] = res.z();
+}
+
+/* Jet.cpp:31-37 and Pipe.cpp:31-40: constructor-time normalisation of the axis */
+void btc_jet_axis(const double dir[3], double n_out[3])
+{
+    Vector3 n = Vector3(dir[0], dir[1], dir[2]).normalized();
+    n_out[0] = n.x(); n_out[1] = n.y(); n_out[2] = n.z();
+}
+void btc_pipe_axis(const double p1[3], const double p2[3], double n_out[3], double* l_out)
+{
+    Vector3 point1(p1[0], p1[1], p1[2]), point2(p2[0], p2[1], p2[2]);
+    Scalar l = (point2 - point1).length();
+    Vector3 n = (point2 - point1) / l;
+    n_out[0] = n.x(); n_out[1] = n.y(); n_out[2] = n.z();
+    *l_out = l;
+}
+
+/* Ocean.cpp:183-196 */
+void btc_fluid_velocity(const sfh_ocean* o, const double pp[3], double out[3])
+{
+    Vector3 fv(0, 0, 0);
+    if (o->currents_enabled) {
+        for (size_t i = 0; i < o->n_currents; ++i) {
+            if (o->currents[i].enabled) {
+                double v[3];
+                btc_current_velocity(&o->currents[i], pp, v);
+                fv += Vector3(v[0], v[1], v[2]);
+            }
+        }
+    }
+    out[0] = fv.x(); out[1] = fv.y(); out[2] = fv.z();
+}
+
+/* SolidEntity.cpp:1263-1287 */
+void btc_correct(double density, double Fdq_[3], double Tdq_[3], double Fdf_[3], double Tdf_[3], const double Cd[3],
+                 const double Cf[3], const double B[9])
+{
+    Transform T_O(Matrix3(B[0], B[1], B[2], B[3], B[4], B[5], B[6], B[7], B[8]), Vector3(0, 0, 0));
+    Vector3 _Fdq(Fdq_[0], Fdq_[1], Fdq_[2]), _Tdq(Tdq_[0], Tdq_[1], Tdq_[2]);
+    Vector3 _Fdf(Fdf_[0], Fdf_[1], Fdf_[2]), _Tdf(Tdf_[0], Tdf_[1], Tdf_[2]);
+    Vector3 fdCd(Cd[0], Cd[1], Cd[2]), fdCf(Cf[0], Cf[1], Cf[2]);
+
+    Matrix3 toOrigin = T_O.getBasis().inverse();
+
+    Vector3 Fdq = toOrigin * _Fdq;
+    Fdq = Fdq.safeNormalize();
+    Scalar Fdqc = btFabs(Fdq.getX()) * fdCd.getX() + btFabs(Fdq.getY()) * fdCd.getY() + btFabs(Fdq.getZ()) * fdCd.getZ();
+    _Fdq = Scalar(0.5) * density * Fdqc * _Fdq;
+
+    Vector3 Tdq = toOrigin * _Tdq;
+    Tdq = Tdq.safeNormalize();
+    Scalar Tdqc = btFabs(Tdq.getX()) * fdCd.getX() + btFabs(Tdq.getY()) * fdCd.getY() + btFabs(Tdq.getZ()) * fdCd.getZ();
+    _Tdq = Scalar(0.5) * density * Tdqc * _Tdq;
+
+    Vector3 Fdf = toOrigin * _Fdf;
+    Fdf = Fdf.safeNormalize();
+    Scalar Fdfc = btFabs(Fdf.getX()) * fdCf.getX() + btFabs(Fdf.getY()) * fdCf.getY() + btFabs(Fdf.getZ()) * fdCf.getZ();
+    _Fdf = density * Fdfc * _Fdf;
+
+    Vector3 Tdf = toOrigin * _Tdf;
+    Tdf = Tdf.safeNormalize();
+    Scalar Tdfc = btFabs(Tdf.getX()) * fdCf.getX() + btFabs(Tdf.getY()) * fdCf.getY() + btFabs(Tdf.getZ()) * fdCf.getZ();
+    _Tdf = density * Tdfc * _Tdf;
+
+    for (int k = 0; k < 3; ++k) { Fdq_[k] = _Fdq[k]; Tdq_[k] = _Tdq[k]; Fdf_[k] = _Fdf[k]; Tdf_[k] = _Tdf[k]; }
+}
+
+/* OpenGLDataStructs.cpp:148-156: getOpenGLMatrix then (GLfloat) per element */
+void btc_gl_matrix(const double T[12], float out[16])
+{
+    Scalar glmatrix[16];
+    make_transform(T).getOpenGLMatrix(glmatrix);
+    for (int k = 0; k < 16; ++k) out[k] = (float)glmatrix[k];
+}
+
+/* SolidEntity.cpp:1833-1834: INSIDE analytic buoyancy */
+void btc_inside_buoyancy(const double T_CG_[12], const double P_CB_[3], double volume, double density, double g,
+                         double Fb_[3], double Tb_[3])
+{
+    Transform T_CG = make_transform(T_CG_);
+    Vector3 P_CB(P_CB_[0], P_CB_[1], P_CB_[2]);
+    Vector3 gravity(0, 0, g);
+    Vector3 Fb = -volume * density * gravity;
+    Vector3 Tb = (T_CG * P_CB - T_CG.getOrigin()).cross(Fb);
+    for (int k = 0; k < 3; ++k) { Fb_[k] = Fb[k]; Tb_[k] = Tb[k]; }
+}
+
+/* SolidEntity.cpp:1703-1706 (flat-sea branch), fp64 tail only */
+void btc_flat_buoyancy(const double T_CG_[12], const double CBsub_[3], double Vsub, double density, double g,
+                       double Fb_[3], double Tb_[3])
+{
+    Transform T_CG = make_transform(T_CG_);
+    Vector3 _CBsub(CBsub_[0], CBsub_[1], CBsub_[2]);
+    Vector3 gravity(0, 0, g);
+    Vector3 _Fb = -Vsub * density * gravity;
+    Vector3 _Tb = (_CBsub - T_CG.getOrigin()).cross(_Fb);
+    for (int k = 0; k < 3; ++k) { Fb_[k] = _Fb[k]; Tb_[k] = _Tb[k]; }
+}
+
+/* helpers to build inputs the way reference scenes do: Transform(Quaternion(yaw,pitch,roll), origin)
+ * with BT_EULER_DEFAULT_ZYX (CMakeLists.txt:53), and transform composition T_A * T_B */
+void btc_transform_from_euler(double yaw, double pitch, double roll, const double origin[3], double out[12])
+{
+    btQuaternion q(yaw, pitch, roll);
+    Transform T(q, Vector3(origin[0], origin[1], origin[2]));
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) out[3 * r + c] = T.getBasis()[r][c];
+    for (int k = 0; k < 3; ++k) out[9 + k] = T.getOrigin()[k];
+}
+void btc_transform_from_quat(const double q_[4], const double origin[3], double out[12])
+{
+    btQuaternion q(q_[0], q_[1], q_[2], q_[3]);
+    Transform T(q, Vector3(origin[0], origin[1], origin[2]));
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) out[3 * r + c] = T.getBasis()[r][c];
+    for (int k = 0; k < 3; ++k) out[9 + k] = T.getOrigin()[k];
+}
+void btc_transform_mul(const double A[12], const double B[12], double out[12])
+{
+    Transform T = make_transform(A) * make_transform(B);
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) out[3 * r + c] = T.getBasis()[r][c];
+    for (int k = 0; k < 3; ++k) out[9 + k] = T.getOrigin()[k];
+}
+
+} // extern "C"

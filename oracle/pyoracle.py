@@ -1,0 +1,130 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE ONLY.
+
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by
+the product package. PARITY UNPINNED at the glm boundary (see oracle/hydro_oracle.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from stonefish_b200 import _abi
+from stonefish_b200.hydro import BODY_STATE_DTYPE, INFO_DTYPE, Mesh, Ocean
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+REF_LIB = os.path.join(HERE, "_ref", "libbtcheck.so")
+ORC_REF_F32_SEQ, ORC_F64_ACC = 0, 1
+
+
+class orc_mesh(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("stride_bytes", C.c_size_t), ("n_verts", C.c_uint32), ("faces", C.c_void_p),
+                ("n_faces", C.c_uint32)]
+
+
+def build(force: bool = False):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "hydro_oracle.cpp")):
+        subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/3rdparty/LinearMath"):
+        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        L = C.CDLL(LIB)
+        P = C.POINTER
+        D3 = P(C.c_double)
+        L.orc_wave_bilinear.restype = C.c_float
+        L.orc_wave_bilinear.argtypes = [P(_abi.sfh_waves), C.c_float, C.c_float, C.c_uint32]
+        L.orc_wave_height.restype = C.c_float
+        L.orc_wave_height.argtypes = [P(_abi.sfh_waves), C.c_float, C.c_float]
+        L.orc_get_depth.restype = C.c_float
+        L.orc_get_depth.argtypes = [P(_abi.sfh_ocean), P(_abi.sfh_waves), C.c_float, C.c_float, C.c_float]
+        L.orc_current_velocity.restype = None
+        L.orc_current_velocity.argtypes = [P(_abi.sfh_current), D3, D3]
+        L.orc_fluid_velocity_d.restype = None
+        L.orc_fluid_velocity_d.argtypes = [P(_abi.sfh_ocean), D3, D3]
+        L.orc_fluid_velocity_f.restype = None
+        L.orc_fluid_velocity_f.argtypes = [P(_abi.sfh_ocean), P(C.c_float), P(C.c_float)]
+        L.orc_check_body_fluid_position.restype = C.c_uint32
+        L.orc_check_body_fluid_position.argtypes = [P(_abi.sfh_ocean), P(_abi.sfh_waves), D3, D3]
+        L.orc_correct.restype = None
+        L.orc_correct.argtypes = [C.c_double, D3, D3, D3, D3, D3, D3, D3]
+        L.orc_gl_matrix.restype = None
+        L.orc_gl_matrix.argtypes = [D3, P(C.c_float)]
+        for name in ("orc_submerged",):
+            f = getattr(L, name)
+            f.restype = None
+            f.argtypes = [P(orc_mesh), P(_abi.sfh_ocean), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        for name in ("orc_surface", "orc_body"):
+            f = getattr(L, name)
+            f.restype = None
+            f.argtypes = [P(orc_mesh), P(_abi.sfh_ocean), P(_abi.sfh_waves), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_step.restype = C.c_double
+        L.orc_step.argtypes = [P(P(orc_mesh)), P(_abi.sfh_ocean), P(_abi.sfh_waves), C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+        L.orc_body_split.restype = C.c_double
+        L.orc_body_split.argtypes = [P(orc_mesh), P(_abi.sfh_ocean), P(_abi.sfh_waves), C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_selftest_unfused.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def mesh_struct(m: Mesh) -> orc_mesh:
+    return orc_mesh(m.vertex_data.ctypes.data, m.stride_bytes, m.n_verts, m.faces.ctypes.data, m.n_faces)
+
+
+class OracleScene:
+    """Keeps the ctypes views of a scene alive and runs oracle entry points on it."""
+
+    def __init__(self, meshes: list[Mesh], body_mesh, ocean: Ocean, states: np.ndarray):
+        self.meshes = meshes
+        self.body_mesh = np.asarray(body_mesh)
+        self.mstructs = [mesh_struct(m) for m in meshes]
+        self.ocean = ocean
+        self.o = ocean.to_struct()
+        self.w = ocean.waves_struct() if ocean.hasWaves() else _abi.sfh_waves()
+        self.states = np.ascontiguousarray(states)
+        assert self.states.dtype == BODY_STATE_DTYPE
+        arr = (C.POINTER(orc_mesh) * len(self.body_mesh))()
+        for i, mi in enumerate(self.body_mesh):
+            arr[i] = C.pointer(self.mstructs[int(mi)])
+        self.mesh_ptrs = arr
+
+    def body(self, i: int, acc_mode: int = ORC_F64_ACC, codes: bool = False):
+        out = np.zeros(1, dtype=INFO_DTYPE)
+        m = self.meshes[int(self.body_mesh[i])]
+        cbuf = np.zeros(max(m.n_faces, 1), dtype=np.uint8) if codes else None
+        lib().orc_body(C.byref(self.mstructs[int(self.body_mesh[i])]), C.byref(self.o), C.byref(self.w),
+                       self.states[i:i + 1].ctypes.data, acc_mode, out.ctypes.data, cbuf.ctypes.data if codes else None)
+        return (out[0], cbuf[: m.n_faces]) if codes else out[0]
+
+    def step(self, acc_mode: int = ORC_F64_ACC, n_threads: int = 1, first: int = 0, count: int | None = None):
+        n = len(self.body_mesh) - first if count is None else count
+        out = np.zeros(n, dtype=INFO_DTYPE)
+        ptrs = C.cast(C.byref(self.mesh_ptrs, first * C.sizeof(C.c_void_p)), C.POINTER(C.POINTER(orc_mesh)))
+        secs = lib().orc_step(ptrs, C.byref(self.o), C.byref(self.w), self.states[first:first + n].ctypes.data, n, acc_mode,
+                              n_threads, out.ctypes.data)
+        return out, secs
+
+    def body_split(self, i: int, n_threads: int):
+        out = np.zeros(1, dtype=INFO_DTYPE)
+        secs = lib().orc_body_split(C.byref(self.mstructs[int(self.body_mesh[i])]), C.byref(self.o), C.byref(self.w),
+                                    self.states[i:i + 1].ctypes.data, n_threads, out.ctypes.data)
+        return out[0], secs
+
+    def all_codes(self, acc_mode: int = ORC_F64_ACC):
+        infos, codes = [], []
+        for i in range(len(self.body_mesh)):
+            info, c = self.body(i, acc_mode, codes=True)
+            infos.append(info)
+            codes.append(c)
+        return np.array(infos, dtype=INFO_DTYPE), np.concatenate(codes) if codes else np.zeros(0, np.uint8)

@@ -1,0 +1,14 @@
+"""stonefish_b200 — B200 (sm_100a) implementation of Stonefish's per-triangle hydrodynamic force integration.
+
+The product is the C-ABI shared library `libsfh.so` (include/sfh.h, sources in stonefish_b200/csrc). This
+package binds it with ctypes and mirrors the reference's host interface for that path (hydro.py); scenes.py
+and meshes.py hold the synthetic BASELINE inputs. Importing the package does not require a GPU; creating a
+`HydroContext` does, and fails loudly without one — there is no CPU fallback.
+"""
+from . import _abi
+from .hydro import (BODY_STATE_DTYPE, INFO_DTYPE, BodyFluidPosition, HydroContext, HydrodynamicsSettings, Jet, Mesh, Ocean, Pipe,
+                    SfhError, Uniform, VelocityField, make_transform, new_body_states, quat_to_basis, transform_mul)
+
+__all__ = ["_abi", "BODY_STATE_DTYPE", "INFO_DTYPE", "BodyFluidPosition", "HydroContext", "HydrodynamicsSettings", "Jet", "Mesh",
+           "Ocean", "Pipe", "SfhError", "Uniform", "VelocityField", "make_transform", "new_body_states", "quat_to_basis",
+           "transform_mul"]

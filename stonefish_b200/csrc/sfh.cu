@@ -1,0 +1,662 @@
+// sfh.cu — C ABI (include/sfh.h) over the sm_100a kernels in sfh_kernels.cuh.
+// One sfh_ctx = one GPU: stream, pinned staging, device arenas, mesh table. No CPU fallback anywhere:
+// every entry point either enqueues CUDA work or returns an error.
+#include "../../include/sfh.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sfh_kernels.cuh"
+
+using namespace sfh;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+struct Slab {
+    uint8_t* base = nullptr;
+    size_t size = 0, used = 0;
+};
+
+struct HostMesh {
+    MeshDev dev{};
+    sfh_mesh_stats stats{};
+    bool live = false;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0; // elements
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0; // bytes
+};
+
+} // namespace
+
+struct sfh_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int num_sms = 0;
+    std::string err;
+    std::mutex mesh_mutex;
+
+    // static geometry
+    std::vector<Slab> slabs;
+    std::vector<HostMesh> meshes;
+    DevBuf<MeshDev> d_meshes;
+    bool mesh_table_dirty = true;
+    PinBuf h_mesh_table;
+
+    // waves
+    DevBuf<float> d_wave_rgba, d_wave_ch0, d_wave_ch1;
+    PinBuf h_wave;
+    WavesDev waves{nullptr, nullptr, 0, 0.f, 0.f};
+    bool have_waves = false;
+
+    // per-step buffers
+    DevBuf<sfh_body_state> d_states;
+    DevBuf<sfh_info> d_info;
+    DevBuf<BodyDev> d_bodies;
+    DevBuf<uint32_t> d_off_sub, d_off_surf, d_status;
+    DevBuf<PartialSub> d_part_sub;
+    DevBuf<PartialSurf> d_part_surf;
+    DevBuf<OceanDev> d_ocean;
+    DevBuf<uint8_t> d_codes;
+    DevBuf<uint64_t> d_code_base;
+    PinBuf h_ocean, h_states, h_info, h_status, h_codes, h_code_base;
+
+    // pending host-side completion of the last async step
+    sfh_info* pending_out = nullptr;
+    size_t pending_out_bytes = 0;
+    uint8_t* pending_codes = nullptr;
+    size_t pending_codes_bytes = 0;
+    bool step_in_flight = false;
+
+    // occupancy cache: blocks per SM for [kernel variant]
+    int occ_sub[2] = {0, 0};
+    int occ_surf[2][2] = {{0, 0}, {0, 0}};
+
+    // profiling
+    bool profiling = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_sub = false, ev_surf = false, ev_valid = false;
+    uint32_t last_launches = 0;
+    uint64_t last_faces = 0;
+};
+
+namespace {
+
+int fail(sfh_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? SFH_ERR_OOM : SFH_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                         \
+    } while (0)
+
+template <typename T>
+int ensure_dev(sfh_ctx* ctx, DevBuf<T>& b, size_t n)
+{
+    if (n <= b.cap) return SFH_OK;
+    size_t cap = b.cap ? b.cap : 1;
+    while (cap < n) cap *= 2;
+    if (b.p) CU(ctx, cudaFree(b.p)); // stream-ordered users finished: callers sync before growing (see prepare)
+    b.p = nullptr; b.cap = 0;
+    CU(ctx, cudaMalloc(&b.p, cap * sizeof(T)));
+    b.cap = cap;
+    return SFH_OK;
+}
+
+int ensure_pin(sfh_ctx* ctx, PinBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return SFH_OK;
+    size_t cap = b.cap ? b.cap : 256;
+    while (cap < bytes) cap *= 2;
+    if (b.p) CU(ctx, cudaFreeHost(b.p));
+    b.p = nullptr; b.cap = 0;
+    CU(ctx, cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
+    b.cap = cap;
+    return SFH_OK;
+}
+
+bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int arena_alloc(sfh_ctx* ctx, size_t bytes, uint8_t** out)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    for (auto& s : ctx->slabs)
+        if (s.size - s.used >= bytes) { *out = s.base + s.used; s.used += bytes; return SFH_OK; }
+    Slab s;
+    s.size = bytes > ((size_t)256 << 20) ? bytes : ((size_t)256 << 20);
+    cudaError_t e = cudaMalloc(&s.base, s.size);
+    if (e != cudaSuccess && s.size > bytes) { cudaGetLastError(); s.size = bytes; e = cudaMalloc(&s.base, s.size); }
+    if (e != cudaSuccess) return fail(ctx, SFH_ERR_OOM, "cudaMalloc(%zu) for mesh arena: %s", s.size, cudaGetErrorString(e));
+    s.used = bytes;
+    *out = s.base;
+    ctx->slabs.push_back(s);
+    return SFH_OK;
+}
+
+template <typename K>
+int occupancy(sfh_ctx* ctx, K kernel, int* cache)
+{
+    if (*cache == 0) {
+        int n = 0;
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, SFH_BLOCK, 0));
+        *cache = n > 0 ? n : 1;
+    }
+    return SFH_OK;
+}
+
+// Fill the device ocean record (pinned staging -> device) and report which kernel variants the step needs.
+int stage_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
+{
+    if (o->n_currents > SFH_MAX_CURRENTS) return fail(ctx, SFH_ERR_INVALID, "n_currents %u > %u", o->n_currents, SFH_MAX_CURRENTS);
+    if (o->has_waves && !ctx->have_waves) return fail(ctx, SFH_ERR_STATE, "ocean.has_waves set but sfh_waves_upload was never called");
+    int rc;
+    if ((rc = ensure_pin(ctx, ctx->h_ocean, sizeof(OceanDev))) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_ocean, 1)) != SFH_OK) return rc;
+    OceanDev* h = static_cast<OceanDev*>(ctx->h_ocean.p);
+    h->density = o->density;
+    h->gravity_z = o->gravity_z;
+    h->has_waves = o->has_waves ? 1u : 0u;
+    h->currents_enabled = o->currents_enabled ? 1u : 0u;
+    h->n_currents = o->n_currents;
+    bool general = false;
+    for (uint32_t i = 0; i < o->n_currents; ++i) {
+        h->currents[i] = o->currents[i];
+        if (o->currents[i].type > SFH_CURRENT_PIPE) return fail(ctx, SFH_ERR_INVALID, "current %u: unknown type %u", i, o->currents[i].type);
+        if (o->currents_enabled && o->currents[i].enabled && o->currents[i].type != SFH_CURRENT_UNIFORM) general = true;
+    }
+    h->cur_general = general ? 1u : 0u;
+    *cur_general = general;
+    const size_t bytes = offsetof(OceanDev, currents) + sizeof(sfh_current) * (o->n_currents ? o->n_currents : 1);
+    CU(ctx, cudaMemcpyAsync(ctx->d_ocean.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SFH_OK;
+}
+
+int sync_mesh_table(sfh_ctx* ctx)
+{
+    std::lock_guard<std::mutex> lock(ctx->mesh_mutex);
+    if (!ctx->mesh_table_dirty) return SFH_OK;
+    const size_t n = ctx->meshes.size() ? ctx->meshes.size() : 1;
+    int rc;
+    if (n > ctx->d_meshes.cap) CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensure_dev(ctx, ctx->d_meshes, n)) != SFH_OK) return rc;
+    if (n * sizeof(MeshDev) > ctx->h_mesh_table.cap) CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensure_pin(ctx, ctx->h_mesh_table, n * sizeof(MeshDev))) != SFH_OK) return rc;
+    MeshDev* h = static_cast<MeshDev*>(ctx->h_mesh_table.p);
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); // previous async copy from this staging buffer is done
+    for (size_t i = 0; i < ctx->meshes.size(); ++i) h[i] = ctx->meshes[i].live ? ctx->meshes[i].dev : MeshDev{nullptr, nullptr, 0, 0};
+    CU(ctx, cudaMemcpyAsync(ctx->d_meshes.p, h, ctx->meshes.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->mesh_table_dirty = false;
+    return SFH_OK;
+}
+
+struct StepPlan {
+    bool host_states = true;     // states/out are host pointers
+    bool debug = false;
+    bool may_sub = true, may_surf = true; // host knows no body can reach the kernel -> skip the launch
+    uint64_t chunks_ub = 0;      // upper bound of work items (host variant), 0 = unknown
+    uint64_t faces = 0;
+};
+
+template <int CUR, bool DEBUG>
+void launch_sub(const StepParams& P, int grid, cudaStream_t s) { k_submerged<CUR, DEBUG><<<grid, SFH_BLOCK, 0, s>>>(P); }
+template <bool WAVES, int CUR, bool DEBUG>
+void launch_surf(const StepParams& P, int grid, cudaStream_t s) { k_surface<WAVES, CUR, DEBUG><<<grid, SFH_BLOCK, 0, s>>>(P); }
+
+int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n, sfh_info* d_out, const StepPlan& plan)
+{
+    int rc;
+    bool general = false;
+    if ((rc = stage_ocean(ctx, ocean, &general)) != SFH_OK) return rc;
+    if ((rc = sync_mesh_table(ctx)) != SFH_OK) return rc;
+    const bool waves = ocean->has_waves != 0;
+
+    // persistent grids
+    if (general) { if ((rc = occupancy(ctx, k_submerged<1, false>, &ctx->occ_sub[1])) != SFH_OK) return rc; }
+    else         { if ((rc = occupancy(ctx, k_submerged<0, false>, &ctx->occ_sub[0])) != SFH_OK) return rc; }
+    int* occs = &ctx->occ_surf[waves ? 1 : 0][general ? 1 : 0];
+    if (waves) {
+        if (general) rc = occupancy(ctx, k_surface<true, 1, false>, occs); else rc = occupancy(ctx, k_surface<true, 0, false>, occs);
+    } else {
+        if (general) rc = occupancy(ctx, k_surface<false, 1, false>, occs); else rc = occupancy(ctx, k_surface<false, 0, false>, occs);
+    }
+    if (rc != SFH_OK) return rc;
+    uint64_t g_sub = (uint64_t)ctx->num_sms * (uint64_t)ctx->occ_sub[general ? 1 : 0];
+    uint64_t g_surf = (uint64_t)ctx->num_sms * (uint64_t)*occs;
+    if (plan.chunks_ub) {
+        if (g_sub > plan.chunks_ub) g_sub = plan.chunks_ub;
+        if (g_surf > plan.chunks_ub) g_surf = plan.chunks_ub;
+    }
+
+    // buffers (growing them requires the stream to be idle: older kernels may still read the old ones)
+    const bool grow = n > ctx->d_bodies.cap || n + 1 > ctx->d_off_sub.cap || g_sub + n > ctx->d_part_sub.cap || g_surf + n > ctx->d_part_surf.cap;
+    if (grow) CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensure_dev(ctx, ctx->d_bodies, n)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_off_sub, n + 1)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_off_surf, n + 1)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_part_sub, g_sub + n)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_part_surf, g_surf + n)) != SFH_OK) return rc;
+    if (!ctx->d_status.p) {
+        if ((rc = ensure_dev(ctx, ctx->d_status, 4)) != SFH_OK) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->d_status.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+    }
+
+    const bool prof = ctx->profiling;
+    if (prof) CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    PrologueParams pp;
+    pp.states = d_states; pp.meshes = ctx->d_meshes.p; pp.n_meshes = (uint32_t)ctx->meshes.size(); pp.n_bodies = n;
+    pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;
+    pp.off_sub = ctx->d_off_sub.p; pp.off_surf = ctx->d_off_surf.p; pp.status = ctx->d_status.p;
+    k_prologue<<<1, 1024, 0, ctx->stream>>>(pp);
+    uint32_t launches = 1;
+    if (prof) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    StepParams sp;
+    sp.bodies = ctx->d_bodies.p; sp.n_bodies = n; sp.ocean = ctx->d_ocean.p; sp.waves = ctx->waves;
+    sp.codes = plan.debug ? ctx->d_codes.p : nullptr; sp.code_base = plan.debug ? ctx->d_code_base.p : nullptr;
+
+    ctx->ev_sub = ctx->ev_surf = false;
+    if (plan.may_sub && g_sub > 0) {
+        sp.item_off = ctx->d_off_sub.p; sp.partials = ctx->d_part_sub.p;
+        if (plan.debug) { if (general) launch_sub<1, true>(sp, (int)g_sub, ctx->stream); else launch_sub<0, true>(sp, (int)g_sub, ctx->stream); }
+        else            { if (general) launch_sub<1, false>(sp, (int)g_sub, ctx->stream); else launch_sub<0, false>(sp, (int)g_sub, ctx->stream); }
+        ++launches;
+        ctx->ev_sub = true;
+    }
+    if (prof) CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (plan.may_surf && g_surf > 0) {
+        sp.item_off = ctx->d_off_surf.p; sp.partials = ctx->d_part_surf.p;
+        const int g = (int)g_surf;
+        if (plan.debug) {
+            if (waves) { if (general) launch_surf<true, 1, true>(sp, g, ctx->stream); else launch_surf<true, 0, true>(sp, g, ctx->stream); }
+            else       { if (general) launch_surf<false, 1, true>(sp, g, ctx->stream); else launch_surf<false, 0, true>(sp, g, ctx->stream); }
+        } else {
+            if (waves) { if (general) launch_surf<true, 1, false>(sp, g, ctx->stream); else launch_surf<true, 0, false>(sp, g, ctx->stream); }
+            else       { if (general) launch_surf<false, 1, false>(sp, g, ctx->stream); else launch_surf<false, 0, false>(sp, g, ctx->stream); }
+        }
+        ++launches;
+        ctx->ev_surf = true;
+    }
+    if (prof) CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+
+    EpilogueParams ep;
+    ep.states = d_states; ep.bodies = ctx->d_bodies.p; ep.n_bodies = n; ep.ocean = ctx->d_ocean.p;
+    ep.off_sub = ctx->d_off_sub.p; ep.off_surf = ctx->d_off_surf.p;
+    ep.part_sub = ctx->d_part_sub.p; ep.part_surf = ctx->d_part_surf.p;
+    ep.grid_sub = (uint32_t)g_sub; ep.grid_surf = (uint32_t)g_surf; ep.out = d_out;
+    k_epilogue<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ep);
+    ++launches;
+    if (prof) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    CU(ctx, cudaGetLastError());
+    ctx->last_launches = launches;
+    ctx->last_faces = plan.faces;
+    return SFH_OK;
+}
+
+int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n, sfh_info* out, uint8_t* codes,
+              size_t codes_bytes, bool debug)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!ocean || (!states && n) || (!out && n)) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    if (ctx->step_in_flight) { int rc = sfh_sync(ctx); if (rc != SFH_OK) return rc; }
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return SFH_OK;
+    int rc;
+
+    // host-side validation and work bound (the mesh table is host-visible)
+    StepPlan plan;
+    plan.debug = debug;
+    plan.may_sub = plan.may_surf = false;
+    std::vector<uint64_t> code_base;
+    if (debug) code_base.resize(n);
+    uint64_t total_codes = 0;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mesh_mutex);
+        for (uint32_t i = 0; i < n; ++i) {
+            const sfh_body_state& s = states[i];
+            if (s.mode > SFH_POS_AUTO) return fail(ctx, SFH_ERR_INVALID, "body %u: bad mode %u", i, s.mode);
+            if (s.mesh_id >= ctx->meshes.size() || !ctx->meshes[s.mesh_id].live)
+                return fail(ctx, SFH_ERR_INVALID, "body %u: unknown mesh id %u", i, s.mesh_id);
+            const HostMesh& m = ctx->meshes[s.mesh_id];
+            if (debug) { code_base[i] = total_codes; total_codes += m.stats.n_faces; }
+            if (s.mode == SFH_POS_OUTSIDE) continue;
+            plan.chunks_ub += m.stats.n_chunks;
+            if (s.mode != SFH_POS_CROSSING) plan.may_sub = true;
+            if (s.mode != SFH_POS_INSIDE) plan.may_surf = true;
+            plan.faces += m.stats.n_faces; // AUTO bodies that turn out OUTSIDE are subtracted by callers via info.n_faces
+        }
+    }
+    if (plan.chunks_ub == 0) plan.chunks_ub = 1;
+    if (debug && codes_bytes < total_codes) return fail(ctx, SFH_ERR_INVALID, "face_codes buffer too small: %zu < %llu", codes_bytes, (unsigned long long)total_codes);
+
+    const bool grow = n > ctx->d_states.cap || n > ctx->d_info.cap;
+    if (grow) CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensure_dev(ctx, ctx->d_states, n)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_info, n)) != SFH_OK) return rc;
+
+    if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    const size_t sbytes = (size_t)n * sizeof(sfh_body_state);
+    const void* src = states;
+    if (!is_pinned_host(states)) {
+        if ((rc = ensure_pin(ctx, ctx->h_states, sbytes)) != SFH_OK) return rc;
+        std::memcpy(ctx->h_states.p, states, sbytes);
+        src = ctx->h_states.p;
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->d_states.p, src, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+
+    if (debug) {
+        if ((rc = ensure_dev(ctx, ctx->d_codes, total_codes ? total_codes : 1)) != SFH_OK) return rc;
+        if ((rc = ensure_dev(ctx, ctx->d_code_base, n)) != SFH_OK) return rc;
+        if ((rc = ensure_pin(ctx, ctx->h_code_base, n * sizeof(uint64_t))) != SFH_OK) return rc;
+        std::memcpy(ctx->h_code_base.p, code_base.data(), n * sizeof(uint64_t));
+        CU(ctx, cudaMemcpyAsync(ctx->d_code_base.p, ctx->h_code_base.p, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->d_codes.p, 0, total_codes ? total_codes : 1, ctx->stream));
+    }
+
+    if ((rc = run_step(ctx, ocean, ctx->d_states.p, n, ctx->d_info.p, plan)) != SFH_OK) return rc;
+
+    const size_t obytes = (size_t)n * sizeof(sfh_info);
+    ctx->pending_out = nullptr;
+    if (is_pinned_host(out)) {
+        CU(ctx, cudaMemcpyAsync(out, ctx->d_info.p, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        if ((rc = ensure_pin(ctx, ctx->h_info, obytes)) != SFH_OK) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->h_info.p, ctx->d_info.p, obytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->pending_out = out;
+        ctx->pending_out_bytes = obytes;
+    }
+    ctx->pending_codes = nullptr;
+    if (debug && total_codes) {
+        if ((rc = ensure_pin(ctx, ctx->h_codes, total_codes)) != SFH_OK) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->h_codes.p, ctx->d_codes.p, total_codes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->pending_codes = codes;
+        ctx->pending_codes_bytes = total_codes;
+    }
+    if ((rc = ensure_pin(ctx, ctx->h_status, 16)) != SFH_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->step_in_flight = true;
+    ctx->ev_valid = ctx->profiling;
+    return SFH_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sfh_abi_version(void) { return SFH_ABI_VERSION; }
+
+int sfh_create_on_stream(int cuda_device, void* cuda_stream, sfh_ctx** out)
+{
+    if (!out) return fail(nullptr, SFH_ERR_INVALID, "out == NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SFH_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (cuda_device < 0 || cuda_device >= count) return fail(nullptr, SFH_ERR_INVALID, "cuda_device %d out of range [0,%d)", cuda_device, count);
+    sfh_ctx* ctx = new sfh_ctx();
+    ctx->device = cuda_device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        fail(nullptr, SFH_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        delete ctx;
+        return SFH_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(cuda_device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cuda_device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        fail(nullptr, SFH_ERR_NO_DEVICE, "device %d is sm_%d%d; this library ships sm_100a code only", cuda_device, prop.major, prop.minor);
+        delete ctx;
+        return SFH_ERR_NO_DEVICE;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cuda_stream) {
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+        ctx->own_stream = false;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    }
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    *out = ctx;
+    return SFH_OK;
+}
+
+int sfh_create(int cuda_device, sfh_ctx** out) { return sfh_create_on_stream(cuda_device, nullptr, out); }
+
+void sfh_destroy(sfh_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->slabs) cudaFree(s.base);
+    cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_wave_rgba.p); cudaFree(ctx->d_wave_ch0.p); cudaFree(ctx->d_wave_ch1.p);
+    cudaFree(ctx->d_states.p); cudaFree(ctx->d_info.p); cudaFree(ctx->d_bodies.p); cudaFree(ctx->d_off_sub.p);
+    cudaFree(ctx->d_off_surf.p); cudaFree(ctx->d_status.p); cudaFree(ctx->d_part_sub.p); cudaFree(ctx->d_part_surf.p);
+    cudaFree(ctx->d_ocean.p); cudaFree(ctx->d_codes.p); cudaFree(ctx->d_code_base.p);
+    for (PinBuf* b : {&ctx->h_mesh_table, &ctx->h_wave, &ctx->h_ocean, &ctx->h_states, &ctx->h_info, &ctx->h_status, &ctx->h_codes, &ctx->h_code_base})
+        if (b->p) cudaFreeHost(b->p);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sfh_last_error(const sfh_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sfh_mesh_upload(sfh_ctx* ctx, const void* pos, size_t stride_bytes, uint32_t n_verts, const uint32_t* faces, uint32_t n_faces,
+                    uint32_t flags, uint32_t* mesh_id_out)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!mesh_id_out || (n_verts && !pos) || (n_faces && !faces)) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    if (stride_bytes < 12 || (stride_bytes & 3)) return fail(ctx, SFH_ERR_INVALID, "vertex stride %zu must be >= 12 and a multiple of 4", stride_bytes);
+    ChunkedMesh cm; // heavy part outside the lock: callers may upload from several threads
+    if (!chunk_mesh(pos, stride_bytes, n_verts, faces, n_faces, (flags & SFH_MESH_KEEP_ORDER) != 0, cm))
+        return fail(ctx, SFH_ERR_INVALID, "a face references a vertex id >= n_verts (%u)", n_verts);
+
+    std::lock_guard<std::mutex> lock(ctx->mesh_mutex);
+    CU(ctx, cudaSetDevice(ctx->device));
+    HostMesh hm;
+    hm.stats.n_faces = n_faces; hm.stats.n_verts = n_verts; hm.stats.n_chunks = cm.n_chunks; hm.stats.n_chunk_verts = cm.n_chunk_verts;
+    hm.stats.device_bytes = cm.device_bytes;
+    hm.stats.algorithmic_bytes = 12ull * n_faces + 12ull * n_verts;
+    hm.dev.n_chunks = cm.n_chunks; hm.dev.n_faces = n_faces;
+    if (cm.n_chunks) {
+        uint8_t *d_chunks = nullptr, *d_orig = nullptr;
+        int rc;
+        if ((rc = arena_alloc(ctx, cm.chunks.size(), &d_chunks)) != SFH_OK) return rc;
+        if ((rc = arena_alloc(ctx, cm.orig_face.size() * sizeof(uint32_t), &d_orig)) != SFH_OK) return rc;
+        CU(ctx, cudaMemcpy(d_chunks, cm.chunks.data(), cm.chunks.size(), cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(d_orig, cm.orig_face.data(), cm.orig_face.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        hm.dev.chunks = d_chunks;
+        hm.dev.orig_face = reinterpret_cast<const uint32_t*>(d_orig);
+    }
+    hm.live = true;
+    ctx->meshes.push_back(hm);
+    ctx->mesh_table_dirty = true;
+    *mesh_id_out = (uint32_t)(ctx->meshes.size() - 1);
+    return SFH_OK;
+}
+
+int sfh_mesh_release(sfh_ctx* ctx, uint32_t mesh_id)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mesh_mutex);
+    if (mesh_id >= ctx->meshes.size() || !ctx->meshes[mesh_id].live) return fail(ctx, SFH_ERR_INVALID, "unknown mesh id %u", mesh_id);
+    ctx->meshes[mesh_id].live = false; // arena memory is reclaimed when the context is destroyed
+    ctx->mesh_table_dirty = true;
+    return SFH_OK;
+}
+
+int sfh_mesh_get_stats(sfh_ctx* ctx, uint32_t mesh_id, sfh_mesh_stats* out)
+{
+    if (!ctx || !out) return SFH_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mesh_mutex);
+    if (mesh_id >= ctx->meshes.size() || !ctx->meshes[mesh_id].live) return fail(ctx, SFH_ERR_INVALID, "unknown mesh id %u", mesh_id);
+    *out = ctx->meshes[mesh_id].stats;
+    return SFH_OK;
+}
+
+int sfh_waves_upload(sfh_ctx* ctx, const sfh_waves* w)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!w || !w->data) return fail(ctx, SFH_ERR_INVALID, "null waves");
+    if (w->fft_size < 2 || w->fft_size > 4096) return fail(ctx, SFH_ERR_INVALID, "fft_size %d out of range", w->fft_size);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)w->fft_size;
+    const size_t texels = N * N + N + 1; // what OpenGLRealOcean.cpp:289-311 can index with i,j in [0,N]
+    const size_t want = texels * 4;
+    const size_t have = w->n_floats < want ? w->n_floats : want;
+    int rc;
+    const bool grow = want > ctx->d_wave_rgba.cap || texels > ctx->d_wave_ch0.cap || want * 4 > ctx->h_wave.cap;
+    if (grow || ctx->have_waves) CU(ctx, cudaStreamSynchronize(ctx->stream)); // staging buffer reuse
+    if ((rc = ensure_dev(ctx, ctx->d_wave_rgba, want)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_wave_ch0, texels)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_wave_ch1, texels)) != SFH_OK) return rc;
+    const void* src = w->data;
+    if (!is_pinned_host(w->data)) {
+        if ((rc = ensure_pin(ctx, ctx->h_wave, want * sizeof(float))) != SFH_OK) return rc;
+        std::memcpy(ctx->h_wave.p, w->data, have * sizeof(float));
+        src = ctx->h_wave.p;
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->d_wave_rgba.p, src, have * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_waves_planar<<<(unsigned)((texels + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_wave_rgba.p, (uint32_t)have, (uint32_t)texels,
+                                                                               ctx->d_wave_ch0.p, ctx->d_wave_ch1.p);
+    CU(ctx, cudaGetLastError());
+    ctx->waves.ch0 = ctx->d_wave_ch0.p;
+    ctx->waves.ch1 = ctx->d_wave_ch1.p;
+    ctx->waves.N = w->fft_size;
+    ctx->waves.gx = w->grid_sizes[0];
+    ctx->waves.gy = w->grid_sizes[1];
+    ctx->have_waves = true;
+    return SFH_OK;
+}
+
+int sfh_step_async(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n_bodies, sfh_info* out)
+{
+    return step_host(ctx, ocean, states, n_bodies, out, nullptr, 0, false);
+}
+
+int sfh_sync(sfh_ctx* ctx)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->step_in_flight) {
+        ctx->step_in_flight = false;
+        if (ctx->pending_out) std::memcpy(ctx->pending_out, ctx->h_info.p, ctx->pending_out_bytes);
+        if (ctx->pending_codes) std::memcpy(ctx->pending_codes, ctx->h_codes.p, ctx->pending_codes_bytes);
+        ctx->pending_out = nullptr;
+        ctx->pending_codes = nullptr;
+        if (ctx->h_status.p && *static_cast<uint32_t*>(ctx->h_status.p) != 0) {
+            cudaMemsetAsync(ctx->d_status.p, 0, 4 * sizeof(uint32_t), ctx->stream);
+            return fail(ctx, SFH_ERR_INVALID, "a body referenced an unknown mesh id");
+        }
+    }
+    return SFH_OK;
+}
+
+int sfh_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n_bodies, sfh_info* out)
+{
+    int rc = sfh_step_async(ctx, ocean, states, n_bodies, out);
+    if (rc != SFH_OK) return rc;
+    return sfh_sync(ctx);
+}
+
+int sfh_step_debug(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n_bodies, sfh_info* out,
+                   uint8_t* face_codes, size_t face_codes_bytes)
+{
+    if (!face_codes) return fail(ctx, SFH_ERR_INVALID, "face_codes == NULL");
+    int rc = step_host(ctx, ocean, states, n_bodies, out, face_codes, face_codes_bytes, true);
+    if (rc != SFH_OK) return rc;
+    return sfh_sync(ctx);
+}
+
+int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies, sfh_info* d_out)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!ocean || (!d_states && n_bodies) || (!d_out && n_bodies)) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n_bodies == 0) return SFH_OK;
+    StepPlan plan;
+    plan.host_states = false;
+    if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = run_step(ctx, ocean, d_states, n_bodies, d_out, plan);
+    if (rc != SFH_OK) return rc;
+    ctx->ev_valid = ctx->profiling;
+    return SFH_OK;
+}
+
+int sfh_host_alloc(sfh_ctx* ctx, size_t bytes, void** out)
+{
+    if (!ctx || !out) return SFH_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SFH_OK;
+}
+
+int sfh_host_free(sfh_ctx* ctx, void* p)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (p) CU(ctx, cudaFreeHost(p));
+    return SFH_OK;
+}
+
+int sfh_set_profiling(sfh_ctx* ctx, int enabled)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    ctx->profiling = enabled != 0;
+    ctx->ev_valid = false;
+    return SFH_OK;
+}
+
+int sfh_get_timings(sfh_ctx* ctx, sfh_timings* out)
+{
+    if (!ctx || !out) return SFH_ERR_INVALID;
+    std::memset(out, 0, sizeof(*out));
+    if (!ctx->ev_valid) return fail(ctx, SFH_ERR_STATE, "no profiled step: call sfh_set_profiling(ctx,1) before the step");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventSynchronize(ctx->ev[5]));
+    CU(ctx, cudaEventElapsedTime(&out->prologue_ms, ctx->ev[1], ctx->ev[2]));
+    if (ctx->ev_sub) CU(ctx, cudaEventElapsedTime(&out->submerged_ms, ctx->ev[2], ctx->ev[3]));
+    if (ctx->ev_surf) CU(ctx, cudaEventElapsedTime(&out->surface_ms, ctx->ev[3], ctx->ev[4]));
+    CU(ctx, cudaEventElapsedTime(&out->epilogue_ms, ctx->ev[4], ctx->ev[5]));
+    CU(ctx, cudaEventElapsedTime(&out->total_ms, ctx->ev[0], ctx->ev[5]));
+    out->launches = ctx->last_launches;
+    out->faces = ctx->last_faces;
+    return SFH_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,231 @@
+// sfh_device.cuh — device-side arithmetic of the hydrodynamics hot path (sm_100a).
+//
+// Every fp32/fp64 operation that feeds a branch or a sum goes through an explicit round-to-nearest
+// intrinsic (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn, __dmul_rn, ...): nvcc never contracts those
+// into FMAs, so the per-face terms are bit-identical to the reference's x86-64 build, which has no FMA
+// in its baseline ISA (hard part 1). Denormals are kept (no -ftz).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/sfh_types.h"
+#include "mesh_chunker.hpp"
+
+namespace sfh {
+
+// ---------------------------------------------------------------------------------------------
+// device-side data
+// ---------------------------------------------------------------------------------------------
+struct MeshDev {
+    const uint8_t* chunks;     // n_chunks * SFH_CH_BYTES
+    const uint32_t* orig_face; // n_chunks * SFH_CH_FACES (debug only)
+    uint32_t n_chunks;
+    uint32_t n_faces;
+};
+
+enum { KIND_NONE = 0, KIND_SUBMERGED = 1, KIND_SURFACE = 2 };
+enum { BF_DAMPING = 1u, BF_BUOYANCY = 2u };
+
+// Per-body record prepared by the prologue kernel; everything the per-face kernels need, already narrowed to
+// fp32 exactly like SolidEntity.cpp:1325-1334 / 1740-1746 (glMatrixFromTransform, glVectorFromVector).
+struct BodyDev {
+    float R[9];      // T_C basis, row-major: world = (R[0]*x + R[1]*y) + (R[2]*z + t[0]) ...
+    float t[3];      // T_C origin
+    float p[3];      // T_CG origin (torque reference point)
+    float v[3];
+    float omega[3];
+    float cur[3];    // Ocean::GetFluidVelocity result when it is position independent (no Jet/Pipe enabled)
+    uint32_t flags;  // BF_*
+    uint32_t kind;   // KIND_*
+    uint32_t n_chunks;
+    uint32_t pad;
+    const uint8_t* chunks;
+    const uint32_t* orig_face;
+};
+
+// Ocean parameters staged on the device once per step.
+struct OceanDev {
+    double density, gravity_z;
+    uint32_t has_waves, currents_enabled, n_currents, cur_general; // cur_general: some enabled current is Jet/Pipe
+    sfh_current currents[SFH_MAX_CURRENTS];
+};
+
+struct WavesDev {
+    const float* ch0; // planar copy of fftData channel 0 (grid 893 m), index j*N+i, N*N+N+1 entries
+    const float* ch1; // channel 1 (grid 101 m)
+    int32_t N;
+    float gx, gy;     // gridSizes.x, gridSizes.y
+};
+
+// Partial sums written by one thread block for one body.
+#define SFH_NACC_SUB 12
+#define SFH_NACC_SURF 23
+struct PartialSub {
+    double a[SFH_NACC_SUB]; // Fdq[3] Tdq[3] Fdf[3] Tdf[3]
+    uint32_t n_degenerate, n_quadratic, n_skin, pad;
+};
+struct PartialSurf {
+    double a[SFH_NACC_SURF]; // Fdq Tdq Fdf Tdf | Fb[3] Tb[3] | Swet Vsub | CBsub[3]
+    double pad0;
+    uint32_t cls[8];
+    uint32_t n_degenerate, n_quadratic, n_skin, pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// fp32 chain: glm::vec3 semantics, one rounding per operator, nothing fused
+// ---------------------------------------------------------------------------------------------
+struct F3 {
+    float x, y, z;
+};
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return {fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z)}; }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return {fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)}; }
+__device__ __forceinline__ F3 operator-(F3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return {fmul(a.x, s), fmul(a.y, s), fmul(a.z, s)}; }
+__device__ __forceinline__ F3 operator/(F3 a, float s) { return {fdiv(a.x, s), fdiv(a.y, s), fdiv(a.z, s)}; }
+__device__ __forceinline__ float dot(F3 a, F3 b) { return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z)); }
+__device__ __forceinline__ float length2(F3 a) { return dot(a, a); }
+__device__ __forceinline__ F3 cross(F3 x, F3 y)
+{
+    return {fsub(fmul(x.y, y.z), fmul(y.y, x.z)), fsub(fmul(x.z, y.x), fmul(y.z, x.x)), fsub(fmul(x.x, y.y), fmul(y.x, x.y))};
+}
+
+// glm::vec3(TC * glm::vec4(p, 1.f)) = (m0*x + m1*y) + (m2*z + m3*1)
+__device__ __forceinline__ F3 xform(const float* R, const float* t, float x, float y, float z)
+{
+    F3 r;
+    r.x = fadd(fadd(fmul(R[0], x), fmul(R[1], y)), fadd(fmul(R[2], z), t[0]));
+    r.y = fadd(fadd(fmul(R[3], x), fmul(R[4], y)), fadd(fmul(R[5], z), t[1]));
+    r.z = fadd(fadd(fmul(R[6], x), fmul(R[7], y)), fadd(fmul(R[8], z), t[2]));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 pieces: Bullet btVector3 operator order (3rdparty/LinearMath/btVector3.h), unfused
+// ---------------------------------------------------------------------------------------------
+struct D3 {
+    double x, y, z;
+};
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {dsub(a.x, b.x), dsub(a.y, b.y), dsub(a.z, b.z)}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {dadd(a.x, b.x), dadd(a.y, b.y), dadd(a.z, b.z)}; }
+__device__ __forceinline__ D3 operator*(D3 v, double s) { return {dmul(v.x, s), dmul(v.y, s), dmul(v.z, s)}; }
+__device__ __forceinline__ double ddot(D3 a, D3 b) { return dadd(dadd(dmul(a.x, b.x), dmul(a.y, b.y)), dmul(a.z, b.z)); }
+__device__ __forceinline__ D3 dcross(D3 a, D3 v)
+{
+    return {dsub(dmul(a.y, v.z), dmul(a.z, v.y)), dsub(dmul(a.z, v.x), dmul(a.x, v.z)), dsub(dmul(a.x, v.y), dmul(a.y, v.x))};
+}
+__device__ __forceinline__ double dnorm(D3 a) { return __dsqrt_rn(ddot(a, a)); }
+
+// Uniform/Jet/Pipe::GetVelocityAtPoint (Uniform.cpp:54-57, Jet.cpp:54-75, Pipe.cpp:57-78).
+// exp/pow are CUDA's (<= 1-2 ulp) where the reference calls glibc's: see DESIGN.md "fp64 transcendentals".
+__device__ __forceinline__ D3 current_velocity(const sfh_current& c, D3 p)
+{
+    D3 r = {0.0, 0.0, 0.0};
+    if (c.type == SFH_CURRENT_UNIFORM) {
+        r = D3{c.a[0], c.a[1], c.a[2]};
+    } else if (c.type == SFH_CURRENT_JET) {
+        D3 cc = {c.a[0], c.a[1], c.a[2]}, n = {c.n[0], c.n[1], c.n[2]};
+        const double rr = c.r1, vout = c.vel;
+        D3 cp = p - cc;
+        double d = dnorm(dcross(cp, n));
+        double t = ddot(cp, n);
+        if (!(t < 0.0)) {
+            double spread = dadd(t, dmul(5.0, rr));
+            double r_ = dmul(0.2, spread); // Scalar(1)/Scalar(5) folds to the double nearest 0.2
+            if (!(d >= r_)) {
+                double s = dmul(ddiv(dmul(10.0, rr), spread), vout);
+                D3 vmax = n * s;
+                double f = exp(ddiv(dmul(dmul(-50.0, d), d), dmul(t, t)));
+                r = vmax * f;
+            }
+        }
+    } else {
+        D3 p1 = {c.a[0], c.a[1], c.a[2]}, n = {c.n[0], c.n[1], c.n[2]};
+        const double l = c.l, r1 = c.r1, r2 = c.r2, vin = c.vel, gamma = c.gamma;
+        D3 p1p = p - p1;
+        double d = dnorm(dcross(p1p, n));
+        double t = ddot(p1p, n);
+        if (!(t < 0.0 || t > l)) {
+            double rad = dadd(r1, ddiv(dmul(dsub(r2, r1), t), l));
+            if (!(d >= rad)) {
+                D3 v = n * dmul(ddiv(r1, rad), vin);
+                double f = pow(dsub(1.0, ddiv(d, rad)), gamma);
+                r = v * f;
+            }
+        }
+    }
+    return r;
+}
+
+// Ocean::GetFluidVelocity(glm::vec3) (Ocean.cpp:183-201): widen, sum enabled currents in list order, narrow.
+__device__ __forceinline__ F3 fluid_velocity_general(const sfh_current* cur, uint32_t n_cur, F3 fc)
+{
+    D3 p = {(double)fc.x, (double)fc.y, (double)fc.z};
+    D3 fv = {0.0, 0.0, 0.0};
+    for (uint32_t i = 0; i < n_cur; ++i)
+        if (cur[i].enabled) fv = fv + current_velocity(cur[i], p);
+    return F3{(float)fv.x, (float)fv.y, (float)fv.z};
+}
+
+// OpenGLRealOcean::ComputeInterpolatedWaveData (OpenGLRealOcean.cpp:280-319) on a planar channel copy.
+__device__ __forceinline__ float wave_bilinear(const float* __restrict__ ch, int N, float x, float y)
+{
+    const float fN = (float)N;
+    const float half = fdiv(0.5f, fN);
+    float tmp;
+    float i0f = modff(fsub(x, half), &tmp);
+    float j0f = modff(fsub(y, half), &tmp);
+    if (i0f < 0.f) i0f = fsub(1.f, fabsf(i0f));
+    if (j0f < 0.f) j0f = fsub(1.f, fabsf(j0f));
+    int i0 = (int)truncf(fmul(i0f, fN));
+    int j0 = (int)truncf(fmul(j0f, fN));
+    float i1f = modff(fadd(x, half), &tmp);
+    float j1f = modff(fadd(y, half), &tmp);
+    if (i1f < 0.f) i1f = fsub(1.f, fabsf(i1f));
+    if (j1f < 0.f) j1f = fsub(1.f, fabsf(j1f));
+    int i1 = (int)truncf(fmul(i1f, fN));
+    int j1 = (int)truncf(fmul(j1f, fN));
+    float alpha = modff(fmul(i0f, fN), &tmp);
+    float beta = modff(fmul(j0f, fN), &tmp);
+    // Indices stay within [0, N*N+N] for finite inputs (i,j in [0,N]); clamp only guards NaN/Inf coordinates,
+    // where the reference's (int) cast is undefined behaviour.
+    const int lim = N * N + N;
+    int k00 = j0 * N + i0, k01 = j0 * N + i1, k10 = j1 * N + i0, k11 = j1 * N + i1;
+    k00 = min(max(k00, 0), lim); k01 = min(max(k01, 0), lim); k10 = min(max(k10, 0), lim); k11 = min(max(k11, 0), lim);
+    const float t0 = __ldg(ch + k00), t1 = __ldg(ch + k01), t2 = __ldg(ch + k10), t3 = __ldg(ch + k11);
+    const float oma = fsub(1.f, alpha), omb = fsub(1.f, beta);
+    float h = fmul(fmul(oma, omb), t0);
+    h = fadd(h, fmul(fmul(alpha, omb), t1));
+    h = fadd(h, fmul(fmul(oma, beta), t2));
+    h = fadd(h, fmul(fmul(alpha, beta), t3));
+    return h;
+}
+
+// OpenGLRealOcean::ComputeWaveHeight (OpenGLRealOcean.cpp:321-331)
+__device__ __forceinline__ float wave_height(const WavesDev& w, float x, float y)
+{
+    float z = 0.f;
+    z = fsub(z, wave_bilinear(w.ch0, w.N, fdiv(x, w.gx), fdiv(y, w.gx)));
+    z = fsub(z, wave_bilinear(w.ch1, w.N, fdiv(x, w.gy), fdiv(y, w.gy)));
+    return z;
+}
+
+// Ocean::GetDepth(glm::vec3) (Ocean.cpp:149-168)
+template <bool WAVES>
+__device__ __forceinline__ float get_depth(const WavesDev& w, float x, float y, float z)
+{
+    if (WAVES) return fsub(z, wave_height(w, x, y));
+    return z;
+}
+
+} // namespace sfh

@@ -1,0 +1,738 @@
+// sfh_kernels.cuh — the four kernels of one hydrodynamics step (sm_100a).
+//
+//   k_prologue   1 block        per-body: CheckBodyFluidPosition (a9), dispatcher gates (a10), fp64->fp32
+//                               narrowing of transforms/velocities, position-independent current sum,
+//                               then an exclusive scan of chunk counts -> two work lists (submerged / surface)
+//   k_submerged  persistent     per-face ComputeHydrodynamicForcesSubmerged (a1) over (body, chunk) items
+//   k_surface    persistent     per-face ComputeHydrodynamicForcesSurface  (a2) incl. waves (a3/a4)
+//   k_epilogue   1 warp/body    fixed-order reduction of the per-block partials, finalisation (A.5),
+//                               INSIDE analytic buoyancy and CorrectHydrodynamicForces (a11)
+//
+// Work decomposition: the work list is the concatenation of every active body's chunks; block `blk` of a grid
+// of G blocks owns the contiguous item range [blk*W/G, (blk+1)*W/G). A block keeps fp64 partial sums in
+// registers and writes ONE record per (block, body) it touched at index blk + body — those indices are unique
+// because block ranges are contiguous and monotone in the body index — so no atomics, no zero-fill, and the
+// epilogue reduces each body's records in a fixed order: results are bitwise reproducible for a given G.
+#pragma once
+
+#include "sfh_device.cuh"
+
+namespace sfh {
+
+#define SFH_BLOCK 128
+#define SFH_FULL 0xffffffffu
+#define SFH_SPILL_EVERY 100u /* chunks between counter spills: 2 faces/thread/chunk keeps 8/10-bit fields < 255 */
+
+struct StepParams {
+    const BodyDev* bodies;
+    const uint32_t* item_off; // n_bodies + 1, exclusive scan of chunk counts of this kernel's kind
+    uint32_t n_bodies;
+    const OceanDev* ocean;
+    WavesDev waves;
+    void* partials;
+    uint8_t* codes;            // debug: per-face codes, nullptr otherwise
+    const uint64_t* code_base; // debug: first code index of each body
+};
+
+__device__ __forceinline__ uint32_t block_of_item(uint64_t w, uint64_t G, uint64_t W)
+{
+    return (uint32_t)(((w + 1) * G - 1) / W);
+}
+
+// first body whose item range contains w (item_off is non-decreasing, empty bodies are skipped)
+__device__ __forceinline__ uint32_t body_of_item(const uint32_t* __restrict__ item_off, uint32_t n_bodies, uint32_t w)
+{
+    uint32_t lo = 0, hi = n_bodies; // invariant: item_off[lo] <= w < item_off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (item_off[mid] <= w) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = dadd(v, __shfl_down_sync(SFH_FULL, v, off));
+    return v;
+}
+
+template <int NACC>
+__device__ __forceinline__ void block_reduce_store(double (&acc)[NACC], double (*red)[NACC], double* out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        double v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+        acc[i] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double s = red[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < SFH_BLOCK / 32; ++w) s = dadd(s, red[w][threadIdx.x]);
+        out[threadIdx.x] = s;
+    }
+}
+
+struct BodyRegs { // hot per-body constants
+    F3 p, v, omega, cur;
+};
+
+// Damping block shared by both integrators (SolidEntity.cpp:1661-1683, 1771-1790). acc[0..11] = Fdq Tdq Fdf Tdf.
+template <int CUR>
+__device__ __forceinline__ uint32_t damping_terms(const BodyRegs& B, const sfh_current* s_cur, uint32_t n_cur, F3 fc, F3 fn1,
+                                                  float A, double* acc, uint32_t& epack)
+{
+    uint32_t code = 0;
+    F3 fluid = CUR ? fluid_velocity_general(s_cur, n_cur, fc) : B.cur;
+    F3 r = fc - B.p;
+    F3 vc = fluid - (B.v + cross(B.omega, r));
+    float vc_n = dot(vc, fn1);
+    F3 vn = fn1 * vc_n;
+    F3 vt = vc - vn;
+    if (vc_n < -1e-12f) {
+        float vmag2 = length2(vc);
+        F3 q = ((vc * fsqrt(vmag2)) * (-vc_n)) * A;
+        F3 tq = cross(r, q);
+        acc[0] = dadd(acc[0], (double)q.x);  acc[1] = dadd(acc[1], (double)q.y);  acc[2] = dadd(acc[2], (double)q.z);
+        acc[3] = dadd(acc[3], (double)tq.x); acc[4] = dadd(acc[4], (double)tq.y); acc[5] = dadd(acc[5], (double)tq.z);
+        epack += 1u << 10;
+        code |= SFH_FACE_QUADRATIC;
+    }
+    float vmag2 = length2(vt);
+    if (vmag2 > 1e-9f) {
+        F3 s = vt * A;
+        F3 ts = cross(r, s);
+        acc[6] = dadd(acc[6], (double)s.x);  acc[7] = dadd(acc[7], (double)s.y);   acc[8] = dadd(acc[8], (double)s.z);
+        acc[9] = dadd(acc[9], (double)ts.x); acc[10] = dadd(acc[10], (double)ts.y); acc[11] = dadd(acc[11], (double)ts.z);
+        epack += 1u << 20;
+        code |= SFH_FACE_SKIN;
+    }
+    return code;
+}
+
+__device__ __forceinline__ void load_body(BodyDev* sb, const BodyDev* __restrict__ src)
+{
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(sb);
+    for (uint32_t i = threadIdx.x; i < sizeof(BodyDev) / 4; i += SFH_BLOCK) d[i] = __ldg(s + i);
+}
+
+__device__ __forceinline__ void stage_currents(sfh_current* s_cur, const OceanDev* __restrict__ ocean, uint32_t n_cur)
+{
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(ocean->currents);
+    uint32_t* d = reinterpret_cast<uint32_t*>(s_cur);
+    for (uint32_t i = threadIdx.x; i < n_cur * (uint32_t)(sizeof(sfh_current) / 4); i += SFH_BLOCK) d[i] = __ldg(s + i);
+}
+
+// 3 x 10-bit event counters (degenerate | quadratic << 10 | skin << 20) -> shared u32 counters
+__device__ __forceinline__ void spill_epack(uint32_t& epack, uint32_t* s_cnt)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint32_t v = __reduce_add_sync(SFH_FULL, (epack >> (10 * k)) & 1023u);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], v);
+    }
+    epack = 0;
+}
+__device__ __forceinline__ void spill_cpack(uint64_t& cpack, uint32_t* s_cls)
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t v = __reduce_add_sync(SFH_FULL, (uint32_t)(cpack >> (8 * k)) & 255u);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cls[k], v);
+    }
+    cpack = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_submerged — SolidEntity::ComputeHydrodynamicForcesSubmerged (SolidEntity.cpp:1749-1791)
+// ---------------------------------------------------------------------------------------------
+template <int CUR, bool DEBUG>
+__global__ void __launch_bounds__(SFH_BLOCK) k_submerged(StepParams P)
+{
+    __shared__ float4 s_v[SFH_CH_VERTS];
+    __shared__ BodyDev s_body;
+    __shared__ double s_red[SFH_BLOCK / 32][SFH_NACC_SUB];
+    __shared__ uint32_t s_cnt[4];
+    __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
+
+    const uint32_t tid = threadIdx.x;
+    const uint64_t W = P.item_off[P.n_bodies], G = gridDim.x;
+    const uint32_t w0 = (uint32_t)((uint64_t)blockIdx.x * W / G), w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
+    if (w0 >= w1) return;
+
+    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
+    if (CUR) stage_currents(s_cur, P.ocean, n_cur);
+    if (tid < 4) s_cnt[tid] = 0;
+
+    double acc[SFH_NACC_SUB];
+#pragma unroll
+    for (int i = 0; i < SFH_NACC_SUB; ++i) acc[i] = 0.0;
+    uint32_t epack = 0, since_spill = 0;
+
+    uint32_t b = body_of_item(P.item_off, P.n_bodies, w0);
+    uint32_t b_end = P.item_off[b + 1];
+    load_body(&s_body, P.bodies + b);
+    __syncthreads();
+    BodyRegs B;
+
+    auto flush = [&](uint32_t body) {
+        spill_epack(epack, s_cnt);
+        since_spill = 0;
+        PartialSub* rec = reinterpret_cast<PartialSub*>(P.partials) + (blockIdx.x + body);
+        __syncthreads();
+        block_reduce_store<SFH_NACC_SUB>(acc, s_red, rec->a);
+        if (tid < 3) { (&rec->n_degenerate)[tid] = s_cnt[tid]; }
+        __syncthreads();
+        if (tid < 4) s_cnt[tid] = 0;
+    };
+    auto fetch_regs = [&]() {
+        B.p = F3{s_body.p[0], s_body.p[1], s_body.p[2]};
+        B.v = F3{s_body.v[0], s_body.v[1], s_body.v[2]};
+        B.omega = F3{s_body.omega[0], s_body.omega[1], s_body.omega[2]};
+        B.cur = F3{s_body.cur[0], s_body.cur[1], s_body.cur[2]};
+    };
+    fetch_regs();
+
+    for (uint32_t w = w0; w < w1; ++w) {
+        if (w >= b_end) {
+            flush(b);
+            do { ++b; b_end = P.item_off[b + 1]; } while (w >= b_end);
+            load_body(&s_body, P.bodies + b);
+            __syncthreads();
+            fetch_regs();
+        }
+        const uint32_t c = w - P.item_off[b];
+        const uint8_t* __restrict__ ch = s_body.chunks + (size_t)c * SFH_CH_BYTES;
+        const uint2 hdr = __ldg(reinterpret_cast<const uint2*>(ch));
+        const uint32_t nv = hdr.x, nf = hdr.y;
+
+        // faces first (independent of the barrier), then vertices: each transformed once per chunk
+        uint32_t fpk[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t slot = tid + k * SFH_BLOCK;
+            fpk[k] = slot < nf ? __ldg(reinterpret_cast<const uint32_t*>(ch + SFH_CH_F_OFF) + slot) : 0u;
+        }
+        float vx[2], vy[2], vz[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t i = tid + k * SFH_BLOCK;
+            if (i < nv) {
+                vx[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_X_OFF) + i);
+                vy[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_Y_OFF) + i);
+                vz[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_Z_OFF) + i);
+            }
+        }
+        __syncthreads(); // previous chunk's readers are done with s_v
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t i = tid + k * SFH_BLOCK;
+            if (i < nv) {
+                F3 pw = xform(s_body.R, s_body.t, vx[k], vy[k], vz[k]);
+                s_v[i] = make_float4(pw.x, pw.y, pw.z, 0.f);
+            }
+        }
+        __syncthreads();
+
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t slot = tid + k * SFH_BLOCK;
+            if (slot < nf) {
+                const float4 a4 = s_v[fpk[k] & 255u], b4 = s_v[(fpk[k] >> 8) & 255u], c4 = s_v[(fpk[k] >> 16) & 255u];
+                const F3 p1 = {a4.x, a4.y, a4.z}, p2 = {b4.x, b4.y, b4.z}, p3 = {c4.x, c4.y, c4.z};
+                uint32_t code = 7;
+                F3 fv1 = p2 - p1;
+                F3 fv2 = p3 - p1;
+                F3 fn = cross(fv1, fv2);
+                float len = length2(fn);
+                if (len < 1e-12f) {
+                    epack += 1u;
+                    code |= SFH_FACE_DEGENERATE;
+                } else {
+                    len = fsqrt(len);
+                    F3 fn1 = fn / len;
+                    float A = fdiv(len, 2.f);
+                    F3 fc = ((p1 + p2) + p3) / 3.f;
+                    code |= damping_terms<CUR>(B, s_cur, n_cur, fc, fn1, A, acc, epack);
+                }
+                if (DEBUG) P.codes[P.code_base[b] + s_body.orig_face[(size_t)c * SFH_CH_FACES + slot]] = (uint8_t)code;
+            }
+        }
+        if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); since_spill = 0; }
+    }
+    flush(b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_surface — SolidEntity::ComputeHydrodynamicForcesSurface (SolidEntity.cpp:1337-1687)
+// acc: [0..11] Fdq Tdq Fdf Tdf | [12..14] Fb | [15..17] Tb | [18] Swet | [19] Vsub | [20..22] CBsub
+// ---------------------------------------------------------------------------------------------
+template <bool WAVES, int CUR, bool DEBUG>
+__global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
+{
+    __shared__ float4 s_v[SFH_CH_VERTS]; // world x,y,z and depth
+    __shared__ BodyDev s_body;
+    __shared__ double s_red[SFH_BLOCK / 32][SFH_NACC_SURF];
+    __shared__ uint32_t s_cnt[12]; // [0..2] degenerate quadratic skin, [4..11] classes
+    __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
+
+    const uint32_t tid = threadIdx.x;
+    const uint64_t W = P.item_off[P.n_bodies], G = gridDim.x;
+    const uint32_t w0 = (uint32_t)((uint64_t)blockIdx.x * W / G), w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
+    if (w0 >= w1) return;
+
+    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
+    if (CUR) stage_currents(s_cur, P.ocean, n_cur);
+    if (tid < 12) s_cnt[tid] = 0;
+    const WavesDev wv = P.waves;
+
+    double acc[SFH_NACC_SURF];
+#pragma unroll
+    for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = 0.0;
+    uint32_t epack = 0, since_spill = 0;
+    uint64_t cpack = 0;
+
+    uint32_t b = body_of_item(P.item_off, P.n_bodies, w0);
+    uint32_t b_end = P.item_off[b + 1];
+    load_body(&s_body, P.bodies + b);
+    __syncthreads();
+    BodyRegs B;
+    F3 p0;
+    bool buoy, damp;
+
+    auto flush = [&](uint32_t body) {
+        spill_epack(epack, s_cnt);
+        spill_cpack(cpack, s_cnt + 4);
+        since_spill = 0;
+        PartialSurf* rec = reinterpret_cast<PartialSurf*>(P.partials) + (blockIdx.x + body);
+        __syncthreads();
+        block_reduce_store<SFH_NACC_SURF>(acc, s_red, rec->a);
+        if (tid < 3) (&rec->n_degenerate)[tid] = s_cnt[tid];
+        if (tid >= 4 && tid < 12) rec->cls[tid - 4] = s_cnt[tid];
+        __syncthreads();
+        if (tid < 12) s_cnt[tid] = 0;
+    };
+    auto fetch_regs = [&]() {
+        B.p = F3{s_body.p[0], s_body.p[1], s_body.p[2]};
+        B.v = F3{s_body.v[0], s_body.v[1], s_body.v[2]};
+        B.omega = F3{s_body.omega[0], s_body.omega[1], s_body.omega[2]};
+        B.cur = F3{s_body.cur[0], s_body.cur[1], s_body.cur[2]};
+        p0 = F3{B.p.x, B.p.y, 0.f}; // SolidEntity.cpp:1332-1334
+        buoy = (s_body.flags & BF_BUOYANCY) != 0;
+        damp = (s_body.flags & BF_DAMPING) != 0;
+    };
+    fetch_regs();
+
+    for (uint32_t w = w0; w < w1; ++w) {
+        if (w >= b_end) {
+            flush(b);
+            do { ++b; b_end = P.item_off[b + 1]; } while (w >= b_end);
+            load_body(&s_body, P.bodies + b);
+            __syncthreads();
+            fetch_regs();
+        }
+        const uint32_t c = w - P.item_off[b];
+        const uint8_t* __restrict__ ch = s_body.chunks + (size_t)c * SFH_CH_BYTES;
+        const uint2 hdr = __ldg(reinterpret_cast<const uint2*>(ch));
+        const uint32_t nv = hdr.x, nf = hdr.y;
+
+        uint32_t fpk[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t slot = tid + k * SFH_BLOCK;
+            fpk[k] = slot < nf ? __ldg(reinterpret_cast<const uint32_t*>(ch + SFH_CH_F_OFF) + slot) : 0u;
+        }
+        float vx[2], vy[2], vz[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t i = tid + k * SFH_BLOCK;
+            if (i < nv) {
+                vx[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_X_OFF) + i);
+                vy[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_Y_OFF) + i);
+                vz[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_Z_OFF) + i);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t i = tid + k * SFH_BLOCK;
+            if (i < nv) {
+                F3 pw = xform(s_body.R, s_body.t, vx[k], vy[k], vz[k]);
+                // Ocean::GetDepth per vertex (SolidEntity.cpp:1349-1351): same bits for every incident face
+                s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(wv, pw.x, pw.y, pw.z));
+            }
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t slot = tid + k * SFH_BLOCK;
+            if (slot >= nf) continue;
+            const uint32_t fp = k ? fpk[1] : fpk[0];
+            const float4 a4 = s_v[fp & 255u], b4 = s_v[(fp >> 8) & 255u], c4 = s_v[(fp >> 16) & 255u];
+            F3 p1 = {a4.x, a4.y, a4.z}, p2 = {b4.x, b4.y, b4.z}, p3 = {c4.x, c4.y, c4.z};
+            const float d0 = a4.w, d1 = b4.w, d2 = c4.w;
+            const bool a0 = d0 < 0.f, a1 = d1 < 0.f, a2 = d2 < 0.f;
+            const uint32_t cls = (a0 ? 0u : 4u) | (a1 ? 0u : 2u) | (a2 ? 0u : 1u);
+            cpack += 1ull << (8 * cls);
+            uint32_t code = cls;
+            if (cls != 0) {
+                // waterline point on the edge from the submerged vertex pu (du >= 0) to the dry vertex pa (da < 0)
+                auto clip = [](F3 pa, F3 pu, float da, float du) { return pu + (pa - pu) * fdiv(du, fadd(fabsf(da), du)); };
+                // tetrahedron (p0, a, b, c) of the submerged volume (SolidEntity.cpp:1371-1377 and twins)
+                auto tetra = [&](F3 pa, F3 pb, F3 pc) {
+                    F3 cg = ((pa + pb) + pc) / 4.f;
+                    float v6 = dot(pa, cross(pb, pc));
+                    F3 m = cg * v6;
+                    acc[20] = dadd(acc[20], (double)m.x); acc[21] = dadd(acc[21], (double)m.y); acc[22] = dadd(acc[22], (double)m.z);
+                    acc[19] = dadd(acc[19], (double)v6);
+                };
+                F3 p4 = p1, fv1, fv2, fv3, fv4;
+                bool is_quad = false;
+                switch (cls) {
+                case 1: p1 = clip(p1, p3, d0, d2); p2 = clip(p2, p3, d1, d2); break;
+                case 2: p1 = clip(p1, p2, d0, d1); p3 = clip(p3, p2, d2, d1); break;
+                case 3: p4 = clip(p1, p3, d0, d2); p1 = clip(p1, p2, d0, d1); is_quad = true; break;
+                case 4: p2 = clip(p2, p1, d1, d0); p3 = clip(p3, p1, d2, d0); break;
+                case 5: p4 = clip(p2, p3, d1, d2); p2 = clip(p2, p1, d1, d0); is_quad = true; break;
+                case 6: p4 = clip(p3, p1, d2, d0); p3 = clip(p3, p2, d2, d1); is_quad = true; break;
+                default: break;
+                }
+                const F3 p01 = p1 - p0, p02 = p2 - p0, p03 = p3 - p0;
+                tetra(p01, p02, p03);
+                F3 fc;
+                if (is_quad) {
+                    const F3 p04 = p4 - p0;
+                    if (cls == 5) { tetra(p02, p04, p03); fv2 = p3 - p1; }
+                    else          { tetra(p01, p03, p04); fv2 = p4 - p1; }
+                    fv1 = p2 - p1; fv3 = p2 - p3; fv4 = p4 - p3;
+                    fc = (((p1 + p2) + p3) + p4) / 4.f;
+                } else {
+                    fv1 = p2 - p1; fv2 = p3 - p1;
+                    fc = ((p1 + p2) + p3) / 3.f;
+                }
+                F3 fn = cross(fv1, fv2);
+                float len = length2(fn);
+                if (len < 1e-12f) {
+                    epack += 1u;
+                    code |= SFH_FACE_DEGENERATE;
+                } else {
+                    len = fsqrt(len);
+                    F3 fn1 = fn / len;
+                    float A = is_quad ? fdiv(fadd(len, fsqrt(length2(cross(fv3, fv4)))), 2.f) : fdiv(len, 2.f);
+                    if (WAVES && buoy) { // SolidEntity.cpp:1650-1658
+                        float depthc = get_depth<WAVES>(wv, fc.x, fc.y, fc.z);
+                        F3 Fbi = ((-fn1) * A) * depthc;
+                        F3 Tbi = cross(fc - B.p, Fbi);
+                        acc[12] = dadd(acc[12], (double)Fbi.x); acc[13] = dadd(acc[13], (double)Fbi.y); acc[14] = dadd(acc[14], (double)Fbi.z);
+                        acc[15] = dadd(acc[15], (double)Tbi.x); acc[16] = dadd(acc[16], (double)Tbi.y); acc[17] = dadd(acc[17], (double)Tbi.z);
+                    }
+                    if (damp) code |= damping_terms<CUR>(B, s_cur, n_cur, fc, fn1, A, acc, epack);
+                    acc[18] = dadd(acc[18], (double)A); // SolidEntity.cpp:1686
+                }
+            }
+            if (DEBUG) P.codes[P.code_base[b] + s_body.orig_face[(size_t)c * SFH_CH_FACES + slot]] = (uint8_t)code;
+        }
+        if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); spill_cpack(cpack, s_cnt + 4); since_spill = 0; }
+    }
+    flush(b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_prologue — per-body gates and narrowing, then the two work-list scans. One block of 1024 threads.
+// ---------------------------------------------------------------------------------------------
+struct PrologueParams {
+    const sfh_body_state* states;
+    const MeshDev* meshes;
+    uint32_t n_meshes;
+    uint32_t n_bodies;
+    const OceanDev* ocean;
+    WavesDev waves;
+    BodyDev* bodies;
+    uint32_t* off_sub;  // n_bodies + 1
+    uint32_t* off_surf; // n_bodies + 1
+    uint32_t* status;   // [0] |= 1 if a body referenced an unknown mesh
+};
+
+// SolidEntity::CheckBodyFluidPosition (SolidEntity.cpp:1239-1261); each corner narrowed to fp32 by
+// Ocean::GetDepth(const Vector3&) (Ocean.cpp:170-173)
+__device__ inline uint32_t check_body_fluid_position(bool waves, const WavesDev& wv, const double* mn, const double* mx)
+{
+    const double d[3] = {dsub(mx[0], mn[0]), dsub(mx[1], mn[1]), dsub(mx[2], mn[2])};
+    const double c[8][3] = {{mn[0], mn[1], mn[2]},
+                            {mx[0], mx[1], mx[2]},
+                            {dadd(mn[0], d[0]), dadd(mn[1], 0.0), dadd(mn[2], 0.0)},
+                            {dadd(mn[0], 0.0), dadd(mn[1], d[1]), dadd(mn[2], 0.0)},
+                            {dadd(mn[0], d[0]), dadd(mn[1], d[1]), dadd(mn[2], 0.0)},
+                            {dadd(mn[0], 0.0), dadd(mn[1], 0.0), dadd(mn[2], d[2])},
+                            {dadd(mn[0], d[0]), dadd(mn[1], 0.0), dadd(mn[2], d[2])},
+                            {dadd(mn[0], 0.0), dadd(mn[1], d[1]), dadd(mn[2], d[2])}};
+    uint32_t under = 0;
+    for (int k = 0; k < 8; ++k) {
+        const float x = (float)c[k][0], y = (float)c[k][1], z = (float)c[k][2];
+        const float depth = waves ? get_depth<true>(wv, x, y, z) : z;
+        if ((double)depth > 0.0) ++under;
+    }
+    return under == 0 ? SFH_POS_OUTSIDE : (under == 8 ? SFH_POS_INSIDE : SFH_POS_CROSSING);
+}
+
+__global__ void __launch_bounds__(1024) k_prologue(PrologueParams P)
+{
+    __shared__ uint32_t s_warp[2][32];
+    __shared__ uint32_t s_carry[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const OceanDev* __restrict__ oc = P.ocean;
+    const bool waves = oc->has_waves != 0;
+    if (tid < 2) s_carry[tid] = 0;
+    __syncthreads();
+
+    // position-independent part of Ocean::GetFluidVelocity (Ocean.cpp:183-201)
+    float cur[3] = {0.f, 0.f, 0.f};
+    if (oc->currents_enabled && !oc->cur_general) {
+        D3 fv = {0.0, 0.0, 0.0};
+        for (uint32_t i = 0; i < oc->n_currents; ++i)
+            if (oc->currents[i].enabled) fv = fv + D3{oc->currents[i].a[0], oc->currents[i].a[1], oc->currents[i].a[2]};
+        cur[0] = (float)fv.x; cur[1] = (float)fv.y; cur[2] = (float)fv.z;
+    }
+
+    for (uint32_t base = 0; base < P.n_bodies; base += blockDim.x) {
+        const uint32_t i = base + tid;
+        uint32_t n_sub = 0, n_surf = 0;
+        if (i < P.n_bodies) {
+            const sfh_body_state& st = P.states[i];
+            BodyDev bd;
+            uint32_t pos = st.mode;
+            if (pos == SFH_POS_AUTO) pos = check_body_fluid_position(waves, P.waves, st.aabb_min, st.aabb_max);
+            if (pos > SFH_POS_CROSSING) pos = SFH_POS_OUTSIDE;
+            const bool dispatch = (st.flags & SFH_F_DISPATCH) != 0;
+            bool damping = (st.flags & SFH_F_DAMPING) != 0, buoyancy = (st.flags & SFH_F_BUOYANCY) != 0;
+            uint32_t kind = KIND_NONE;
+            if (pos == SFH_POS_INSIDE) {
+                // raw integrator: always runs (it has no settings); dispatcher: only `if(settings.dampingForces)`
+                if (!dispatch || damping) kind = KIND_SUBMERGED;
+                damping = true;
+            } else if (pos == SFH_POS_CROSSING) {
+                if (dispatch && !(st.flags & SFH_F_BUOYANT)) buoyancy = false; // SolidEntity.cpp:1844
+                kind = KIND_SURFACE;
+            }
+            MeshDev m = {nullptr, nullptr, 0, 0};
+            if (st.mesh_id < P.n_meshes) m = P.meshes[st.mesh_id];
+            else if (kind != KIND_NONE) atomicOr(P.status, 1u);
+            // glMatrixFromTransform / glVectorFromVector (OpenGLDataStructs.cpp:148-171)
+            for (int k = 0; k < 9; ++k) bd.R[k] = (float)st.T_C[k];
+            for (int k = 0; k < 3; ++k) {
+                bd.t[k] = (float)st.T_C[9 + k];
+                bd.p[k] = (float)st.T_CG[9 + k];
+                bd.v[k] = (float)st.v[k];
+                bd.omega[k] = (float)st.omega[k];
+                bd.cur[k] = cur[k];
+            }
+            bd.flags = (damping ? BF_DAMPING : 0u) | (buoyancy ? BF_BUOYANCY : 0u);
+            bd.kind = kind | (pos << 8);
+            bd.n_chunks = (kind != KIND_NONE) ? m.n_chunks : 0u;
+            bd.pad = m.n_faces;
+            bd.chunks = m.chunks;
+            bd.orig_face = m.orig_face;
+            P.bodies[i] = bd;
+            if (kind == KIND_SUBMERGED) n_sub = bd.n_chunks;
+            if (kind == KIND_SURFACE) n_surf = bd.n_chunks;
+        }
+        // block-wide exclusive scan of (n_sub, n_surf)
+        uint32_t xs = n_sub, xf = n_surf;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t ys = __shfl_up_sync(SFH_FULL, xs, off), yf = __shfl_up_sync(SFH_FULL, xf, off);
+            if (lane >= (uint32_t)off) { xs += ys; xf += yf; }
+        }
+        if (lane == 31) { s_warp[0][warp] = xs; s_warp[1][warp] = xf; }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = s_warp[0][lane], wf = s_warp[1][lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t ys = __shfl_up_sync(SFH_FULL, ws, off), yf = __shfl_up_sync(SFH_FULL, wf, off);
+                if (lane >= (uint32_t)off) { ws += ys; wf += yf; }
+            }
+            s_warp[0][lane] = ws; s_warp[1][lane] = wf; // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t pre_s = s_carry[0] + (warp ? s_warp[0][warp - 1] : 0u) + xs - n_sub;
+        const uint32_t pre_f = s_carry[1] + (warp ? s_warp[1][warp - 1] : 0u) + xf - n_surf;
+        if (i < P.n_bodies) { P.off_sub[i] = pre_s; P.off_surf[i] = pre_f; }
+        __syncthreads();
+        if (tid == 0) { s_carry[0] += s_warp[0][31]; s_carry[1] += s_warp[1][31]; }
+        __syncthreads();
+    }
+    if (tid == 0) { P.off_sub[P.n_bodies] = s_carry[0]; P.off_surf[P.n_bodies] = s_carry[1]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_epilogue — one warp per body: reduce partial records in block order, finalise, correct.
+// ---------------------------------------------------------------------------------------------
+struct EpilogueParams {
+    const sfh_body_state* states;
+    const BodyDev* bodies;
+    uint32_t n_bodies;
+    const OceanDev* ocean;
+    const uint32_t* off_sub;
+    const uint32_t* off_surf;
+    const PartialSub* part_sub;
+    const PartialSurf* part_surf;
+    uint32_t grid_sub, grid_surf;
+    sfh_info* out;
+};
+
+// SolidEntity::CorrectHydrodynamicForces (SolidEntity.cpp:1263-1287)
+__device__ inline void correct_forces(double density, double* Fdq, double* Tdq, double* Fdf, double* Tdf, const double* Cd,
+                                      const double* Cf, const double* B)
+{
+#define EL(r, c) B[3 * (r) + (c)]
+#define COFAC(r1, c1, r2, c2) dsub(dmul(EL(r1, c1), EL(r2, c2)), dmul(EL(r1, c2), EL(r2, c1)))
+    const D3 co = {COFAC(1, 1, 2, 2), COFAC(1, 2, 2, 0), COFAC(1, 0, 2, 1)};
+    const double det = ddot(D3{EL(0, 0), EL(0, 1), EL(0, 2)}, co);
+    const double s = ddiv(1.0, det);
+    const D3 r0 = {dmul(co.x, s), dmul(COFAC(0, 2, 2, 1), s), dmul(COFAC(0, 1, 1, 2), s)};
+    const D3 r1 = {dmul(co.y, s), dmul(COFAC(0, 0, 2, 2), s), dmul(COFAC(0, 2, 1, 0), s)};
+    const D3 r2 = {dmul(co.z, s), dmul(COFAC(0, 1, 2, 0), s), dmul(COFAC(0, 0, 1, 1), s)};
+#undef EL
+#undef COFAC
+    auto coeff = [&](const double* X, const double* C) {
+        D3 v = {X[0], X[1], X[2]};
+        D3 q = {ddot(r0, v), ddot(r1, v), ddot(r2, v)};
+        double l2 = ddot(q, q);
+        if (l2 >= 2.2204460492503131e-16 * 2.2204460492503131e-16) q = q * ddiv(1.0, __dsqrt_rn(l2));
+        else q = D3{1.0, 0.0, 0.0};
+        return dadd(dadd(dmul(fabs(q.x), C[0]), dmul(fabs(q.y), C[1])), dmul(fabs(q.z), C[2]));
+    };
+    double k;
+    k = dmul(dmul(0.5, density), coeff(Fdq, Cd)); Fdq[0] = dmul(Fdq[0], k); Fdq[1] = dmul(Fdq[1], k); Fdq[2] = dmul(Fdq[2], k);
+    k = dmul(dmul(0.5, density), coeff(Tdq, Cd)); Tdq[0] = dmul(Tdq[0], k); Tdq[1] = dmul(Tdq[1], k); Tdq[2] = dmul(Tdq[2], k);
+    k = dmul(density, coeff(Fdf, Cf)); Fdf[0] = dmul(Fdf[0], k); Fdf[1] = dmul(Fdf[1], k); Fdf[2] = dmul(Fdf[2], k);
+    k = dmul(density, coeff(Tdf, Cf)); Tdf[0] = dmul(Tdf[0], k); Tdf[1] = dmul(Tdf[1], k); Tdf[2] = dmul(Tdf[2], k);
+}
+
+__global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= P.n_bodies) return;
+    const BodyDev& bd = P.bodies[b];
+    const uint32_t kind = bd.kind & 255u, pos = bd.kind >> 8;
+
+    double acc[SFH_NACC_SURF];
+#pragma unroll
+    for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = 0.0;
+    uint32_t cnt[11]; // degenerate quadratic skin | cls[8]
+#pragma unroll
+    for (int i = 0; i < 11; ++i) cnt[i] = 0;
+
+    if (kind == KIND_SUBMERGED) {
+        const uint32_t o0 = P.off_sub[b], o1 = P.off_sub[b + 1];
+        if (o1 > o0) {
+            const uint64_t W = P.off_sub[P.n_bodies], G = P.grid_sub;
+            const uint32_t k0 = block_of_item(o0, G, W), k1 = block_of_item(o1 - 1, G, W);
+            for (uint32_t k = k0 + lane; k <= k1; k += 32) {
+                const PartialSub& r = P.part_sub[k + b];
+#pragma unroll
+                for (int i = 0; i < SFH_NACC_SUB; ++i) acc[i] = dadd(acc[i], r.a[i]);
+                cnt[0] += r.n_degenerate; cnt[1] += r.n_quadratic; cnt[2] += r.n_skin;
+            }
+        }
+    } else if (kind == KIND_SURFACE) {
+        const uint32_t o0 = P.off_surf[b], o1 = P.off_surf[b + 1];
+        if (o1 > o0) {
+            const uint64_t W = P.off_surf[P.n_bodies], G = P.grid_surf;
+            const uint32_t k0 = block_of_item(o0, G, W), k1 = block_of_item(o1 - 1, G, W);
+            for (uint32_t k = k0 + lane; k <= k1; k += 32) {
+                const PartialSurf& r = P.part_surf[k + b];
+#pragma unroll
+                for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = dadd(acc[i], r.a[i]);
+                cnt[0] += r.n_degenerate; cnt[1] += r.n_quadratic; cnt[2] += r.n_skin;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cnt[3 + i] += r.cls[i];
+            }
+        }
+    }
+    if (kind != KIND_NONE) {
+#pragma unroll
+        for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = warp_sum(acc[i]);
+#pragma unroll
+        for (int i = 0; i < 11; ++i) cnt[i] = __reduce_add_sync(SFH_FULL, cnt[i]);
+    }
+    if (lane != 0) return;
+
+    const sfh_body_state& st = P.states[b];
+    const OceanDev& oc = *P.ocean;
+    const bool dispatch = (st.flags & SFH_F_DISPATCH) != 0;
+    sfh_info o;
+    for (int k = 0; k < 3; ++k) { o.Fb[k] = 0; o.Tb[k] = 0; o.Fdq[k] = 0; o.Tdq[k] = 0; o.Fdf[k] = 0; o.Tdf[k] = 0; }
+    o.Swet = 0; o.Vsub = 0; o.wrote_buoyancy = 0; o.wrote_damping = 0; o.position = pos; o.reserved = 0;
+    o.n_faces = (kind != KIND_NONE) ? bd.pad : 0u;
+    o.n_degenerate = cnt[0]; o.n_quadratic = cnt[1]; o.n_skin = cnt[2];
+    for (int k = 0; k < 8; ++k) o.class_count[k] = cnt[3 + k];
+
+    if (pos == SFH_POS_OUTSIDE) { // SolidEntity.cpp:1810-1821
+        o.wrote_buoyancy = 1; o.wrote_damping = 1;
+    } else if (pos == SFH_POS_INSIDE) {
+        if (kind == KIND_SUBMERGED) { // SolidEntity.cpp:1793-1796
+            for (int k = 0; k < 3; ++k) { o.Fdq[k] = acc[k]; o.Tdq[k] = acc[3 + k]; o.Fdf[k] = acc[6 + k]; o.Tdf[k] = acc[9 + k]; }
+            o.wrote_damping = 1;
+            o.class_count[7] = o.n_faces;
+        }
+        if (dispatch) { // SolidEntity.cpp:1828-1841
+            if (st.flags & SFH_F_BUOYANT) {
+                const double s = dmul(-st.volume, oc.density);
+                const D3 Fb = {dmul(0.0, s), dmul(0.0, s), dmul(oc.gravity_z, s)};
+                const double* T = st.T_CG;
+                const D3 pcb = {st.P_CB[0], st.P_CB[1], st.P_CB[2]}, org = {T[9], T[10], T[11]};
+                const D3 wcb = {dadd(ddot(D3{T[0], T[1], T[2]}, pcb), org.x), dadd(ddot(D3{T[3], T[4], T[5]}, pcb), org.y),
+                                dadd(ddot(D3{T[6], T[7], T[8]}, pcb), org.z)};
+                const D3 Tb = dcross(wcb - org, Fb);
+                o.Fb[0] = Fb.x; o.Fb[1] = Fb.y; o.Fb[2] = Fb.z; o.Tb[0] = Tb.x; o.Tb[1] = Tb.y; o.Tb[2] = Tb.z;
+                o.wrote_buoyancy = 1;
+            }
+            o.Swet = st.surface;
+        }
+    } else { // CROSSING: SolidEntity.cpp:1689-1720 on the fp64 sums (F64_ACC contract)
+        const bool buoy = (bd.flags & BF_BUOYANCY) != 0, damp = (bd.flags & BF_DAMPING) != 0;
+        const double Vsub = acc[19];
+        if (buoy && Vsub > (double)1e-9f) {
+            o.wrote_buoyancy = 1;
+            o.Vsub = ddiv(Vsub, (double)6.f);
+            if (oc.has_waves) {
+                const double kk = (double)(float)dmul(oc.density, oc.gravity_z);
+                for (int k = 0; k < 3; ++k) { o.Fb[k] = dmul(acc[12 + k], kk); o.Tb[k] = dmul(acc[15 + k], kk); }
+            } else {
+                const D3 cb = {dadd(ddiv(acc[20], Vsub), (double)bd.p[0]), dadd(ddiv(acc[21], Vsub), (double)bd.p[1]),
+                               dadd(ddiv(acc[22], Vsub), (double)0.f)};
+                const double s = dmul(-o.Vsub, oc.density);
+                const D3 Fb = {dmul(0.0, s), dmul(0.0, s), dmul(oc.gravity_z, s)};
+                const D3 Tb = dcross(cb - D3{st.T_CG[9], st.T_CG[10], st.T_CG[11]}, Fb);
+                o.Fb[0] = Fb.x; o.Fb[1] = Fb.y; o.Fb[2] = Fb.z; o.Tb[0] = Tb.x; o.Tb[1] = Tb.y; o.Tb[2] = Tb.z;
+            }
+        }
+        if (damp) {
+            o.wrote_damping = 1;
+            for (int k = 0; k < 3; ++k) { o.Fdq[k] = acc[k]; o.Tdq[k] = acc[3 + k]; o.Fdf[k] = acc[6 + k]; o.Tdf[k] = acc[9 + k]; }
+        }
+        o.Swet = acc[18];
+    }
+    if (dispatch && pos != SFH_POS_OUTSIDE && (st.flags & SFH_F_DAMPING)) // SolidEntity.cpp:1848-1849
+        correct_forces(oc.density, o.Fdq, o.Tdq, o.Fdf, o.Tdf, st.Cd, st.Cf, st.T_O_basis);
+    P.out[b] = o;
+}
+
+// wave field de-interleave: RGBA32F layer 0 (+ spill-over row) -> planar channel 0 / 1
+__global__ void k_waves_planar(const float* __restrict__ rgba, uint32_t n_floats_valid, uint32_t n_texels, float* ch0, float* ch1)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_texels) return;
+    ch0[i] = (4 * i + 0 < n_floats_valid) ? rgba[4 * i + 0] : 0.f;
+    ch1[i] = (4 * i + 1 < n_floats_valid) ? rgba[4 * i + 1] : 0.f;
+}
+
+} // namespace sfh

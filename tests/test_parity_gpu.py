@@ -1,0 +1,192 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle — the first gate.
+
+Bit-exact: per-face clipping class / degenerate / drag-branch codes and the per-body counters.
+1e-9 of the force norm: the six force/torque sums, Swet, Vsub against the oracle's F64_ACC mode (identical fp32
+per-face terms, fp64 sums). The reference's own fp32 sequential sums (REF_F32_SEQ) are compared with a loose
+tolerance that documents the reference's rounding noise.
+"""
+import numpy as np
+import pytest
+
+from stonefish_b200 import scenes
+from tests.parity import REL_TOL, assert_counts_equal, max_rel_err, run_both
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("waves", [False, True])
+@pytest.mark.parametrize("currents", ["none", "uniform", "jetpipe"])
+@pytest.mark.parametrize("seed", [7, 8])
+def test_mixed_small_bit_exact_classes_and_forces(ctx, oracle, waves, currents, seed):
+    sc = scenes.mixed_small(seed, waves, currents)
+    gi, gc, ri, rc = run_both(ctx, oracle, sc)
+    assert_counts_equal(gi, ri)
+    if currents == "jetpipe":
+        # exp/pow differ by <=1-2 ulp between CUDA and glibc: clipping class and degenerate bits stay exact,
+        # drag-branch bits may flip with probability ~1e-8 per face; none expected at this size.
+        assert np.array_equal(gc & 15, rc & 15)
+        assert (gc != rc).sum() <= 1
+    else:
+        assert np.array_equal(gc, rc)
+    err, where = max_rel_err(gi, ri)
+    assert err <= REL_TOL, (err, where)
+    # every position and every clipping class is reached by this scene family
+    assert set(np.unique(gi["position"])) == {0, 1, 2}
+    assert (gi["class_count"].sum(axis=0) > 0).all()
+
+
+def test_config2_reduced_and_full(ctx, oracle):
+    for seg, st in ((100, 51), (400, 251)):
+        sc = scenes.config2(seg, st)
+        gi, gc, ri, rc = run_both(ctx, oracle, sc)
+        assert_counts_equal(gi, ri)
+        assert np.array_equal(gc, rc)
+        err, where = max_rel_err(gi, ri)
+        assert err <= REL_TOL, (err, where)
+    assert gi["n_faces"][0] == 200000
+
+
+@pytest.mark.parametrize("waves", [False, True])
+def test_config3_reduced_and_full(ctx, oracle, waves):
+    for seg, st in ((100, 51), (400, 251)):
+        sc = scenes.config3(seg, st, waves)
+        gi, gc, ri, rc = run_both(ctx, oracle, sc)
+        assert_counts_equal(gi, ri)
+        assert np.array_equal(gc, rc)
+        err, where = max_rel_err(gi, ri)
+        assert err <= REL_TOL, (err, where)
+        assert gi["wrote_buoyancy"][0] == 1
+        if not waves:  # Archimedes on a flat sea: Fb = -Vsub * rho * g (SolidEntity.cpp:1705)
+            assert gi["Fb"][0][2] == -gi["Vsub"][0] * sc.ocean.density * sc.ocean.gravity
+
+
+def test_config1_scene_full_dispatch(ctx, oracle):
+    sc = scenes.config1()
+    gi, gc, ri, rc = run_both(ctx, oracle, sc)
+    assert_counts_equal(gi, ri)
+    assert np.array_equal(gc, rc)
+    err, where = max_rel_err(gi, ri)
+    assert err <= REL_TOL, (err, where)
+    assert set(np.unique(gi["position"])) == {0, 1, 2}
+
+
+def test_reference_fp32_sequential_gap_is_rounding_noise(ctx, oracle):
+    sc = scenes.config2(200, 101)
+    gi, _, ri, _ = run_both(ctx, oracle, sc, debug=False, acc_mode=0)
+    assert_counts_equal(gi, ri)
+    err, _ = max_rel_err(gi, ri)
+    assert err < 1e-4  # ~1e-7*sqrt(N) relative: the reference's own accumulation error, not ours
+
+
+@pytest.mark.parametrize("unique", [False, True])
+def test_config4_batch(ctx, oracle, unique):
+    sc = scenes.config4(96, 50, 21, unique_meshes=unique)
+    gi, gc, ri, rc = run_both(ctx, oracle, sc)
+    assert_counts_equal(gi, ri)
+    assert np.array_equal(gc, rc)
+    err, where = max_rel_err(gi, ri)
+    assert err <= REL_TOL, (err, where)
+
+
+def test_config4_many_bodies_no_debug(ctx, oracle):
+    sc = scenes.config4(3000, 20, 11)  # thousands of tiny bodies: several bodies per thread block
+    gi, _, ri, _ = run_both(ctx, oracle, sc, debug=False)
+    assert_counts_equal(gi, ri)
+    err, where = max_rel_err(gi, ri)
+    assert err <= REL_TOL, (err, where)
+
+
+def test_config5_reduced(ctx, oracle):
+    sc = scenes.config5(6, 120, 61, unique_meshes=True)
+    gi, gc, ri, rc = run_both(ctx, oracle, sc)
+    assert_counts_equal(gi, ri)
+    assert np.array_equal(gc & 15, rc & 15)
+    assert (gc != rc).sum() <= 1
+    err, where = max_rel_err(gi, ri)
+    assert err <= REL_TOL, (err, where)
+
+
+def test_bitwise_reproducible(ctx):
+    sc = scenes.mixed_small(11, True, "jetpipe")
+    st = sc.bind(ctx)
+    a = ctx.compute(sc.ocean, st)
+    b = ctx.compute(sc.ocean, st)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_keep_order_equals_morton_order(ctx, oracle):
+    sc = scenes.config3(100, 51, True)
+    ids_m = ctx.upload_mesh(sc.meshes[0], keep_order=False)
+    ids_k = ctx.upload_mesh(sc.meshes[0], keep_order=True)
+    st = sc.states.copy()
+    st["mesh_id"] = ids_m
+    a = ctx.compute(sc.ocean, st)
+    st["mesh_id"] = ids_k
+    b = ctx.compute(sc.ocean, st)
+    assert_counts_equal(a, b)
+    err, where = max_rel_err(a, b)
+    assert err <= 1e-12, (err, where)
+
+
+def test_edge_cases(ctx, oracle):
+    from stonefish_b200 import Mesh, Ocean, SfhError, new_body_states
+
+    ocean = Ocean()
+    # zero bodies is a no-op
+    assert ctx.compute(ocean, new_body_states(0)).shape == (0,)
+    # a mesh with no faces gives zero outputs, like mesh == nullptr in the reference (SolidEntity.cpp:1726-1733)
+    empty = Mesh(np.zeros((3, 3), np.float32), np.zeros((0, 3), np.uint32))
+    mid = ctx.upload_mesh(empty)
+    st = new_body_states(2)
+    st["mesh_id"] = mid
+    st["mode"] = [1, 2]
+    st["flags"] = 3
+    out = ctx.compute(ocean, st)
+    assert out["n_faces"].tolist() == [0, 0]
+    for k in ("Fb", "Tb", "Fdq", "Tdq", "Fdf", "Tdf"):
+        assert not out[k].any()
+    assert out["wrote_damping"].tolist() == [1, 1]
+    # errors are loud
+    st["mesh_id"] = 10**6
+    with pytest.raises(SfhError):
+        ctx.compute(ocean, st)
+    wavy = Ocean()
+    wavy.fft_data = None
+    o = wavy.to_struct()
+    o.has_waves = 1
+    st["mesh_id"] = mid
+    fresh = type(ctx)(0)
+    try:
+        with pytest.raises(SfhError):
+            fresh._check(fresh.lib.sfh_step(fresh.ctx, o, st.ctypes.data, 2, np.zeros(2, out.dtype).ctypes.data), "sfh_step")
+    finally:
+        fresh.close()
+    with pytest.raises(SfhError):
+        ctx.upload_mesh(Mesh(np.zeros((3, 3), np.float32), np.array([[0, 1, 7]], np.uint32)))
+
+
+def test_full_size_properties_config4(ctx):
+    """BASELINE size (50k-face hulls) through size-independent properties: counts add up, zero relative flow gives
+    zero drag, and doubling every velocity scales form drag by 4 and skin friction by 2 (up to fp32 rounding)."""
+    sc = scenes.config4(64, 250, 101)
+    st = sc.bind(ctx)
+    out = ctx.compute(sc.ocean, st)
+    assert (out["n_faces"] == 50000).all()
+    assert (out["class_count"][:, 7] == 50000).all()
+    assert (out["n_quadratic"] + out["n_degenerate"] <= 50000).all()
+    # at rest in still water: nothing
+    sc.ocean.DisableCurrents()
+    st0 = st.copy()
+    st0["v"] = 0
+    st0["omega"] = 0
+    out0 = ctx.compute(sc.ocean, st0)
+    assert not out0["Fdq"].any() and not out0["Fdf"].any() and out0["n_quadratic"].sum() == 0
+    # scaling law (exact powers of two scale every fp32 term exactly)
+    st1 = st.copy()
+    st1["omega"] = 0
+    a = ctx.compute(sc.ocean, st1)
+    st1["v"] *= 2
+    b = ctx.compute(sc.ocean, st1)
+    assert np.array_equal(a["n_quadratic"], b["n_quadratic"])
+    np.testing.assert_allclose(b["Fdq"], 4 * a["Fdq"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(b["Fdf"], 2 * a["Fdf"], rtol=1e-12, atol=0)
