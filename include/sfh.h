@@ -107,6 +107,14 @@ int sfh_step_debug(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* s
 int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies,
                     sfh_info* d_out);
 
+/* Batched point queries with the same arithmetic as the per-face kernels (host buffers, synchronous):
+ *   sfh_query_depth          = Ocean::GetDepth(const glm::vec3&)          (Ocean.cpp:149-168), n points -> n floats
+ *   sfh_query_fluid_velocity = Ocean::GetFluidVelocity(const glm::vec3&)  (Ocean.cpp:198-201), n points -> 3n floats
+ * The reference calls these one point at a time from actuators and sensors (Thruster.cpp:130-139,
+ * Pressure.cpp:44); here they also let tests check rows a3-a8 of the scope table in isolation. */
+int sfh_query_depth(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint32_t n, float* depth_out);
+int sfh_query_fluid_velocity(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint32_t n, float* vel_out);
+
 /* Pinned host memory for states/out so the per-step copies are truly asynchronous. */
 int sfh_host_alloc(sfh_ctx* ctx, size_t bytes, void** out);
 int sfh_host_free(sfh_ctx* ctx, void* p);

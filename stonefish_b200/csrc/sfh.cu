@@ -619,6 +619,41 @@ int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* 
     return SFH_OK;
 }
 
+static int point_query(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint32_t n, float* out, bool velocity)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!ocean || (n && (!xyz || !out))) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ctx->step_in_flight) { int rc = sfh_sync(ctx); if (rc != SFH_OK) return rc; }
+    if (n == 0) return SFH_OK;
+    bool general = false;
+    int rc = stage_ocean(ctx, ocean, &general);
+    if (rc != SFH_OK) return rc;
+    float *d_in = nullptr, *d_out = nullptr;
+    const size_t out_floats = velocity ? 3 * (size_t)n : (size_t)n;
+    CU(ctx, cudaMalloc(&d_in, 3 * (size_t)n * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_out, out_floats * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(ctx, SFH_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemcpyAsync(d_in, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (velocity) k_query_velocity<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_in, n, ctx->d_ocean.p, d_out);
+    else k_query_depth<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_in, n, ocean->has_waves != 0, ctx->waves, d_out);
+    cudaMemcpyAsync(out, d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, SFH_ERR_CUDA, "point query: %s", cudaGetErrorString(e));
+    return SFH_OK;
+}
+
+int sfh_query_depth(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint32_t n, float* depth_out)
+{
+    return point_query(ctx, ocean, xyz, n, depth_out, false);
+}
+
+int sfh_query_fluid_velocity(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint32_t n, float* vel_out)
+{
+    return point_query(ctx, ocean, xyz, n, vel_out, true);
+}
+
 int sfh_host_alloc(sfh_ctx* ctx, size_t bytes, void** out)
 {
     if (!ctx || !out) return SFH_ERR_INVALID;

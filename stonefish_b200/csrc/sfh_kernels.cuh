@@ -160,9 +160,11 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_submerged(StepParams P)
     __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
 
     const uint32_t tid = threadIdx.x;
-    const uint64_t W = P.item_off[P.n_bodies], G = gridDim.x;
+    // effective grid = min(launched blocks, work items): every participating block owns >= 1 item, so the
+    // epilogue's [first block, last block] range of a body never contains a block that wrote no record
+    const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x, W);
+    if (blockIdx.x >= G) return;
     const uint32_t w0 = (uint32_t)((uint64_t)blockIdx.x * W / G), w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
-    if (w0 >= w1) return;
 
     const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
     if (CUR) stage_currents(s_cur, P.ocean, n_cur);
@@ -281,9 +283,11 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
     __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
 
     const uint32_t tid = threadIdx.x;
-    const uint64_t W = P.item_off[P.n_bodies], G = gridDim.x;
+    // effective grid = min(launched blocks, work items): every participating block owns >= 1 item, so the
+    // epilogue's [first block, last block] range of a body never contains a block that wrote no record
+    const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x, W);
+    if (blockIdx.x >= G) return;
     const uint32_t w0 = (uint32_t)((uint64_t)blockIdx.x * W / G), w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
-    if (w0 >= w1) return;
 
     const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
     if (CUR) stage_currents(s_cur, P.ocean, n_cur);
@@ -633,7 +637,7 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
     if (kind == KIND_SUBMERGED) {
         const uint32_t o0 = P.off_sub[b], o1 = P.off_sub[b + 1];
         if (o1 > o0) {
-            const uint64_t W = P.off_sub[P.n_bodies], G = P.grid_sub;
+            const uint64_t W = P.off_sub[P.n_bodies], G = min((uint64_t)P.grid_sub, W);
             const uint32_t k0 = block_of_item(o0, G, W), k1 = block_of_item(o1 - 1, G, W);
             for (uint32_t k = k0 + lane; k <= k1; k += 32) {
                 const PartialSub& r = P.part_sub[k + b];
@@ -645,7 +649,7 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
     } else if (kind == KIND_SURFACE) {
         const uint32_t o0 = P.off_surf[b], o1 = P.off_surf[b + 1];
         if (o1 > o0) {
-            const uint64_t W = P.off_surf[P.n_bodies], G = P.grid_surf;
+            const uint64_t W = P.off_surf[P.n_bodies], G = min((uint64_t)P.grid_surf, W);
             const uint32_t k0 = block_of_item(o0, G, W), k1 = block_of_item(o1 - 1, G, W);
             for (uint32_t k = k0 + lane; k <= k1; k += 32) {
                 const PartialSurf& r = P.part_surf[k + b];
@@ -724,6 +728,23 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
     if (dispatch && pos != SFH_POS_OUTSIDE && (st.flags & SFH_F_DAMPING)) // SolidEntity.cpp:1848-1849
         correct_forces(oc.density, o.Fdq, o.Tdq, o.Fdf, o.Tdf, st.Cd, st.Cf, st.T_O_basis);
     P.out[b] = o;
+}
+
+// point queries: Ocean::GetDepth(glm::vec3) / Ocean::GetFluidVelocity(glm::vec3) for n points
+__global__ void k_query_depth(const float* __restrict__ xyz, uint32_t n, bool waves, WavesDev wv, float* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    out[i] = waves ? get_depth<true>(wv, x, y, z) : z;
+}
+__global__ void k_query_velocity(const float* __restrict__ xyz, uint32_t n, const OceanDev* __restrict__ ocean, float* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F3 v = {0.f, 0.f, 0.f};
+    if (ocean->currents_enabled) v = fluid_velocity_general(ocean->currents, ocean->n_currents, F3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
+    out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
 }
 
 // wave field de-interleave: RGBA32F layer 0 (+ spill-over row) -> planar channel 0 / 1

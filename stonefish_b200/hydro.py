@@ -334,6 +334,24 @@ class HydroContext:
         """Device-resident step (sfh_step_device): asynchronous on the context's stream."""
         self._check(self.lib.sfh_step_device(self.ctx, C.byref(ocean_struct), d_states_ptr, n, d_out_ptr), "sfh_step_device")
 
+    def GetDepth(self, ocean: Ocean, points: np.ndarray) -> np.ndarray:
+        """Ocean::GetDepth(glm::vec3) for an [n,3] float32 array of world points."""
+        self._sync_waves(ocean)
+        p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(p.shape[0], dtype=np.float32)
+        o = ocean.to_struct()
+        self._check(self.lib.sfh_query_depth(self.ctx, C.byref(o), p.ctypes.data, p.shape[0], out.ctypes.data), "sfh_query_depth")
+        return out
+
+    def GetFluidVelocity(self, ocean: Ocean, points: np.ndarray) -> np.ndarray:
+        """Ocean::GetFluidVelocity(glm::vec3) for an [n,3] float32 array of world points."""
+        p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((p.shape[0], 3), dtype=np.float32)
+        o = ocean.to_struct()
+        self._check(self.lib.sfh_query_fluid_velocity(self.ctx, C.byref(o), p.ctypes.data, p.shape[0], out.ctypes.data),
+                    "sfh_query_fluid_velocity")
+        return out
+
     def host_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         self._check(self.lib.sfh_host_alloc(self.ctx, nbytes, C.byref(p)), "sfh_host_alloc")
