@@ -115,6 +115,12 @@ int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* 
 int sfh_query_depth(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint32_t n, float* depth_out);
 int sfh_query_fluid_velocity(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint32_t n, float* vel_out);
 
+/* On-device checks of the hand-written IEEE sequences the kernels use (stonefish_b200/csrc/sfh_packed.cuh):
+ *   which 0: square root, exhaustive over [2^-101, FLT_MAX]      which 2: shared-reciprocal division, n random pairs
+ *   which 1: division by 3, exhaustive over its domain            which 3: packed f32x2 operators vs scalar, n samples
+ * Writes the number of operands tested and of results that differ from the hardware's div.rn/sqrt.rn/add.rn/... */
+int sfh_selftest(sfh_ctx* ctx, uint32_t which, uint64_t n, uint64_t* tested_out, uint64_t* mismatches_out);
+
 /* Pinned host memory for states/out so the per-step copies are truly asynchronous. */
 int sfh_host_alloc(sfh_ctx* ctx, size_t bytes, void** out);
 int sfh_host_free(sfh_ctx* ctx, void* p);

@@ -98,6 +98,7 @@ PROTOTYPES = {
     "sfh_step_device": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_query_depth": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_query_fluid_velocity": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sfh_selftest": (C.c_int, [_ctx, C.c_uint32, C.c_uint64, _P(C.c_uint64), _P(C.c_uint64)]),
     "sfh_host_alloc": (C.c_int, [_ctx, C.c_size_t, _P(C.c_void_p)]),
     "sfh_host_free": (C.c_int, [_ctx, C.c_void_p]),
     "sfh_set_profiling": (C.c_int, [_ctx, C.c_int]),

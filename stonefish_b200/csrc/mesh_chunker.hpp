@@ -2,19 +2,22 @@
 //
 // Input  : what the reference's Mesh exposes (OpenGLDataStructs.h:120-262): strided vertex positions and
 //          3 x u32 vertex ids per face.
-// Output : fixed-stride chunks, each holding <= SFH_CH_FACES faces and the <= SFH_CH_VERTS distinct
-//          vertices they reference:
-//              +0     u32 n_verts, u32 n_faces, u32 first_slot, u32 pad
-//              +16    float x[SFH_CH_VERTS]      (only the first n_verts are ever read)
-//              +1040  float y[SFH_CH_VERTS]
-//              +2064  float z[SFH_CH_VERTS]
-//              +3088  u32   face[SFH_CH_FACES]   local ids packed i0 | i1<<8 | i2<<16
-//          so a thread block transforms every vertex of a chunk ONCE into shared memory (the reference
-//          transforms each vertex once per incident face, SolidEntity.cpp:1343-1345 — same bits either way)
-//          and faces read 4 bytes of indices instead of 12.
-// Faces are Morton-ordered by centroid first (unless SFH_MESH_KEEP_ORDER) so that consecutive faces share
-// vertices; the per-body sums are order-independent within the fp64 contract and the class counts exactly.
-// `orig_face[slot]` maps a chunk slot back to the caller's face index (debug codes only).
+// Output : a packed stream of chunks, each holding <= SFH_CH_FACES faces and the <= SFH_CH_VERTS distinct
+//          vertices they reference, sized and aligned so that ONE bulk async copy (cp.async.bulk, 16-byte
+//          granularity) brings a whole chunk into shared memory:
+//              +0                u32 n_verts, u32 n_faces, u32 next_bytes, u32 first_slot
+//              +16               float x[nv4]        nv4 = n_verts rounded up to a multiple of 4
+//              +16 + 4*nv4       float y[nv4]
+//              +16 + 8*nv4       float z[nv4]
+//              +16 + 12*nv4      u32   face[nf4]     local ids packed i0 | i1<<8 | i2<<16, nf4 = n_faces up to 4
+//          `next_bytes` is the size of the FOLLOWING chunk of the same mesh (0 for the last), so a block can
+//          issue the copy of chunk c+1 while it still works on chunk c without a dependent header read.
+//          chunk_off[c] (16-byte units, n_chunks+1 entries) gives random access for a block's first chunk.
+// A thread block transforms every vertex of a chunk ONCE into shared memory (the reference transforms each vertex
+// once per incident face, SolidEntity.cpp:1343-1345 — same bits either way) and faces read 4 bytes of indices
+// instead of 12. Faces are Morton-ordered by centroid first (unless SFH_MESH_KEEP_ORDER) so that consecutive
+// faces share vertices; the per-body sums are order-independent within the fp64 contract and the class counts
+// exactly. `orig_face[c*SFH_CH_FACES + slot]` maps a chunk slot back to the caller's face index (debug codes).
 #pragma once
 
 #include <algorithm>
@@ -25,19 +28,16 @@
 #define SFH_CH_FACES 256u
 #define SFH_CH_VERTS 256u
 #define SFH_CH_HDR_BYTES 16u
-#define SFH_CH_X_OFF SFH_CH_HDR_BYTES
-#define SFH_CH_Y_OFF (SFH_CH_X_OFF + 4u * SFH_CH_VERTS)
-#define SFH_CH_Z_OFF (SFH_CH_Y_OFF + 4u * SFH_CH_VERTS)
-#define SFH_CH_F_OFF (SFH_CH_Z_OFF + 4u * SFH_CH_VERTS)
-#define SFH_CH_BYTES (SFH_CH_F_OFF + 4u * SFH_CH_FACES) /* 4112 = 257 * 16 */
+#define SFH_CH_MAX_BYTES (SFH_CH_HDR_BYTES + 12u * SFH_CH_VERTS + 4u * SFH_CH_FACES) /* 4112 */
 
 namespace sfh {
 
 struct ChunkedMesh {
-    std::vector<uint8_t> chunks;     // n_chunks * SFH_CH_BYTES
+    std::vector<uint8_t> chunks;     // packed chunk stream
+    std::vector<uint32_t> chunk_off; // n_chunks + 1 offsets into `chunks`, in 16-byte units
     std::vector<uint32_t> orig_face; // n_chunks * SFH_CH_FACES, 0xFFFFFFFF for unused slots
     uint32_t n_chunks = 0, n_faces = 0, n_verts = 0, n_chunk_verts = 0;
-    uint64_t device_bytes = 0; // bytes one evaluation reads: headers + 12 B per stored vertex + 4 B per face
+    uint64_t device_bytes = 0; // bytes one evaluation reads (= chunks.size())
 };
 
 inline uint64_t morton_spread21(uint64_t v)
@@ -97,23 +97,34 @@ inline bool chunk_mesh(const void* pos, size_t stride, uint32_t n_verts, const u
     std::vector<uint32_t> stamp(n_verts, 0xFFFFFFFFu);
     std::vector<uint16_t> local(n_verts, 0);
 
+    // staging of the chunk being filled
+    std::vector<float> cx(SFH_CH_VERTS), cy(SFH_CH_VERTS), cz(SFH_CH_VERTS);
+    std::vector<uint32_t> cf(SFH_CH_FACES);
     uint32_t chunk_id = 0, nv = 0, nf = 0;
-    auto begin_chunk = [&]() {
-        out.chunks.resize((size_t)(chunk_id + 1) * SFH_CH_BYTES, 0);
-        out.orig_face.resize((size_t)(chunk_id + 1) * SFH_CH_FACES, 0xFFFFFFFFu);
-        nv = 0;
-        nf = 0;
-    };
+    size_t prev_hdr = (size_t)-1;
+
     auto end_chunk = [&]() {
-        uint8_t* base = out.chunks.data() + (size_t)chunk_id * SFH_CH_BYTES;
-        uint32_t hdr[4] = {nv, nf, chunk_id * SFH_CH_FACES, 0};
-        std::memcpy(base, hdr, sizeof(hdr));
+        const uint32_t nv4 = (nv + 3u) & ~3u, nf4 = (nf + 3u) & ~3u;
+        const uint32_t bytes = SFH_CH_HDR_BYTES + 12u * nv4 + 4u * nf4;
+        const size_t base = out.chunks.size();
+        out.chunk_off.push_back((uint32_t)(base / 16));
+        out.chunks.resize(base + bytes, 0);
+        uint8_t* p = out.chunks.data() + base;
+        const uint32_t hdr[4] = {nv, nf, 0u, chunk_id * SFH_CH_FACES};
+        std::memcpy(p, hdr, sizeof(hdr));
+        std::memcpy(p + 16, cx.data(), 4 * nv);
+        std::memcpy(p + 16 + 4 * nv4, cy.data(), 4 * nv);
+        std::memcpy(p + 16 + 8 * nv4, cz.data(), 4 * nv);
+        std::memcpy(p + 16 + 12 * nv4, cf.data(), 4 * nf);
+        if (prev_hdr != (size_t)-1) std::memcpy(out.chunks.data() + prev_hdr + 8, &bytes, 4); // previous.next_bytes
+        prev_hdr = base;
         out.n_chunk_verts += nv;
-        out.device_bytes += SFH_CH_HDR_BYTES + 12ull * nv + 4ull * nf;
+        out.orig_face.resize((size_t)(chunk_id + 1) * SFH_CH_FACES, 0xFFFFFFFFu);
         ++chunk_id;
+        nv = nf = 0;
     };
 
-    if (n_faces > 0) begin_chunk();
+    std::vector<uint32_t> slot_face(SFH_CH_FACES);
     for (uint32_t i = 0; i < n_faces; ++i) {
         const uint32_t f = order[i];
         const uint32_t* id = faces + 3 * (size_t)f;
@@ -124,10 +135,10 @@ inline bool chunk_mesh(const void* pos, size_t stride, uint32_t n_verts, const u
             if (!seen) ++fresh;
         }
         if (nf == SFH_CH_FACES || nv + fresh > SFH_CH_VERTS) {
+            const uint32_t done = nf;
             end_chunk();
-            begin_chunk();
+            for (uint32_t s = 0; s < done; ++s) out.orig_face[(size_t)(chunk_id - 1) * SFH_CH_FACES + s] = slot_face[s];
         }
-        uint8_t* base = out.chunks.data() + (size_t)chunk_id * SFH_CH_BYTES;
         uint32_t packed = 0;
         for (int k = 0; k < 3; ++k) {
             const uint32_t v = id[k];
@@ -135,19 +146,23 @@ inline bool chunk_mesh(const void* pos, size_t stride, uint32_t n_verts, const u
                 stamp[v] = chunk_id;
                 local[v] = (uint16_t)nv;
                 const float* p = vptr(v);
-                std::memcpy(base + SFH_CH_X_OFF + 4 * nv, &p[0], 4);
-                std::memcpy(base + SFH_CH_Y_OFF + 4 * nv, &p[1], 4);
-                std::memcpy(base + SFH_CH_Z_OFF + 4 * nv, &p[2], 4);
+                cx[nv] = p[0]; cy[nv] = p[1]; cz[nv] = p[2];
                 ++nv;
             }
             packed |= (uint32_t)local[v] << (8 * k);
         }
-        std::memcpy(base + SFH_CH_F_OFF + 4 * nf, &packed, 4);
-        out.orig_face[(size_t)chunk_id * SFH_CH_FACES + nf] = f;
+        cf[nf] = packed;
+        slot_face[nf] = f;
         ++nf;
     }
-    if (n_faces > 0) end_chunk();
+    if (nf > 0) {
+        const uint32_t done = nf;
+        end_chunk();
+        for (uint32_t s = 0; s < done; ++s) out.orig_face[(size_t)(chunk_id - 1) * SFH_CH_FACES + s] = slot_face[s];
+    }
+    out.chunk_off.push_back((uint32_t)(out.chunks.size() / 16));
     out.n_chunks = chunk_id;
+    out.device_bytes = out.chunks.size();
     return true;
 }
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "sfh_kernels.cuh"
+#include "sfh_selftest.cuh"
 
 using namespace sfh;
 
@@ -213,7 +214,7 @@ int sync_mesh_table(sfh_ctx* ctx)
     if ((rc = ensure_pin(ctx, ctx->h_mesh_table, n * sizeof(MeshDev))) != SFH_OK) return rc;
     MeshDev* h = static_cast<MeshDev*>(ctx->h_mesh_table.p);
     CU(ctx, cudaStreamSynchronize(ctx->stream)); // previous async copy from this staging buffer is done
-    for (size_t i = 0; i < ctx->meshes.size(); ++i) h[i] = ctx->meshes[i].live ? ctx->meshes[i].dev : MeshDev{nullptr, nullptr, 0, 0};
+    for (size_t i = 0; i < ctx->meshes.size(); ++i) h[i] = ctx->meshes[i].live ? ctx->meshes[i].dev : MeshDev{nullptr, nullptr, nullptr, 0, 0};
     CU(ctx, cudaMemcpyAsync(ctx->d_meshes.p, h, ctx->meshes.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
     ctx->mesh_table_dirty = false;
     return SFH_OK;
@@ -494,13 +495,16 @@ int sfh_mesh_upload(sfh_ctx* ctx, const void* pos, size_t stride_bytes, uint32_t
     hm.stats.algorithmic_bytes = 12ull * n_faces + 12ull * n_verts;
     hm.dev.n_chunks = cm.n_chunks; hm.dev.n_faces = n_faces;
     if (cm.n_chunks) {
-        uint8_t *d_chunks = nullptr, *d_orig = nullptr;
+        uint8_t *d_chunks = nullptr, *d_off = nullptr, *d_orig = nullptr;
         int rc;
         if ((rc = arena_alloc(ctx, cm.chunks.size(), &d_chunks)) != SFH_OK) return rc;
+        if ((rc = arena_alloc(ctx, cm.chunk_off.size() * sizeof(uint32_t), &d_off)) != SFH_OK) return rc;
         if ((rc = arena_alloc(ctx, cm.orig_face.size() * sizeof(uint32_t), &d_orig)) != SFH_OK) return rc;
         CU(ctx, cudaMemcpy(d_chunks, cm.chunks.data(), cm.chunks.size(), cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(d_off, cm.chunk_off.data(), cm.chunk_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemcpy(d_orig, cm.orig_face.data(), cm.orig_face.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         hm.dev.chunks = d_chunks;
+        hm.dev.chunk_off = reinterpret_cast<const uint32_t*>(d_off);
         hm.dev.orig_face = reinterpret_cast<const uint32_t*>(d_orig);
     }
     hm.live = true;
@@ -652,6 +656,26 @@ int sfh_query_depth(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint
 int sfh_query_fluid_velocity(sfh_ctx* ctx, const sfh_ocean* ocean, const float* xyz, uint32_t n, float* vel_out)
 {
     return point_query(ctx, ocean, xyz, n, vel_out, true);
+}
+
+int sfh_selftest(sfh_ctx* ctx, uint32_t which, uint64_t n, uint64_t* tested_out, uint64_t* mismatches_out)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (which > 3 || !tested_out || !mismatches_out) return fail(ctx, SFH_ERR_INVALID, "bad selftest arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    CU(ctx, cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), ctx->stream);
+    k_selftest<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(which, n, d, d + 1);
+    unsigned long long h[3] = {0, 0, 0};
+    cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, SFH_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+    *mismatches_out = h[0];
+    *tested_out = h[1];
+    if (h[0]) fail(ctx, SFH_OK, "selftest %u: %llu mismatches, e.g. operand/index 0x%llx", which, h[0], h[2] & ~(1ull << 63));
+    return SFH_OK;
 }
 
 int sfh_host_alloc(sfh_ctx* ctx, size_t bytes, void** out)

@@ -18,7 +18,8 @@ namespace sfh {
 // device-side data
 // ---------------------------------------------------------------------------------------------
 struct MeshDev {
-    const uint8_t* chunks;     // n_chunks * SFH_CH_BYTES
+    const uint8_t* chunks;     // packed chunk stream (mesh_chunker.hpp)
+    const uint32_t* chunk_off; // n_chunks + 1 offsets into `chunks`, 16-byte units
     const uint32_t* orig_face; // n_chunks * SFH_CH_FACES (debug only)
     uint32_t n_chunks;
     uint32_t n_faces;
@@ -39,8 +40,11 @@ struct BodyDev {
     uint32_t flags;  // BF_*
     uint32_t kind;   // KIND_*
     uint32_t n_chunks;
+    uint32_t n_faces;
+    const uint8_t* chunks;     // 16 bytes read together by the chunk prefetcher:
+    uint32_t first_bytes;      //   chunks pointer + size of chunk 0
     uint32_t pad;
-    const uint8_t* chunks;
+    const uint32_t* chunk_off;
     const uint32_t* orig_face;
 };
 

@@ -147,127 +147,11 @@ __device__ __forceinline__ void spill_cpack(uint64_t& cpack, uint32_t* s_cls)
     cpack = 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_submerged — SolidEntity::ComputeHydrodynamicForcesSubmerged (SolidEntity.cpp:1749-1791)
-// ---------------------------------------------------------------------------------------------
-template <int CUR, bool DEBUG>
-__global__ void __launch_bounds__(SFH_BLOCK) k_submerged(StepParams P)
-{
-    __shared__ float4 s_v[SFH_CH_VERTS];
-    __shared__ BodyDev s_body;
-    __shared__ double s_red[SFH_BLOCK / 32][SFH_NACC_SUB];
-    __shared__ uint32_t s_cnt[4];
-    __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
+} // namespace sfh
 
-    const uint32_t tid = threadIdx.x;
-    // effective grid = min(launched blocks, work items): every participating block owns >= 1 item, so the
-    // epilogue's [first block, last block] range of a body never contains a block that wrote no record
-    const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x, W);
-    if (blockIdx.x >= G) return;
-    const uint32_t w0 = (uint32_t)((uint64_t)blockIdx.x * W / G), w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
+#include "sfh_submerged.cuh" // k_submerged (two faces per thread, packed fp32)
 
-    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
-    if (CUR) stage_currents(s_cur, P.ocean, n_cur);
-    if (tid < 4) s_cnt[tid] = 0;
-
-    double acc[SFH_NACC_SUB];
-#pragma unroll
-    for (int i = 0; i < SFH_NACC_SUB; ++i) acc[i] = 0.0;
-    uint32_t epack = 0, since_spill = 0;
-
-    uint32_t b = body_of_item(P.item_off, P.n_bodies, w0);
-    uint32_t b_end = P.item_off[b + 1];
-    load_body(&s_body, P.bodies + b);
-    __syncthreads();
-    BodyRegs B;
-
-    auto flush = [&](uint32_t body) {
-        spill_epack(epack, s_cnt);
-        since_spill = 0;
-        PartialSub* rec = reinterpret_cast<PartialSub*>(P.partials) + (blockIdx.x + body);
-        __syncthreads();
-        block_reduce_store<SFH_NACC_SUB>(acc, s_red, rec->a);
-        if (tid < 3) { (&rec->n_degenerate)[tid] = s_cnt[tid]; }
-        __syncthreads();
-        if (tid < 4) s_cnt[tid] = 0;
-    };
-    auto fetch_regs = [&]() {
-        B.p = F3{s_body.p[0], s_body.p[1], s_body.p[2]};
-        B.v = F3{s_body.v[0], s_body.v[1], s_body.v[2]};
-        B.omega = F3{s_body.omega[0], s_body.omega[1], s_body.omega[2]};
-        B.cur = F3{s_body.cur[0], s_body.cur[1], s_body.cur[2]};
-    };
-    fetch_regs();
-
-    for (uint32_t w = w0; w < w1; ++w) {
-        if (w >= b_end) {
-            flush(b);
-            do { ++b; b_end = P.item_off[b + 1]; } while (w >= b_end);
-            load_body(&s_body, P.bodies + b);
-            __syncthreads();
-            fetch_regs();
-        }
-        const uint32_t c = w - P.item_off[b];
-        const uint8_t* __restrict__ ch = s_body.chunks + (size_t)c * SFH_CH_BYTES;
-        const uint2 hdr = __ldg(reinterpret_cast<const uint2*>(ch));
-        const uint32_t nv = hdr.x, nf = hdr.y;
-
-        // faces first (independent of the barrier), then vertices: each transformed once per chunk
-        uint32_t fpk[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t slot = tid + k * SFH_BLOCK;
-            fpk[k] = slot < nf ? __ldg(reinterpret_cast<const uint32_t*>(ch + SFH_CH_F_OFF) + slot) : 0u;
-        }
-        float vx[2], vy[2], vz[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t i = tid + k * SFH_BLOCK;
-            if (i < nv) {
-                vx[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_X_OFF) + i);
-                vy[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_Y_OFF) + i);
-                vz[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_Z_OFF) + i);
-            }
-        }
-        __syncthreads(); // previous chunk's readers are done with s_v
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t i = tid + k * SFH_BLOCK;
-            if (i < nv) {
-                F3 pw = xform(s_body.R, s_body.t, vx[k], vy[k], vz[k]);
-                s_v[i] = make_float4(pw.x, pw.y, pw.z, 0.f);
-            }
-        }
-        __syncthreads();
-
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t slot = tid + k * SFH_BLOCK;
-            if (slot < nf) {
-                const float4 a4 = s_v[fpk[k] & 255u], b4 = s_v[(fpk[k] >> 8) & 255u], c4 = s_v[(fpk[k] >> 16) & 255u];
-                const F3 p1 = {a4.x, a4.y, a4.z}, p2 = {b4.x, b4.y, b4.z}, p3 = {c4.x, c4.y, c4.z};
-                uint32_t code = 7;
-                F3 fv1 = p2 - p1;
-                F3 fv2 = p3 - p1;
-                F3 fn = cross(fv1, fv2);
-                float len = length2(fn);
-                if (len < 1e-12f) {
-                    epack += 1u;
-                    code |= SFH_FACE_DEGENERATE;
-                } else {
-                    len = fsqrt(len);
-                    F3 fn1 = fn / len;
-                    float A = fdiv(len, 2.f);
-                    F3 fc = ((p1 + p2) + p3) / 3.f;
-                    code |= damping_terms<CUR>(B, s_cur, n_cur, fc, fn1, A, acc, epack);
-                }
-                if (DEBUG) P.codes[P.code_base[b] + s_body.orig_face[(size_t)c * SFH_CH_FACES + slot]] = (uint8_t)code;
-            }
-        }
-        if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); since_spill = 0; }
-    }
-    flush(b);
-}
+namespace sfh {
 
 // ---------------------------------------------------------------------------------------------
 // k_surface — SolidEntity::ComputeHydrodynamicForcesSurface (SolidEntity.cpp:1337-1687)
@@ -276,6 +160,7 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_submerged(StepParams P)
 template <bool WAVES, int CUR, bool DEBUG>
 __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
 {
+    __shared__ ChunkPipe s_pipe;
     __shared__ float4 s_v[SFH_CH_VERTS]; // world x,y,z and depth
     __shared__ BodyDev s_body;
     __shared__ double s_red[SFH_BLOCK / 32][SFH_NACC_SURF];
@@ -287,7 +172,11 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
     // epilogue's [first block, last block] range of a body never contains a block that wrote no record
     const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x, W);
     if (blockIdx.x >= G) return;
-    const uint32_t w0 = (uint32_t)((uint64_t)blockIdx.x * W / G), w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
+    ItemWalk it;
+    it.w = (uint32_t)((uint64_t)blockIdx.x * W / G);
+    it.w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
+    it.s = 0;
+    it.parity = 0;
 
     const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
     if (CUR) stage_currents(s_cur, P.ocean, n_cur);
@@ -300,10 +189,12 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
     uint32_t epack = 0, since_spill = 0;
     uint64_t cpack = 0;
 
-    uint32_t b = body_of_item(P.item_off, P.n_bodies, w0);
-    uint32_t b_end = P.item_off[b + 1];
-    load_body(&s_body, P.bodies + b);
-    __syncthreads();
+    it.b = body_of_item(P.item_off, P.n_bodies, it.w);
+    it.b_begin = P.item_off[it.b];
+    it.b_end = P.item_off[it.b + 1];
+    load_body(&s_body, P.bodies + it.b);
+    pipe_init(s_pipe); // includes the barrier that publishes s_body
+    if (tid == 0) walk_issue_first(s_pipe, it, s_body);
     BodyRegs B;
     F3 p0;
     bool buoy, damp;
@@ -331,41 +222,21 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
     };
     fetch_regs();
 
-    for (uint32_t w = w0; w < w1; ++w) {
-        if (w >= b_end) {
-            flush(b);
-            do { ++b; b_end = P.item_off[b + 1]; } while (w >= b_end);
-            load_body(&s_body, P.bodies + b);
-            __syncthreads();
-            fetch_regs();
-        }
-        const uint32_t c = w - P.item_off[b];
-        const uint8_t* __restrict__ ch = s_body.chunks + (size_t)c * SFH_CH_BYTES;
-        const uint2 hdr = __ldg(reinterpret_cast<const uint2*>(ch));
-        const uint32_t nv = hdr.x, nf = hdr.y;
+    for (;;) {
+        pipe_wait(s_pipe, it.s, (it.parity >> it.s) & 1u);
+        it.parity ^= 1u << it.s;
+        const ChunkView cv = chunk_view(s_pipe.buf[it.s]);
+        const uint32_t nf = cv.nf, b = it.b, c = it.w - it.b_begin;
 
-        uint32_t fpk[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t slot = tid + k * SFH_BLOCK;
-            fpk[k] = slot < nf ? __ldg(reinterpret_cast<const uint32_t*>(ch + SFH_CH_F_OFF) + slot) : 0u;
-        }
-        float vx[2], vy[2], vz[2];
+        __syncthreads(); // every thread is done with the previous chunk: s_v and the other staging buffer are free
+        const uint8_t* nsrc = nullptr;
+        uint32_t nbytes = 0;
+        if (tid == 0) walk_issue_next(s_pipe, it, P, cv.next_bytes, nsrc, nbytes);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const uint32_t i = tid + k * SFH_BLOCK;
-            if (i < nv) {
-                vx[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_X_OFF) + i);
-                vy[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_Y_OFF) + i);
-                vz[k] = __ldg(reinterpret_cast<const float*>(ch + SFH_CH_Z_OFF) + i);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t i = tid + k * SFH_BLOCK;
-            if (i < nv) {
-                F3 pw = xform(s_body.R, s_body.t, vx[k], vy[k], vz[k]);
+            if (i < cv.nv) {
+                F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
                 // Ocean::GetDepth per vertex (SolidEntity.cpp:1349-1351): same bits for every incident face
                 s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(wv, pw.x, pw.y, pw.z));
             }
@@ -376,7 +247,7 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
         for (int k = 0; k < 2; ++k) {
             const uint32_t slot = tid + k * SFH_BLOCK;
             if (slot >= nf) continue;
-            const uint32_t fp = k ? fpk[1] : fpk[0];
+            const uint32_t fp = cv.faces[slot];
             const float4 a4 = s_v[fp & 255u], b4 = s_v[(fp >> 8) & 255u], c4 = s_v[(fp >> 16) & 255u];
             F3 p1 = {a4.x, a4.y, a4.z}, p2 = {b4.x, b4.y, b4.z}, p3 = {c4.x, c4.y, c4.z};
             const float d0 = a4.w, d1 = b4.w, d2 = c4.w;
@@ -442,8 +313,21 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
             if (DEBUG) P.codes[P.code_base[b] + s_body.orig_face[(size_t)c * SFH_CH_FACES + slot]] = (uint8_t)code;
         }
         if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); spill_cpack(cpack, s_cnt + 4); since_spill = 0; }
+
+        if (++it.w >= it.w1) break;
+        it.s ^= 1;
+        it.src = nsrc;
+        it.bytes = nbytes;
+        if (it.w >= it.b_end) {
+            flush(it.b);
+            do { ++it.b; it.b_end = P.item_off[it.b + 1]; } while (it.w >= it.b_end);
+            it.b_begin = P.item_off[it.b];
+            load_body(&s_body, P.bodies + it.b);
+            __syncthreads();
+            fetch_regs();
+        }
     }
-    flush(b);
+    flush(it.b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -523,7 +407,7 @@ __global__ void __launch_bounds__(1024) k_prologue(PrologueParams P)
                 if (dispatch && !(st.flags & SFH_F_BUOYANT)) buoyancy = false; // SolidEntity.cpp:1844
                 kind = KIND_SURFACE;
             }
-            MeshDev m = {nullptr, nullptr, 0, 0};
+            MeshDev m = {nullptr, nullptr, nullptr, 0, 0};
             if (st.mesh_id < P.n_meshes) m = P.meshes[st.mesh_id];
             else if (kind != KIND_NONE) atomicOr(P.status, 1u);
             // glMatrixFromTransform / glVectorFromVector (OpenGLDataStructs.cpp:148-171)
@@ -538,8 +422,11 @@ __global__ void __launch_bounds__(1024) k_prologue(PrologueParams P)
             bd.flags = (damping ? BF_DAMPING : 0u) | (buoyancy ? BF_BUOYANCY : 0u);
             bd.kind = kind | (pos << 8);
             bd.n_chunks = (kind != KIND_NONE) ? m.n_chunks : 0u;
-            bd.pad = m.n_faces;
+            bd.n_faces = m.n_faces;
             bd.chunks = m.chunks;
+            bd.first_bytes = m.n_chunks ? (m.chunk_off[1] - m.chunk_off[0]) * 16u : 0u;
+            bd.pad = 0;
+            bd.chunk_off = m.chunk_off;
             bd.orig_face = m.orig_face;
             P.bodies[i] = bd;
             if (kind == KIND_SUBMERGED) n_sub = bd.n_chunks;
@@ -675,7 +562,7 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
     sfh_info o;
     for (int k = 0; k < 3; ++k) { o.Fb[k] = 0; o.Tb[k] = 0; o.Fdq[k] = 0; o.Tdq[k] = 0; o.Fdf[k] = 0; o.Tdf[k] = 0; }
     o.Swet = 0; o.Vsub = 0; o.wrote_buoyancy = 0; o.wrote_damping = 0; o.position = pos; o.reserved = 0;
-    o.n_faces = (kind != KIND_NONE) ? bd.pad : 0u;
+    o.n_faces = (kind != KIND_NONE) ? bd.n_faces : 0u;
     o.n_degenerate = cnt[0]; o.n_quadratic = cnt[1]; o.n_skin = cnt[2];
     for (int k = 0; k < 8; ++k) o.class_count[k] = cnt[3 + k];
 

@@ -1,0 +1,279 @@
+// sfh_submerged.cuh — k_submerged: SolidEntity::ComputeHydrodynamicForcesSubmerged (SolidEntity.cpp:1749-1791)
+// over (body, chunk) work items, two faces per thread on the packed fp32 pipe.
+//
+// Per chunk a block of 128 threads
+//   1. transforms the chunk's <=256 vertices ONCE into shared memory (reference: once per incident face,
+//      SolidEntity.cpp:1755-1757 — identical bits),
+//   2. has the NEXT chunk (of this or of the next body) already in flight as one bulk async copy (sfh_chunkpipe.cuh),
+//   3. evaluates faces tid and tid+128 as the two lanes of FADD2/FMUL2/FFMA2 instructions, with the IEEE
+//      divisions and square roots written out (sfh_packed.cuh),
+//   4. adds the fp32 per-face terms into per-thread fp64 accumulators.
+// Accumulators are reduced per (block, body) and written as one partial record (see sfh_kernels.cuh).
+#pragma once
+
+#include "sfh_chunkpipe.cuh"
+#include "sfh_packed.cuh"
+
+namespace sfh {
+
+// fn / len for three numerators sharing one reciprocal (len >= 1e-6 here, and |fn_i| <= ~len). The shared form
+// is proven for numerators that are zero or >= 2^-36 in magnitude (quotient zero or >= 2^-100, remainder exact);
+// anything else — never seen on real meshes — takes the hardware division.
+#define SFH_NUM_KEY 0x5affffffu /* 2*bits(2^-36) - 1 */
+__device__ __forceinline__ V3P normalize_by(V3P fn, P2 len)
+{
+    const P2 nlen = neg(len);
+    const P2 r = refined_rcp2(len, nlen);
+    V3P q = {ieee_div_r2(fn.x, nlen, r), ieee_div_r2(fn.y, nlen, r), ieee_div_r2(fn.z, nlen, r)};
+    const uint32_t m0 = min(min(tiny_key(lo(fn.x)), tiny_key(lo(fn.y))), tiny_key(lo(fn.z)));
+    const uint32_t m1 = min(min(tiny_key(hi(fn.x)), tiny_key(hi(fn.y))), tiny_key(hi(fn.z)));
+    if (min(m0, m1) < SFH_NUM_KEY) {
+        q.x = pk(__fdiv_rn(lo(fn.x), lo(len)), __fdiv_rn(hi(fn.x), hi(len)));
+        q.y = pk(__fdiv_rn(lo(fn.y), lo(len)), __fdiv_rn(hi(fn.y), hi(len)));
+        q.z = pk(__fdiv_rn(lo(fn.z), lo(len)), __fdiv_rn(hi(fn.z), hi(len)));
+    }
+    return q;
+}
+
+// ((a + b) + c) / 3.f per component
+__device__ __forceinline__ V3P centroid3(V3P a, V3P b, V3P c)
+{
+    const V3P s = (a + b) + c;
+    V3P q = {ieee_div3_2(s.x), ieee_div3_2(s.y), ieee_div3_2(s.z)};
+    if (any_tiny_nonzero(s)) {
+        q.x = pk(__fdiv_rn(lo(s.x), 3.f), __fdiv_rn(hi(s.x), 3.f));
+        q.y = pk(__fdiv_rn(lo(s.y), 3.f), __fdiv_rn(hi(s.y), 3.f));
+        q.z = pk(__fdiv_rn(lo(s.z), 3.f), __fdiv_rn(hi(s.z), 3.f));
+    }
+    return q;
+}
+
+struct BodyP2 { // per-body constants broadcast to both lanes
+    V3P p, v, omega, cur;
+};
+
+// Damping block for a pair of faces (SolidEntity.cpp:1771-1790 / 1661-1683). mA/mB: the face exists and is not
+// degenerate. Returns SFH_FACE_QUADRATIC / SFH_FACE_SKIN bits for A in bits 0..7 and for B in bits 8..15.
+template <int CUR>
+__device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_current* s_cur, uint32_t n_cur, V3P fc, V3P fn1, P2 A,
+                                                 bool mA, bool mB, double* acc, uint32_t& epack)
+{
+    V3P fluid = B.cur;
+    if (CUR) {
+        const F3 fa = fluid_velocity_general(s_cur, n_cur, F3{lo(fc.x), lo(fc.y), lo(fc.z)});
+        const F3 fb = fluid_velocity_general(s_cur, n_cur, F3{hi(fc.x), hi(fc.y), hi(fc.z)});
+        fluid = V3P{pk(fa.x, fb.x), pk(fa.y, fb.y), pk(fa.z, fb.z)};
+    }
+    const V3P r = fc - B.p;
+    const V3P vc = fluid - (B.v + cross(B.omega, r));
+    const P2 vc_n = dot(vc, fn1);
+    const V3P vn = fn1 * vc_n;
+    const V3P vt = vc - vn;
+    uint32_t code = 0;
+
+    const bool qA = mA && lo(vc_n) < -1e-12f, qB = mB && hi(vc_n) < -1e-12f;
+    if (__any_sync(SFH_FULL, qA | qB)) {
+        // vc_n < -1e-12 implies |vc|^2 > 1e-24 > 2^-101: inside ieee_sqrt2's range for every lane that is used
+        const P2 vmag2 = dot(vc, vc);
+        const V3P q = ((vc * ieee_sqrt2(vmag2)) * neg(vc_n)) * A;
+        const V3P tq = cross(r, q);
+        if (qA) {
+            acc[0] = dadd(acc[0], (double)lo(q.x));  acc[1] = dadd(acc[1], (double)lo(q.y));  acc[2] = dadd(acc[2], (double)lo(q.z));
+            acc[3] = dadd(acc[3], (double)lo(tq.x)); acc[4] = dadd(acc[4], (double)lo(tq.y)); acc[5] = dadd(acc[5], (double)lo(tq.z));
+            epack += 1u << 10;
+            code |= SFH_FACE_QUADRATIC;
+        }
+        if (qB) {
+            acc[0] = dadd(acc[0], (double)hi(q.x));  acc[1] = dadd(acc[1], (double)hi(q.y));  acc[2] = dadd(acc[2], (double)hi(q.z));
+            acc[3] = dadd(acc[3], (double)hi(tq.x)); acc[4] = dadd(acc[4], (double)hi(tq.y)); acc[5] = dadd(acc[5], (double)hi(tq.z));
+            epack += 1u << 10;
+            code |= SFH_FACE_QUADRATIC << 8;
+        }
+    }
+    const P2 vt2 = dot(vt, vt);
+    const bool sA = mA && lo(vt2) > 1e-9f, sB = mB && hi(vt2) > 1e-9f;
+    if (__any_sync(SFH_FULL, sA | sB)) {
+        const V3P s = vt * A;
+        const V3P ts = cross(r, s);
+        if (sA) {
+            acc[6] = dadd(acc[6], (double)lo(s.x));  acc[7] = dadd(acc[7], (double)lo(s.y));   acc[8] = dadd(acc[8], (double)lo(s.z));
+            acc[9] = dadd(acc[9], (double)lo(ts.x)); acc[10] = dadd(acc[10], (double)lo(ts.y)); acc[11] = dadd(acc[11], (double)lo(ts.z));
+            epack += 1u << 20;
+            code |= SFH_FACE_SKIN;
+        }
+        if (sB) {
+            acc[6] = dadd(acc[6], (double)hi(s.x));  acc[7] = dadd(acc[7], (double)hi(s.y));   acc[8] = dadd(acc[8], (double)hi(s.z));
+            acc[9] = dadd(acc[9], (double)hi(ts.x)); acc[10] = dadd(acc[10], (double)hi(ts.y)); acc[11] = dadd(acc[11], (double)hi(ts.z));
+            epack += 1u << 20;
+            code |= SFH_FACE_SKIN << 8;
+        }
+    }
+    return code;
+}
+
+// State of the block-wide walk over work items, shared by k_submerged and k_surface.
+// Thread 0 alone tracks where the staged chunk came from so it can chain the next copy.
+struct ItemWalk {
+    uint32_t w, w1, b, b_begin, b_end;
+    int s;               // staging buffer holding the current chunk
+    uint32_t parity;     // bit s = phase parity of staging buffer s
+    const uint8_t* src;  // thread 0: global address of the current chunk
+    uint32_t bytes;      // thread 0: its size
+};
+
+// thread 0: start the copy of the chunk of work item `w` of body `b` (random access through chunk_off)
+__device__ __forceinline__ void walk_issue_first(ChunkPipe& pipe, ItemWalk& it, const BodyDev& body)
+{
+    const uint32_t c = it.w - it.b_begin;
+    const uint32_t o0 = __ldg(body.chunk_off + c), o1 = __ldg(body.chunk_off + c + 1);
+    it.src = body.chunks + (size_t)o0 * 16u;
+    it.bytes = (o1 - o0) * 16u;
+    pipe_issue(pipe, it.s, it.src, it.bytes);
+}
+
+// thread 0, right after the block barrier that retires the previous chunk: chain the copy of item w+1 into the
+// other buffer — the following chunk of this body (size from the staged header) or chunk 0 of the next body
+// that has work (pointer and size read as one 16-byte load from its BodyDev record).
+__device__ __forceinline__ void walk_issue_next(ChunkPipe& pipe, ItemWalk& it, const StepParams& P, uint32_t next_bytes,
+                                                const uint8_t*& nsrc, uint32_t& nbytes)
+{
+    const uint32_t wn = it.w + 1;
+    if (wn >= it.w1) return;
+    if (wn < it.b_end) {
+        nsrc = it.src + it.bytes;
+        nbytes = next_bytes;
+    } else {
+        uint32_t nb = it.b + 1;
+        while (__ldg(P.item_off + nb + 1) <= wn) ++nb;
+        const uint4 rec = __ldg(reinterpret_cast<const uint4*>(&P.bodies[nb].chunks));
+        nsrc = reinterpret_cast<const uint8_t*>(((unsigned long long)rec.y << 32) | rec.x);
+        nbytes = rec.z;
+    }
+    pipe_issue(pipe, it.s ^ 1, nsrc, nbytes);
+}
+
+template <int CUR, bool DEBUG>
+__global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
+{
+    __shared__ ChunkPipe s_pipe;
+    __shared__ float4 s_v[SFH_CH_VERTS];
+    __shared__ BodyDev s_body;
+    __shared__ double s_red[SFH_BLOCK / 32][SFH_NACC_SUB];
+    __shared__ uint32_t s_cnt[4];
+    __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
+
+    const uint32_t tid = threadIdx.x;
+    const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x, W);
+    if (blockIdx.x >= G) return;
+    ItemWalk it;
+    it.w = (uint32_t)((uint64_t)blockIdx.x * W / G);
+    it.w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
+    it.s = 0;
+    it.parity = 0;
+
+    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
+    if (CUR) stage_currents(s_cur, P.ocean, n_cur);
+    if (tid < 4) s_cnt[tid] = 0;
+
+    double acc[SFH_NACC_SUB];
+#pragma unroll
+    for (int i = 0; i < SFH_NACC_SUB; ++i) acc[i] = 0.0;
+    uint32_t epack = 0, since_spill = 0;
+
+    it.b = body_of_item(P.item_off, P.n_bodies, it.w);
+    it.b_begin = P.item_off[it.b];
+    it.b_end = P.item_off[it.b + 1];
+    load_body(&s_body, P.bodies + it.b);
+    pipe_init(s_pipe); // includes the barrier that publishes s_body
+    if (tid == 0) walk_issue_first(s_pipe, it, s_body);
+
+    BodyP2 B;
+    auto fetch_regs = [&]() {
+        B.p = V3P{pk1(s_body.p[0]), pk1(s_body.p[1]), pk1(s_body.p[2])};
+        B.v = V3P{pk1(s_body.v[0]), pk1(s_body.v[1]), pk1(s_body.v[2])};
+        B.omega = V3P{pk1(s_body.omega[0]), pk1(s_body.omega[1]), pk1(s_body.omega[2])};
+        B.cur = V3P{pk1(s_body.cur[0]), pk1(s_body.cur[1]), pk1(s_body.cur[2])};
+    };
+    auto flush = [&](uint32_t body) {
+        spill_epack(epack, s_cnt);
+        since_spill = 0;
+        PartialSub* rec = reinterpret_cast<PartialSub*>(P.partials) + (blockIdx.x + body);
+        __syncthreads();
+        block_reduce_store<SFH_NACC_SUB>(acc, s_red, rec->a);
+        if (tid < 3) (&rec->n_degenerate)[tid] = s_cnt[tid];
+        __syncthreads();
+        if (tid < 4) s_cnt[tid] = 0;
+    };
+    fetch_regs();
+
+    for (;;) {
+        pipe_wait(s_pipe, it.s, (it.parity >> it.s) & 1u);
+        it.parity ^= 1u << it.s;
+        const uint8_t* buf = s_pipe.buf[it.s];
+        const ChunkView cv = chunk_view(buf);
+
+        __syncthreads(); // every thread is done with the previous chunk: s_v and the other staging buffer are free
+        const uint8_t* nsrc = nullptr;
+        uint32_t nbytes = 0;
+        if (tid == 0) walk_issue_next(s_pipe, it, P, cv.next_bytes, nsrc, nbytes);
+
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t i = tid + k * SFH_BLOCK;
+            if (i < cv.nv) {
+                const F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
+                s_v[i] = make_float4(pw.x, pw.y, pw.z, 0.f);
+            }
+        }
+        __syncthreads();
+
+        {
+            const uint32_t nf = cv.nf;
+            const bool vA = tid < nf, vB = tid + SFH_BLOCK < nf;
+            const uint32_t fA = vA ? cv.faces[tid] : 0u, fB = vB ? cv.faces[tid + SFH_BLOCK] : 0u;
+            const float4 a1 = s_v[fA & 255u], a2 = s_v[(fA >> 8) & 255u], a3 = s_v[(fA >> 16) & 255u];
+            const float4 b1 = s_v[fB & 255u], b2 = s_v[(fB >> 8) & 255u], b3 = s_v[(fB >> 16) & 255u];
+            const V3P p1 = {pk(a1.x, b1.x), pk(a1.y, b1.y), pk(a1.z, b1.z)};
+            const V3P p2 = {pk(a2.x, b2.x), pk(a2.y, b2.y), pk(a2.z, b2.z)};
+            const V3P p3 = {pk(a3.x, b3.x), pk(a3.y, b3.y), pk(a3.z, b3.z)};
+            const V3P fv1 = p2 - p1;
+            const V3P fv2 = p3 - p1;
+            const V3P fn = cross(fv1, fv2);
+            const P2 len2 = dot(fn, fn);
+            const bool dA = lo(len2) < 1e-12f, dB = hi(len2) < 1e-12f; // SolidEntity.cpp:1764
+            const bool mA = vA && !dA, mB = vB && !dB;
+            epack += (vA && dA ? 1u : 0u) + (vB && dB ? 1u : 0u);
+            uint32_t code = 0;
+            if (__any_sync(SFH_FULL, mA | mB)) {
+                // len2 >= 1e-12 > 2^-101 on every lane that is used
+                const P2 len = ieee_sqrt2(len2);
+                const V3P fn1 = normalize_by(fn, len);
+                const P2 A = len * pk1(0.5f); // len / 2.f, exact scaling
+                const V3P fc = centroid3(p1, p2, p3);
+                code = damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
+            }
+            if (DEBUG) {
+                const uint32_t* of = s_body.orig_face + (size_t)(it.w - it.b_begin) * SFH_CH_FACES;
+                if (vA) P.codes[P.code_base[it.b] + of[tid]] = (uint8_t)(7u | (dA ? SFH_FACE_DEGENERATE : 0u) | (code & 255u));
+                if (vB) P.codes[P.code_base[it.b] + of[tid + SFH_BLOCK]] = (uint8_t)(7u | (dB ? SFH_FACE_DEGENERATE : 0u) | (code >> 8));
+            }
+        }
+        if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); since_spill = 0; }
+
+        if (++it.w >= it.w1) break;
+        it.s ^= 1;
+        it.src = nsrc;
+        it.bytes = nbytes;
+        if (it.w >= it.b_end) {
+            flush(it.b);
+            do { ++it.b; it.b_end = P.item_off[it.b + 1]; } while (it.w >= it.b_end);
+            it.b_begin = P.item_off[it.b];
+            load_body(&s_body, P.bodies + it.b);
+            __syncthreads();
+            fetch_regs();
+        }
+    }
+    flush(it.b);
+}
+
+} // namespace sfh

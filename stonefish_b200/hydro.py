@@ -115,6 +115,8 @@ class Ocean:
     """What the integrators read from sf::Ocean (Ocean.cpp:139-211): liquid density, gravity, the list of
     velocity fields, `currentsEnabled`, and the wave field (`fftData`, an input here)."""
 
+    _wave_token = 0
+
     def __init__(self, density: float = 1000.0, gravity: float = 9.81):
         self.density = float(density)
         self.gravity = float(gravity)
@@ -123,7 +125,7 @@ class Ocean:
         self.fft_data: np.ndarray | None = None
         self.fft_size = 256
         self.grid_sizes = (893.0, 101.0, 21.0, 11.0)  # OpenGLOcean.cpp:70
-        self.waves_version = 0
+        self.waves_version = 0  # process-unique token of the current wave field (0 = none)
 
     def AddVelocityField(self, field: VelocityField):
         self.currents.append(field)
@@ -142,7 +144,8 @@ class Ocean:
             self.fft_data = np.ascontiguousarray(fft_data, dtype=np.float32).reshape(-1)
             self.fft_size = int(fft_size)
             self.grid_sizes = tuple(float(g) for g in grid_sizes)
-        self.waves_version += 1
+        Ocean._wave_token += 1
+        self.waves_version = Ocean._wave_token
 
     def hasWaves(self) -> bool:
         return self.fft_data is not None
@@ -299,10 +302,10 @@ class HydroContext:
 
     # -- per step
     def _sync_waves(self, ocean: Ocean):
-        if ocean.hasWaves() and self._waves_version != (id(ocean), ocean.waves_version):
+        if ocean.hasWaves() and self._waves_version != ocean.waves_version:
             w = ocean.waves_struct()
             self._check(self.lib.sfh_waves_upload(self.ctx, C.byref(w)), "sfh_waves_upload")
-            self._waves_version = (id(ocean), ocean.waves_version)
+            self._waves_version = ocean.waves_version
 
     def compute(self, ocean: Ocean, states: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """One recompute of all bodies: host buffers in, host buffers out (sfh_step)."""
