@@ -114,7 +114,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("SFH_LIB") or LIB_PATH  # SFH_LIB: A/B builds during kernel tuning
     if not os.path.exists(p):
         raise RuntimeError(f"{p} not found: the CUDA extension is not built and there is no CPU fallback "
                            "(make -C stonefish_b200/csrc)")

@@ -14,27 +14,37 @@
 namespace sfh {
 
 struct ChunkPipe { // in shared memory
-    alignas(16) uint8_t buf[2][SFH_CH_MAX_BYTES + 16];
+    alignas(16) uint8_t buf[2][SFH_CH_MAX_BYTES + 16]; // stride SFH_PIPE_BUF_STRIDE
     alignas(8) unsigned long long bar[2];
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#define SFH_PIPE_BUF_STRIDE (SFH_CH_MAX_BYTES + 16u)
+
+struct PipeAddr { // shared-window addresses, computed once per kernel and kept in registers
+    uint32_t bar0, buf0;
+};
+
 // call from all threads once; contains a __syncthreads()
-__device__ __forceinline__ void pipe_init(ChunkPipe& p)
+__device__ __forceinline__ PipeAddr pipe_init(ChunkPipe& p)
 {
+    PipeAddr a;
+    a.bar0 = smem_addr(&p.bar[0]);
+    a.buf0 = smem_addr(&p.buf[0][0]);
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&p.bar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&p.bar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a.bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a.bar0 + 8u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    return a;
 }
 
 // one thread: start the copy of `bytes` (multiple of 16) from global `src` (16-byte aligned) into buffer s
-__device__ __forceinline__ void pipe_issue(ChunkPipe& p, int s, const uint8_t* src, uint32_t bytes)
+__device__ __forceinline__ void pipe_issue(const PipeAddr& a, int s, const uint8_t* src, uint32_t bytes)
 {
-    const uint32_t bar = smem_addr(&p.bar[s]), dst = smem_addr(&p.buf[s][0]);
+    const uint32_t bar = a.bar0 + 8u * (uint32_t)s, dst = a.buf0 + SFH_PIPE_BUF_STRIDE * (uint32_t)s;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
@@ -42,9 +52,9 @@ __device__ __forceinline__ void pipe_issue(ChunkPipe& p, int s, const uint8_t* s
 }
 
 // all threads: wait until the copy into buffer s with the given phase parity has landed
-__device__ __forceinline__ void pipe_wait(ChunkPipe& p, int s, uint32_t parity)
+__device__ __forceinline__ void pipe_wait(const PipeAddr& a, int s, uint32_t parity)
 {
-    const uint32_t bar = smem_addr(&p.bar[s]);
+    const uint32_t bar = a.bar0 + 8u * (uint32_t)s;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"

@@ -1,8 +1,8 @@
 // sfh_kernels.cuh — the four kernels of one hydrodynamics step (sm_100a).
 //
-//   k_prologue   1 block        per-body: CheckBodyFluidPosition (a9), dispatcher gates (a10), fp64->fp32
+//   k_prologue   1 thread/body  per-body: CheckBodyFluidPosition (a9), dispatcher gates (a10), fp64->fp32
 //                               narrowing of transforms/velocities, position-independent current sum,
-//                               then an exclusive scan of chunk counts -> two work lists (submerged / surface)
+//   k_scan_items 1 block        exclusive scan of the per-body chunk counts -> two work lists (submerged / surface)
 //   k_submerged  persistent     per-face ComputeHydrodynamicForcesSubmerged (a1) over (body, chunk) items
 //   k_surface    persistent     per-face ComputeHydrodynamicForcesSurface  (a2) incl. waves (a3/a4)
 //   k_epilogue   1 warp/body    fixed-order reduction of the per-block partials, finalisation (A.5),
@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
     it.b_begin = P.item_off[it.b];
     it.b_end = P.item_off[it.b + 1];
     load_body(&s_body, P.bodies + it.b);
-    pipe_init(s_pipe); // includes the barrier that publishes s_body
-    if (tid == 0) walk_issue_first(s_pipe, it, s_body);
+    const PipeAddr pa = pipe_init(s_pipe); // includes the barrier that publishes s_body
+    if (tid == 0) walk_issue_first(pa, it, s_body);
     BodyRegs B;
     F3 p0;
     bool buoy, damp;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
     fetch_regs();
 
     for (;;) {
-        pipe_wait(s_pipe, it.s, (it.parity >> it.s) & 1u);
+        pipe_wait(pa, it.s, (it.parity >> it.s) & 1u);
         it.parity ^= 1u << it.s;
         const ChunkView cv = chunk_view(s_pipe.buf[it.s]);
         const uint32_t nf = cv.nf, b = it.b, c = it.w - it.b_begin;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
         __syncthreads(); // every thread is done with the previous chunk: s_v and the other staging buffer are free
         const uint8_t* nsrc = nullptr;
         uint32_t nbytes = 0;
-        if (tid == 0) walk_issue_next(s_pipe, it, P, cv.next_bytes, nsrc, nbytes);
+        if (tid == 0) walk_issue_next(pa, it, P, cv.next_bytes, nsrc, nbytes);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const uint32_t i = tid + k * SFH_BLOCK;
@@ -368,71 +368,76 @@ __device__ inline uint32_t check_body_fluid_position(bool waves, const WavesDev&
     return under == 0 ? SFH_POS_OUTSIDE : (under == 8 ? SFH_POS_INSIDE : SFH_POS_CROSSING);
 }
 
-__global__ void __launch_bounds__(1024) k_prologue(PrologueParams P)
+__global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
 {
-    __shared__ uint32_t s_warp[2][32];
-    __shared__ uint32_t s_carry[2];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_bodies) return;
     const OceanDev* __restrict__ oc = P.ocean;
     const bool waves = oc->has_waves != 0;
-    if (tid < 2) s_carry[tid] = 0;
-    __syncthreads();
 
     // position-independent part of Ocean::GetFluidVelocity (Ocean.cpp:183-201)
     float cur[3] = {0.f, 0.f, 0.f};
     if (oc->currents_enabled && !oc->cur_general) {
         D3 fv = {0.0, 0.0, 0.0};
-        for (uint32_t i = 0; i < oc->n_currents; ++i)
-            if (oc->currents[i].enabled) fv = fv + D3{oc->currents[i].a[0], oc->currents[i].a[1], oc->currents[i].a[2]};
+        for (uint32_t k = 0; k < oc->n_currents; ++k)
+            if (oc->currents[k].enabled) fv = fv + D3{oc->currents[k].a[0], oc->currents[k].a[1], oc->currents[k].a[2]};
         cur[0] = (float)fv.x; cur[1] = (float)fv.y; cur[2] = (float)fv.z;
     }
 
-    for (uint32_t base = 0; base < P.n_bodies; base += blockDim.x) {
+    const sfh_body_state& st = P.states[i];
+    BodyDev bd;
+    uint32_t pos = st.mode;
+    if (pos == SFH_POS_AUTO) pos = check_body_fluid_position(waves, P.waves, st.aabb_min, st.aabb_max);
+    if (pos > SFH_POS_CROSSING) pos = SFH_POS_OUTSIDE;
+    const bool dispatch = (st.flags & SFH_F_DISPATCH) != 0;
+    bool damping = (st.flags & SFH_F_DAMPING) != 0, buoyancy = (st.flags & SFH_F_BUOYANCY) != 0;
+    uint32_t kind = KIND_NONE;
+    if (pos == SFH_POS_INSIDE) {
+        // raw integrator: always runs (it has no settings); dispatcher: only `if(settings.dampingForces)`
+        if (!dispatch || damping) kind = KIND_SUBMERGED;
+        damping = true;
+    } else if (pos == SFH_POS_CROSSING) {
+        if (dispatch && !(st.flags & SFH_F_BUOYANT)) buoyancy = false; // SolidEntity.cpp:1844
+        kind = KIND_SURFACE;
+    }
+    MeshDev m = {nullptr, nullptr, nullptr, 0, 0};
+    if (st.mesh_id < P.n_meshes) m = P.meshes[st.mesh_id];
+    else if (kind != KIND_NONE) atomicOr(P.status, 1u);
+    // glMatrixFromTransform / glVectorFromVector (OpenGLDataStructs.cpp:148-171)
+    for (int k = 0; k < 9; ++k) bd.R[k] = (float)st.T_C[k];
+    for (int k = 0; k < 3; ++k) {
+        bd.t[k] = (float)st.T_C[9 + k];
+        bd.p[k] = (float)st.T_CG[9 + k];
+        bd.v[k] = (float)st.v[k];
+        bd.omega[k] = (float)st.omega[k];
+        bd.cur[k] = cur[k];
+    }
+    bd.flags = (damping ? BF_DAMPING : 0u) | (buoyancy ? BF_BUOYANCY : 0u);
+    bd.kind = kind | (pos << 8);
+    bd.n_chunks = (kind != KIND_NONE) ? m.n_chunks : 0u;
+    bd.n_faces = m.n_faces;
+    bd.chunks = m.chunks;
+    bd.first_bytes = m.n_chunks ? (m.chunk_off[1] - m.chunk_off[0]) * 16u : 0u;
+    bd.pad = 0;
+    bd.chunk_off = m.chunk_off;
+    bd.orig_face = m.orig_face;
+    P.bodies[i] = bd;
+    // chunk counts; k_scan_items turns them into the two work lists
+    P.off_sub[i] = (kind == KIND_SUBMERGED) ? bd.n_chunks : 0u;
+    P.off_surf[i] = (kind == KIND_SURFACE) ? bd.n_chunks : 0u;
+}
+
+// In-place exclusive scan of the per-body chunk counts (n_bodies entries -> n_bodies + 1 offsets). One block.
+__global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies)
+{
+    __shared__ uint32_t s_warp[2][32];
+    __shared__ uint32_t s_carry[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 2) s_carry[tid] = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_bodies; base += blockDim.x) {
         const uint32_t i = base + tid;
-        uint32_t n_sub = 0, n_surf = 0;
-        if (i < P.n_bodies) {
-            const sfh_body_state& st = P.states[i];
-            BodyDev bd;
-            uint32_t pos = st.mode;
-            if (pos == SFH_POS_AUTO) pos = check_body_fluid_position(waves, P.waves, st.aabb_min, st.aabb_max);
-            if (pos > SFH_POS_CROSSING) pos = SFH_POS_OUTSIDE;
-            const bool dispatch = (st.flags & SFH_F_DISPATCH) != 0;
-            bool damping = (st.flags & SFH_F_DAMPING) != 0, buoyancy = (st.flags & SFH_F_BUOYANCY) != 0;
-            uint32_t kind = KIND_NONE;
-            if (pos == SFH_POS_INSIDE) {
-                // raw integrator: always runs (it has no settings); dispatcher: only `if(settings.dampingForces)`
-                if (!dispatch || damping) kind = KIND_SUBMERGED;
-                damping = true;
-            } else if (pos == SFH_POS_CROSSING) {
-                if (dispatch && !(st.flags & SFH_F_BUOYANT)) buoyancy = false; // SolidEntity.cpp:1844
-                kind = KIND_SURFACE;
-            }
-            MeshDev m = {nullptr, nullptr, nullptr, 0, 0};
-            if (st.mesh_id < P.n_meshes) m = P.meshes[st.mesh_id];
-            else if (kind != KIND_NONE) atomicOr(P.status, 1u);
-            // glMatrixFromTransform / glVectorFromVector (OpenGLDataStructs.cpp:148-171)
-            for (int k = 0; k < 9; ++k) bd.R[k] = (float)st.T_C[k];
-            for (int k = 0; k < 3; ++k) {
-                bd.t[k] = (float)st.T_C[9 + k];
-                bd.p[k] = (float)st.T_CG[9 + k];
-                bd.v[k] = (float)st.v[k];
-                bd.omega[k] = (float)st.omega[k];
-                bd.cur[k] = cur[k];
-            }
-            bd.flags = (damping ? BF_DAMPING : 0u) | (buoyancy ? BF_BUOYANCY : 0u);
-            bd.kind = kind | (pos << 8);
-            bd.n_chunks = (kind != KIND_NONE) ? m.n_chunks : 0u;
-            bd.n_faces = m.n_faces;
-            bd.chunks = m.chunks;
-            bd.first_bytes = m.n_chunks ? (m.chunk_off[1] - m.chunk_off[0]) * 16u : 0u;
-            bd.pad = 0;
-            bd.chunk_off = m.chunk_off;
-            bd.orig_face = m.orig_face;
-            P.bodies[i] = bd;
-            if (kind == KIND_SUBMERGED) n_sub = bd.n_chunks;
-            if (kind == KIND_SURFACE) n_surf = bd.n_chunks;
-        }
-        // block-wide exclusive scan of (n_sub, n_surf)
+        const uint32_t n_sub = i < n_bodies ? off_sub[i] : 0u, n_surf = i < n_bodies ? off_surf[i] : 0u;
         uint32_t xs = n_sub, xf = n_surf;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -453,12 +458,12 @@ __global__ void __launch_bounds__(1024) k_prologue(PrologueParams P)
         __syncthreads();
         const uint32_t pre_s = s_carry[0] + (warp ? s_warp[0][warp - 1] : 0u) + xs - n_sub;
         const uint32_t pre_f = s_carry[1] + (warp ? s_warp[1][warp - 1] : 0u) + xf - n_surf;
-        if (i < P.n_bodies) { P.off_sub[i] = pre_s; P.off_surf[i] = pre_f; }
+        if (i < n_bodies) { off_sub[i] = pre_s; off_surf[i] = pre_f; }
         __syncthreads();
         if (tid == 0) { s_carry[0] += s_warp[0][31]; s_carry[1] += s_warp[1][31]; }
         __syncthreads();
     }
-    if (tid == 0) { P.off_sub[P.n_bodies] = s_carry[0]; P.off_surf[P.n_bodies] = s_carry[1]; }
+    if (tid == 0) { off_sub[n_bodies] = s_carry[0]; off_surf[n_bodies] = s_carry[1]; }
 }
 
 // ---------------------------------------------------------------------------------------------

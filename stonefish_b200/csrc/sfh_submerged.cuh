@@ -17,35 +17,36 @@
 namespace sfh {
 
 // fn / len for three numerators sharing one reciprocal (len >= 1e-6 here, and |fn_i| <= ~len). The shared form
-// is proven for numerators that are zero or >= 2^-36 in magnitude (quotient zero or >= 2^-100, remainder exact);
-// anything else — never seen on real meshes — takes the hardware division.
+// is proven for numerators that are zero or >= 2^-36 in magnitude (quotient zero or >= 2^-100, remainder exact).
+// ((a + b) + c) / 3.f uses ieee_div3_2, proven for sums that are zero or >= 2^-100.
+// Anything else — never seen on real meshes — is redone with the hardware division by the caller.
 #define SFH_NUM_KEY 0x5affffffu /* 2*bits(2^-36) - 1 */
-__device__ __forceinline__ V3P normalize_by(V3P fn, P2 len)
+__device__ __forceinline__ uint32_t min_key(V3P a)
+{
+    return min(min(min(tiny_key(lo(a.x)), tiny_key(lo(a.y))), tiny_key(lo(a.z))),
+               min(min(tiny_key(hi(a.x)), tiny_key(hi(a.y))), tiny_key(hi(a.z))));
+}
+__device__ __forceinline__ V3P normalize_fast(V3P fn, P2 len)
 {
     const P2 nlen = neg(len);
     const P2 r = refined_rcp2(len, nlen);
-    V3P q = {ieee_div_r2(fn.x, nlen, r), ieee_div_r2(fn.y, nlen, r), ieee_div_r2(fn.z, nlen, r)};
-    const uint32_t m0 = min(min(tiny_key(lo(fn.x)), tiny_key(lo(fn.y))), tiny_key(lo(fn.z)));
-    const uint32_t m1 = min(min(tiny_key(hi(fn.x)), tiny_key(hi(fn.y))), tiny_key(hi(fn.z)));
-    if (min(m0, m1) < SFH_NUM_KEY) {
-        q.x = pk(__fdiv_rn(lo(fn.x), lo(len)), __fdiv_rn(hi(fn.x), hi(len)));
-        q.y = pk(__fdiv_rn(lo(fn.y), lo(len)), __fdiv_rn(hi(fn.y), hi(len)));
-        q.z = pk(__fdiv_rn(lo(fn.z), lo(len)), __fdiv_rn(hi(fn.z), hi(len)));
-    }
-    return q;
+    return {ieee_div_r2(fn.x, nlen, r), ieee_div_r2(fn.y, nlen, r), ieee_div_r2(fn.z, nlen, r)};
+}
+__device__ __forceinline__ void normalize_centroid_slow(V3P fn, P2 len, V3P s, V3P& fn1, V3P& fc)
+{
+    fn1.x = pk(__fdiv_rn(lo(fn.x), lo(len)), __fdiv_rn(hi(fn.x), hi(len)));
+    fn1.y = pk(__fdiv_rn(lo(fn.y), lo(len)), __fdiv_rn(hi(fn.y), hi(len)));
+    fn1.z = pk(__fdiv_rn(lo(fn.z), lo(len)), __fdiv_rn(hi(fn.z), hi(len)));
+    fc.x = pk(__fdiv_rn(lo(s.x), 3.f), __fdiv_rn(hi(s.x), 3.f));
+    fc.y = pk(__fdiv_rn(lo(s.y), 3.f), __fdiv_rn(hi(s.y), 3.f));
+    fc.z = pk(__fdiv_rn(lo(s.z), 3.f), __fdiv_rn(hi(s.z), 3.f));
 }
 
-// ((a + b) + c) / 3.f per component
-__device__ __forceinline__ V3P centroid3(V3P a, V3P b, V3P c)
+// a[0..5] += (double){x0..x5}: the fp32 per-face terms enter the fp64 sums exactly
+__device__ __forceinline__ void acc6(double* a, float x0, float x1, float x2, float x3, float x4, float x5)
 {
-    const V3P s = (a + b) + c;
-    V3P q = {ieee_div3_2(s.x), ieee_div3_2(s.y), ieee_div3_2(s.z)};
-    if (any_tiny_nonzero(s)) {
-        q.x = pk(__fdiv_rn(lo(s.x), 3.f), __fdiv_rn(hi(s.x), 3.f));
-        q.y = pk(__fdiv_rn(lo(s.y), 3.f), __fdiv_rn(hi(s.y), 3.f));
-        q.z = pk(__fdiv_rn(lo(s.z), 3.f), __fdiv_rn(hi(s.z), 3.f));
-    }
-    return q;
+    a[0] = dadd(a[0], (double)x0); a[1] = dadd(a[1], (double)x1); a[2] = dadd(a[2], (double)x2);
+    a[3] = dadd(a[3], (double)x3); a[4] = dadd(a[4], (double)x4); a[5] = dadd(a[5], (double)x5);
 }
 
 struct BodyP2 { // per-body constants broadcast to both lanes
@@ -77,36 +78,20 @@ __device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_curr
         const P2 vmag2 = dot(vc, vc);
         const V3P q = ((vc * ieee_sqrt2(vmag2)) * neg(vc_n)) * A;
         const V3P tq = cross(r, q);
-        if (qA) {
-            acc[0] = dadd(acc[0], (double)lo(q.x));  acc[1] = dadd(acc[1], (double)lo(q.y));  acc[2] = dadd(acc[2], (double)lo(q.z));
-            acc[3] = dadd(acc[3], (double)lo(tq.x)); acc[4] = dadd(acc[4], (double)lo(tq.y)); acc[5] = dadd(acc[5], (double)lo(tq.z));
-            epack += 1u << 10;
-            code |= SFH_FACE_QUADRATIC;
-        }
-        if (qB) {
-            acc[0] = dadd(acc[0], (double)hi(q.x));  acc[1] = dadd(acc[1], (double)hi(q.y));  acc[2] = dadd(acc[2], (double)hi(q.z));
-            acc[3] = dadd(acc[3], (double)hi(tq.x)); acc[4] = dadd(acc[4], (double)hi(tq.y)); acc[5] = dadd(acc[5], (double)hi(tq.z));
-            epack += 1u << 10;
-            code |= SFH_FACE_QUADRATIC << 8;
-        }
+        if (qA) acc6(acc, lo(q.x), lo(q.y), lo(q.z), lo(tq.x), lo(tq.y), lo(tq.z));
+        if (qB) acc6(acc, hi(q.x), hi(q.y), hi(q.z), hi(tq.x), hi(tq.y), hi(tq.z));
+        epack += (qA ? 1u << 10 : 0u) + (qB ? 1u << 10 : 0u);
+        code |= (qA ? (uint32_t)SFH_FACE_QUADRATIC : 0u) | (qB ? (uint32_t)SFH_FACE_QUADRATIC << 8 : 0u);
     }
     const P2 vt2 = dot(vt, vt);
     const bool sA = mA && lo(vt2) > 1e-9f, sB = mB && hi(vt2) > 1e-9f;
     if (__any_sync(SFH_FULL, sA | sB)) {
         const V3P s = vt * A;
         const V3P ts = cross(r, s);
-        if (sA) {
-            acc[6] = dadd(acc[6], (double)lo(s.x));  acc[7] = dadd(acc[7], (double)lo(s.y));   acc[8] = dadd(acc[8], (double)lo(s.z));
-            acc[9] = dadd(acc[9], (double)lo(ts.x)); acc[10] = dadd(acc[10], (double)lo(ts.y)); acc[11] = dadd(acc[11], (double)lo(ts.z));
-            epack += 1u << 20;
-            code |= SFH_FACE_SKIN;
-        }
-        if (sB) {
-            acc[6] = dadd(acc[6], (double)hi(s.x));  acc[7] = dadd(acc[7], (double)hi(s.y));   acc[8] = dadd(acc[8], (double)hi(s.z));
-            acc[9] = dadd(acc[9], (double)hi(ts.x)); acc[10] = dadd(acc[10], (double)hi(ts.y)); acc[11] = dadd(acc[11], (double)hi(ts.z));
-            epack += 1u << 20;
-            code |= SFH_FACE_SKIN << 8;
-        }
+        if (sA) acc6(acc + 6, lo(s.x), lo(s.y), lo(s.z), lo(ts.x), lo(ts.y), lo(ts.z));
+        if (sB) acc6(acc + 6, hi(s.x), hi(s.y), hi(s.z), hi(ts.x), hi(ts.y), hi(ts.z));
+        epack += (sA ? 1u << 20 : 0u) + (sB ? 1u << 20 : 0u);
+        code |= (sA ? (uint32_t)SFH_FACE_SKIN : 0u) | (sB ? (uint32_t)SFH_FACE_SKIN << 8 : 0u);
     }
     return code;
 }
@@ -122,7 +107,7 @@ struct ItemWalk {
 };
 
 // thread 0: start the copy of the chunk of work item `w` of body `b` (random access through chunk_off)
-__device__ __forceinline__ void walk_issue_first(ChunkPipe& pipe, ItemWalk& it, const BodyDev& body)
+__device__ __forceinline__ void walk_issue_first(const PipeAddr& pipe, ItemWalk& it, const BodyDev& body)
 {
     const uint32_t c = it.w - it.b_begin;
     const uint32_t o0 = __ldg(body.chunk_off + c), o1 = __ldg(body.chunk_off + c + 1);
@@ -134,7 +119,7 @@ __device__ __forceinline__ void walk_issue_first(ChunkPipe& pipe, ItemWalk& it, 
 // thread 0, right after the block barrier that retires the previous chunk: chain the copy of item w+1 into the
 // other buffer — the following chunk of this body (size from the staged header) or chunk 0 of the next body
 // that has work (pointer and size read as one 16-byte load from its BodyDev record).
-__device__ __forceinline__ void walk_issue_next(ChunkPipe& pipe, ItemWalk& it, const StepParams& P, uint32_t next_bytes,
+__device__ __forceinline__ void walk_issue_next(const PipeAddr& pipe, ItemWalk& it, const StepParams& P, uint32_t next_bytes,
                                                 const uint8_t*& nsrc, uint32_t& nbytes)
 {
     const uint32_t wn = it.w + 1;
@@ -184,8 +169,8 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
     it.b_begin = P.item_off[it.b];
     it.b_end = P.item_off[it.b + 1];
     load_body(&s_body, P.bodies + it.b);
-    pipe_init(s_pipe); // includes the barrier that publishes s_body
-    if (tid == 0) walk_issue_first(s_pipe, it, s_body);
+    const PipeAddr pa = pipe_init(s_pipe); // includes the barrier that publishes s_body
+    if (tid == 0) walk_issue_first(pa, it, s_body);
 
     BodyP2 B;
     auto fetch_regs = [&]() {
@@ -207,7 +192,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
     fetch_regs();
 
     for (;;) {
-        pipe_wait(s_pipe, it.s, (it.parity >> it.s) & 1u);
+        pipe_wait(pa, it.s, (it.parity >> it.s) & 1u);
         it.parity ^= 1u << it.s;
         const uint8_t* buf = s_pipe.buf[it.s];
         const ChunkView cv = chunk_view(buf);
@@ -215,7 +200,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
         __syncthreads(); // every thread is done with the previous chunk: s_v and the other staging buffer are free
         const uint8_t* nsrc = nullptr;
         uint32_t nbytes = 0;
-        if (tid == 0) walk_issue_next(s_pipe, it, P, cv.next_bytes, nsrc, nbytes);
+        if (tid == 0) walk_issue_next(pa, it, P, cv.next_bytes, nsrc, nbytes);
 
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -231,8 +216,9 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
             const uint32_t nf = cv.nf;
             const bool vA = tid < nf, vB = tid + SFH_BLOCK < nf;
             const uint32_t fA = vA ? cv.faces[tid] : 0u, fB = vB ? cv.faces[tid + SFH_BLOCK] : 0u;
-            const float4 a1 = s_v[fA & 255u], a2 = s_v[(fA >> 8) & 255u], a3 = s_v[(fA >> 16) & 255u];
-            const float4 b1 = s_v[fB & 255u], b2 = s_v[(fB >> 8) & 255u], b3 = s_v[(fB >> 16) & 255u];
+            // byte k of the packed face word -> vertex slot (PRMT) -> float4 in s_v (LEA)
+            const float4 a1 = s_v[__byte_perm(fA, 0, 0x4440)], a2 = s_v[__byte_perm(fA, 0, 0x4441)], a3 = s_v[__byte_perm(fA, 0, 0x4442)];
+            const float4 b1 = s_v[__byte_perm(fB, 0, 0x4440)], b2 = s_v[__byte_perm(fB, 0, 0x4441)], b3 = s_v[__byte_perm(fB, 0, 0x4442)];
             const V3P p1 = {pk(a1.x, b1.x), pk(a1.y, b1.y), pk(a1.z, b1.z)};
             const V3P p2 = {pk(a2.x, b2.x), pk(a2.y, b2.y), pk(a2.z, b2.z)};
             const V3P p3 = {pk(a3.x, b3.x), pk(a3.y, b3.y), pk(a3.z, b3.z)};
@@ -247,10 +233,17 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
             if (__any_sync(SFH_FULL, mA | mB)) {
                 // len2 >= 1e-12 > 2^-101 on every lane that is used
                 const P2 len = ieee_sqrt2(len2);
-                const V3P fn1 = normalize_by(fn, len);
                 const P2 A = len * pk1(0.5f); // len / 2.f, exact scaling
-                const V3P fc = centroid3(p1, p2, p3);
-                code = damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
+                const V3P csum = (p1 + p2) + p3;
+                if ((min_key(fn) >= SFH_NUM_KEY) & (min_key(csum) >= SFH_TINY_KEY)) {
+                    const V3P fn1 = normalize_fast(fn, len);
+                    const V3P fc = {ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)};
+                    code = damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
+                } else { // operands outside the proven range of the shared-reciprocal / multiply-by-1/3 forms
+                    V3P fn1, fc;
+                    normalize_centroid_slow(fn, len, csum, fn1, fc);
+                    code = damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
+                }
             }
             if (DEBUG) {
                 const uint32_t* of = s_body.orig_face + (size_t)(it.w - it.b_begin) * SFH_CH_FACES;
