@@ -1,0 +1,170 @@
+"""Sanity of the oracle itself against physics the reference's (commented-out) known-answer checks assert
+(Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:168-249) and against hand-computable cases of the wave lookup."""
+import ctypes as C
+import math
+
+import numpy as np
+
+from stonefish_b200 import _abi, meshes, scenes
+from stonefish_b200.hydro import Mesh, Ocean, Uniform, make_transform, new_body_states, quat_to_basis
+
+
+def _scene(mesh, T, mode, flags, ocean=None, v=(0, 0, 0), w=(0, 0, 0)):
+    st = new_body_states(1)
+    st["T_CG"][0] = T
+    st["T_C"][0] = T
+    st["mode"][0] = mode
+    st["flags"][0] = flags
+    st["v"][0] = v
+    st["omega"][0] = w
+    return [mesh], np.zeros(1, dtype=np.int64), ocean or Ocean(), st
+
+
+def test_synthetic_meshes_are_closed_and_outward():
+    for m, f in ((meshes.uv_ellipsoid(2.5, 0.3, 0.3, 400, 251), 200000), (meshes.uv_ellipsoid(1.2, 0.15, 0.15, 250, 101), 50000),
+                 (meshes.icosphere(0.5, 3), 1280), (meshes.box(1.0, 0.5, 0.2, 3), 768)):
+        assert m.n_faces == f
+        assert m.n_verts == f // 2 + 2  # closed genus-0 triangle mesh
+        assert meshes.signed_volume(m) > 0
+    assert abs(meshes.signed_volume(meshes.box(1.0, 0.5, 0.2, 3)) - 0.1) < 1e-6
+    assert abs(meshes.signed_volume(meshes.icosphere(0.5, 3)) - 4 / 3 * math.pi * 0.125) < 5e-3
+
+
+def _clipped_area_volume(mesh, z_off):
+    """float64 Sutherland-Hodgman of every face against the plane world-z = 0 (submerged side z >= 0)."""
+    tri = mesh.positions.astype(np.float64)[mesh.faces] + np.array([0.0, 0.0, z_off])
+    area = vol = 0.0
+    for t in tri:
+        out = []
+        for i in range(3):
+            a, b = t[i], t[(i + 1) % 3]
+            if a[2] >= 0:
+                out.append(a)
+            if (a[2] >= 0) != (b[2] >= 0):
+                out.append(a + a[2] / (a[2] - b[2]) * (b - a))
+        for i in range(1, len(out) - 1):
+            area += 0.5 * np.linalg.norm(np.cross(out[i] - out[0], out[i + 1] - out[0]))
+            vol += np.dot(out[0], np.cross(out[i], out[i + 1])) / 6.0
+    return area, vol
+
+
+def test_archimedes_flat_sea(oracle):
+    """Floating sphere on a flat sea: Vsub and Swet equal an independent float64 clipping of the mesh, Fb = -rho g Vsub
+    along z (SolidEntity.cpp:1705), no horizontal force, negligible torque."""
+    m = meshes.icosphere(0.5, 3)
+    z = 0.013  # no vertex exactly on the waterline (the reference drops such faces through its degenerate test)
+    area, vol = _clipped_area_volume(m, z)
+    o = oracle.OracleScene(*_scene(m, make_transform(None, (0.0, 0.0, z)), _abi.SFH_POS_CROSSING, 3))
+    for mode in (0, 1):
+        r = o.body(0, mode)
+        assert r["wrote_buoyancy"] == 1 and r["n_degenerate"] == 0
+        assert math.isclose(r["Vsub"], vol, rel_tol=2e-6)
+        assert math.isclose(r["Swet"], area, rel_tol=2e-6)
+        assert r["Fb"][0] == 0 and r["Fb"][1] == 0
+        assert math.isclose(r["Fb"][2], -r["Vsub"] * 1000.0 * 9.81, rel_tol=1e-15)
+        assert np.abs(r["Tb"]).max() < 1e-2
+    # a vertex exactly at depth 0 makes the first triangle of a clipped quad degenerate and the reference skips the
+    # whole face (SolidEntity.cpp:1465-1467): reproduced, not "fixed"
+    r0 = oracle.OracleScene(*_scene(m, make_transform(None, (0.0, 0.0, 0.0)), _abi.SFH_POS_CROSSING, 3)).body(0, 1)
+    assert r0["n_degenerate"] > 0 and r0["Swet"] < _clipped_area_volume(m, 0.0)[0] - 1e-3
+
+
+def test_fully_submerged_crossing_volume_is_mesh_volume(oracle):
+    m = meshes.uv_ellipsoid(0.9, 0.18, 0.18, 40, 37)
+    q = scenes.euler_zyx_quat(0.3, 0.5, 0.1)
+    o = oracle.OracleScene(*_scene(m, make_transform(quat_to_basis(q), (1, 2, 5.0)), _abi.SFH_POS_CROSSING, 3))
+    r = o.body(0, 1)
+    assert math.isclose(r["Vsub"], meshes.signed_volume(m), rel_tol=1e-5)
+    assert r["class_count"][7] == m.n_faces
+
+
+def test_reference_fp32_sums_close_to_fp64_sums(oracle):
+    sc = scenes.config2(100, 51)
+    o = oracle.OracleScene(sc.meshes, sc.body_mesh, sc.ocean, sc.states)
+    a, b = o.body(0, 0), o.body(0, 1)
+    for k in ("Fdq", "Tdq", "Fdf", "Tdf"):
+        np.testing.assert_allclose(a[k], b[k], rtol=2e-5, atol=1e-6)
+    for k in ("n_quadratic", "n_skin", "n_degenerate"):
+        assert a[k] == b[k]
+
+
+def test_yaw_equivariance_of_drag(oracle):
+    """The reference's check (:238-247): compounds yawed by k*45 deg moving along their own surge axis see the same drag
+    magnitude; here on the raw sums of one box."""
+    m = meshes.box(1.0, 0.5, 0.2, 3)
+    mags = []
+    for k in range(8):
+        yaw = math.pi / 4 * k
+        T = make_transform(quat_to_basis(scenes.euler_zyx_quat(yaw, 0, 0)), (0, 0, 5.0))
+        o = oracle.OracleScene(*_scene(m, T, _abi.SFH_POS_INSIDE, 1, v=(0.8 * math.cos(yaw), 0.8 * math.sin(yaw), 0.0)))
+        r = o.body(0, 1)
+        mags.append((np.linalg.norm(r["Fdq"]), np.linalg.norm(r["Fdf"])))
+    mags = np.array(mags)
+    assert np.ptp(mags[:, 0]) / mags[:, 0].mean() < 1e-5 and np.ptp(mags[:, 1]) / mags[:, 1].mean() < 1e-5
+
+
+def test_at_rest_in_still_water_no_drag(oracle):
+    m = meshes.icosphere(0.5, 2)
+    r = oracle.OracleScene(*_scene(m, make_transform(None, (0, 0, 3.0)), _abi.SFH_POS_INSIDE, 1)).body(0, 1)
+    assert r["n_quadratic"] == 0 and not r["Fdq"].any() and not r["Fdf"].any()
+
+
+def test_mesh_nullptr_and_stale_output_flags(oracle):
+    lib = oracle.lib()
+    sc = scenes.config3(40, 21, waves=False)
+    st = sc.states.copy()
+    out = np.zeros(1, dtype=oracle.INFO_DTYPE)
+    o = sc.ocean.to_struct()
+    w = _abi.sfh_waves()
+    lib.orc_surface(None, C.byref(o), C.byref(w), st.ctypes.data, 1, out.ctypes.data, None)  # mesh == nullptr, :1293-1312
+    assert out["wrote_buoyancy"][0] == 1 and out["wrote_damping"][0] == 1 and out["n_faces"][0] == 0
+    # a body lifted clear of the water but forced through the Surface integrator: Vsub <= 1e-9 -> buoyancy untouched
+    st["T_CG"][0][11] -= 10.0
+    st["T_C"][0][11] -= 10.0
+    r = oracle.OracleScene(sc.meshes, sc.body_mesh, sc.ocean, st).body(0, 1)
+    assert r["wrote_buoyancy"] == 0 and r["wrote_damping"] == 1 and r["class_count"][0] == sc.meshes[0].n_faces and r["Swet"] == 0
+
+
+def test_wave_bilinear_known_answers(oracle):
+    field = np.zeros((4, 256, 256, 4), np.float32)
+    field[0, :, :, 0] = np.arange(65536, dtype=np.float32).reshape(256, 256) / 1024.0
+    field[0, :, :, 1] = 0.25
+    field[1, 0, :, :] = 7.0  # first row of layer 1: what index j0 == 256 reads
+    ocean = Ocean()
+    ocean.setWaves(field, 256, (256.0, 128.0, 21.0, 11.0))
+    w = ocean.waves_struct()
+    bil, height = oracle.lib().orc_wave_bilinear, oracle.lib().orc_wave_height
+    # texel centres return the texel; halfway between two texels the mean
+    assert bil(C.byref(w), (3 + 0.5) / 256, (5 + 0.5) / 256, 0) == field[0, 5, 3, 0]
+    assert bil(C.byref(w), 4.0 / 256, (5 + 0.5) / 256, 0) == (field[0, 5, 3, 0] + field[0, 5, 4, 0]) / 2
+    # repeat wrap on both axes, including negative coordinates
+    assert bil(C.byref(w), (3 + 0.5) / 256 + 2.0, (5 + 0.5) / 256 - 3.0, 0) == field[0, 5, 3, 0]
+    # ComputeWaveHeight = 0 - layer0(x/gx) - layer1(x/gy); depth = z - height
+    assert height(C.byref(w), 3.5, 5.5) == -(field[0, 5, 3, 0]) - 0.25
+    o = ocean.to_struct()
+    assert oracle.lib().orc_get_depth(C.byref(o), C.byref(w), 3.5, 5.5, 1.0) == 1.0 + field[0, 5, 3, 0] + 0.25
+    # i0f == 1.0f after the negative fix-up reads one texel past the row, exactly like the reference's indexing
+    tiny = np.float32(0.5 / 256) - np.float32(1e-10)
+    v = bil(C.byref(w), float(tiny), (255 + 0.5) / 256, 0)
+    assert np.isfinite(v)
+
+
+def test_check_body_fluid_position(oracle):
+    ocean = Ocean()
+    o, w = ocean.to_struct(), _abi.sfh_waves()
+    f = oracle.lib().orc_check_body_fluid_position
+    D3 = C.c_double * 3
+    assert f(C.byref(o), C.byref(w), D3(-1, -1, -2), D3(1, 1, -1)) == _abi.SFH_POS_OUTSIDE
+    assert f(C.byref(o), C.byref(w), D3(-1, -1, 1), D3(1, 1, 2)) == _abi.SFH_POS_INSIDE
+    assert f(C.byref(o), C.byref(w), D3(-1, -1, -1), D3(1, 1, 1)) == _abi.SFH_POS_CROSSING
+    assert f(C.byref(o), C.byref(w), D3(-1, -1, -1), D3(1, 1, 0)) == _abi.SFH_POS_OUTSIDE  # depth > 0 is strict (:1246)
+
+
+def test_step_schedule_one_task_per_body_matches_serial(oracle):
+    sc = scenes.mixed_small(5, True, "jetpipe")
+    o = oracle.OracleScene(sc.meshes, sc.body_mesh, sc.ocean, sc.states)
+    a, _ = o.step(0, n_threads=1)
+    b, secs = o.step(0, n_threads=4)
+    assert a.tobytes() == b.tobytes() and secs > 0
+    split, _ = o.body_split(1, 3)
+    np.testing.assert_allclose(split["Fdq"], o.body(1, 1)["Fdq"], rtol=1e-12, atol=1e-12)
