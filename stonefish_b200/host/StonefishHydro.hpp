@@ -1,0 +1,309 @@
+// StonefishHydro.hpp — C++ host-side mirror of the reference's interface for the hydrodynamics path, over the C ABI
+// (include/sfh.h, libsfh.so). Header-only; this is what a Stonefish build links instead of running
+// SolidEntity::ComputeHydrodynamicForces on its thread pool (see INTEGRATION.md for the call-site patch).
+//
+// Names, argument meaning and behaviour follow the reference:
+//   sf::HydrodynamicsSettings                      Library/include/entities/forcefields/Ocean.h:36-40
+//   sf::Uniform / sf::Jet / sf::Pipe               Library/src/entities/forcefields/{Uniform,Jet,Pipe}.cpp
+//   sf::Ocean::{AddVelocityField,EnableCurrents,DisableCurrents,hasWaves}   Ocean.cpp:139-211
+//   sf::SolidEntity::ComputeHydrodynamicForces     SolidEntity.cpp:1799-1850  (per body; here: one batch per step)
+//   sf::SolidEntity outputs Fb,Tb,Fdq,Tdq,Fdf,Tdf,Swet,Vsub               SolidEntity.h:430-437 ("HydrodynamicsInfo")
+// Error behaviour: the reference's methods are void and cannot fail; here a failing CUDA call throws
+// std::runtime_error with sfh_last_error() — there is no CPU fallback to fall back to.
+//
+// The math types are plain PODs so this header needs neither Bullet nor glm; FromBullet() adapters take anything
+// with the btVector3 / btTransform accessor names (x(),y(),z(), getBasis()[r][c], getOrigin()).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sfh.h"
+
+namespace sfb {
+
+typedef double Scalar;
+
+struct Vector3 {
+    Scalar x = 0, y = 0, z = 0;
+    Vector3() {}
+    Vector3(Scalar x_, Scalar y_, Scalar z_) : x(x_), y(y_), z(z_) {}
+    template <class BtVec>
+    static Vector3 FromBullet(const BtVec& v) { return Vector3(v.x(), v.y(), v.z()); }
+    Vector3 operator+(const Vector3& o) const { return Vector3(x + o.x, y + o.y, z + o.z); }
+};
+
+struct Transform { // btTransform flattened: basis rows then origin
+    Scalar m[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    template <class BtTransform>
+    static Transform FromBullet(const BtTransform& T)
+    {
+        Transform r;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) r.m[3 * i + j] = T.getBasis()[i][j];
+        r.m[9] = T.getOrigin().x(); r.m[10] = T.getOrigin().y(); r.m[11] = T.getOrigin().z();
+        return r;
+    }
+};
+
+//! A structure holding the settings of the hydrodynamics computation (Ocean.h:36-40, spelling as in the reference).
+struct HydrodynamicsSettings {
+    bool dampingForces = true;
+    bool reallisticBuoyancy = true;
+};
+
+enum class BodyFluidPosition { OUTSIDE = SFH_POS_OUTSIDE, INSIDE = SFH_POS_INSIDE, CROSSING_SURFACE = SFH_POS_CROSSING };
+
+//! What SolidEntity stores after ComputeHydrodynamicForces (SolidEntity.h:430-437) plus the validation counters.
+struct HydrodynamicsInfo {
+    Vector3 Fb, Tb, Fdq, Tdq, Fdf, Tdf;
+    Scalar Swet = 0, Vsub = 0;
+    BodyFluidPosition position = BodyFluidPosition::OUTSIDE;
+    uint32_t faces = 0, classCount[8] = {0, 0, 0, 0, 0, 0, 0, 0}, degenerate = 0, quadratic = 0, skin = 0;
+    //! SolidEntity::ApplyHydrodynamicForces (SolidEntity.cpp:1958-1962): what goes to ApplyCentralForce / ApplyTorque
+    Vector3 Force() const { return Fb + Fdq + Fdf; }
+    Vector3 Torque() const { return Tb + Tdq + Tdf; }
+};
+
+// ------------------------------------------------------------------------------------------------ velocity fields
+enum class VelocityFieldType { UNIFORM, JET, PIPE };
+
+class VelocityField {
+public:
+    virtual ~VelocityField() {}
+    void setEnabled(bool en) { enabled = en; }
+    bool isEnabled() const { return enabled; }
+    virtual VelocityFieldType getType() const = 0;
+    virtual void Fill(sfh_current& c) const = 0;
+
+private:
+    bool enabled = true; // VelocityField.cpp:31
+};
+
+class Uniform : public VelocityField { // Uniform.cpp:31-57
+public:
+    explicit Uniform(const Vector3& velocity) : v(velocity) {}
+    void setVelocity(const Vector3& x) { v = x; }
+    Vector3 getVelocity() const { return v; }
+    VelocityFieldType getType() const override { return VelocityFieldType::UNIFORM; }
+    void Fill(sfh_current& c) const override { c.type = SFH_CURRENT_UNIFORM; c.a[0] = v.x; c.a[1] = v.y; c.a[2] = v.z; }
+
+private:
+    Vector3 v;
+};
+
+class Jet : public VelocityField { // Jet.cpp:31-75
+public:
+    Jet(const Vector3& point, const Vector3& direction, Scalar radius, Scalar outletVelocity) : c(point), r(radius), vout(outletVelocity)
+    {
+        // btVector3::normalized(): *this / length() == *this * (1 / sqrt(x*x + y*y + z*z))
+        const Scalar s = Scalar(1.0) / std::sqrt(direction.x * direction.x + direction.y * direction.y + direction.z * direction.z);
+        n = Vector3(direction.x * s, direction.y * s, direction.z * s);
+    }
+    void setOutletVelocity(Scalar x) { vout = x; }
+    Scalar getOutletVelocity() const { return vout; }
+    VelocityFieldType getType() const override { return VelocityFieldType::JET; }
+    void Fill(sfh_current& k) const override
+    {
+        k.type = SFH_CURRENT_JET;
+        k.a[0] = c.x; k.a[1] = c.y; k.a[2] = c.z;
+        k.n[0] = n.x; k.n[1] = n.y; k.n[2] = n.z;
+        k.r1 = r; k.vel = vout;
+    }
+
+private:
+    Vector3 c, n;
+    Scalar r, vout;
+};
+
+class Pipe : public VelocityField { // Pipe.cpp:31-78
+public:
+    Pipe(const Vector3& point1, const Vector3& point2, Scalar radius1, Scalar radius2, Scalar inletVelocity, Scalar exponent)
+        : p1(point1), r1(radius1), r2(radius2), vin(inletVelocity), gamma(exponent)
+    {
+        const Vector3 d(point2.x - point1.x, point2.y - point1.y, point2.z - point1.z);
+        l = std::sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+        const Scalar s = Scalar(1.0) / l; // btVector3 operator/(v, s) == v * (1/s)
+        n = Vector3(d.x * s, d.y * s, d.z * s);
+    }
+    void setInletVelocity(Scalar x) { vin = x; }
+    Scalar getInletVelocity() const { return vin; }
+    VelocityFieldType getType() const override { return VelocityFieldType::PIPE; }
+    void Fill(sfh_current& k) const override
+    {
+        k.type = SFH_CURRENT_PIPE;
+        k.a[0] = p1.x; k.a[1] = p1.y; k.a[2] = p1.z;
+        k.n[0] = n.x; k.n[1] = n.y; k.n[2] = n.z;
+        k.r1 = r1; k.r2 = r2; k.l = l; k.vel = vin; k.gamma = gamma;
+    }
+
+private:
+    Vector3 p1, n;
+    Scalar l, r1, r2, vin, gamma;
+};
+
+// ------------------------------------------------------------------------------------------------ ocean
+//! What the integrators read from sf::Ocean. Owns its velocity fields like the reference (Ocean.cpp:64-75).
+class Ocean {
+public:
+    Ocean(Scalar liquidDensity, Scalar gravity) : density(liquidDensity), g(gravity) {}
+    void AddVelocityField(VelocityField* field) { currents.emplace_back(field); }
+    void EnableCurrents() { currentsEnabled = true; }
+    void DisableCurrents() { currentsEnabled = false; }
+    bool hasWaves() const { return fftData != nullptr; }
+    //! OpenGLRealOcean::fftData (float[fftSize*fftSize*4*layers]); nullptr = flat sea. Not owned. Call again when the
+    //! render thread refreshes it (OpenGLRealOcean.cpp:333-356).
+    void setWaveData(const float* data, size_t nFloats, int fftSize = 256, const float gridSizes[4] = nullptr)
+    {
+        fftData = data; fftFloats = nFloats; this->fftSize = fftSize;
+        if (gridSizes) std::memcpy(grid, gridSizes, sizeof(grid));
+        wavesDirty = true;
+    }
+    Scalar getLiquidDensity() const { return density; }
+    Scalar getGravity() const { return g; }
+
+    void Fill(sfh_ocean& o) const
+    {
+        if (currents.size() > SFH_MAX_CURRENTS) throw std::runtime_error("more than 64 velocity fields");
+        std::memset(&o, 0, offsetof(sfh_ocean, currents));
+        o.density = density; o.gravity_z = g;
+        o.has_waves = hasWaves(); o.currents_enabled = currentsEnabled; o.n_currents = (uint32_t)currents.size();
+        for (size_t i = 0; i < currents.size(); ++i) {
+            std::memset(&o.currents[i], 0, sizeof(sfh_current));
+            o.currents[i].enabled = currents[i]->isEnabled();
+            currents[i]->Fill(o.currents[i]);
+        }
+    }
+    bool TakeWavesDirty(sfh_waves& w)
+    {
+        if (!wavesDirty || !fftData) return false;
+        w.fft_size = fftSize; std::memcpy(w.grid_sizes, grid, sizeof(grid)); w.data = fftData; w.n_floats = fftFloats;
+        wavesDirty = false;
+        return true;
+    }
+
+private:
+    Scalar density, g;
+    std::vector<std::unique_ptr<VelocityField>> currents;
+    bool currentsEnabled = false;
+    const float* fftData = nullptr;
+    size_t fftFloats = 0;
+    int fftSize = 256;
+    float grid[4] = {893.f, 101.f, 21.f, 11.f}; // OpenGLOcean.cpp:70
+    bool wavesDirty = false;
+};
+
+// ------------------------------------------------------------------------------------------------ bodies
+//! The members SolidEntity::ComputeHydrodynamicForces reads from a body (SolidEntity.cpp:1799-1850).
+struct SolidBody {
+    uint32_t meshId = 0;           // from HydroEngine::UploadMesh(getPhysicsMesh())
+    bool buoyant = true;           // isBuoyant()
+    Vector3 fdCd{1, 1, 1}, fdCf{0, 0, 0};
+    Scalar volume = 0, surface = 0;
+    Vector3 P_CB;                  // centre of buoyancy in the CG frame
+    // per step:
+    Transform T_CG, T_C, T_O;      // getCGTransform(), getCTransform(), getOTransform()
+    Vector3 v, omega;              // getLinearVelocity(), getAngularVelocity()
+    Vector3 aabbMin, aabbMax;      // getAABB()
+    HydrodynamicsInfo info;        // outputs, with the reference's "leave untouched" semantics
+};
+
+//! One GPU worth of hydrodynamics: replaces the ThreadPool-driven loop of SimulationManager::SimulationTickCallback
+//! (SimulationManager.cpp:1619-1655). Not copyable; one per GPU.
+class HydroEngine {
+public:
+    explicit HydroEngine(int cudaDevice = 0)
+    {
+        if (sfh_create(cudaDevice, &ctx) != SFH_OK) throw std::runtime_error(std::string("sfh_create: ") + sfh_last_error(nullptr));
+    }
+    ~HydroEngine() { sfh_destroy(ctx); }
+    HydroEngine(const HydroEngine&) = delete;
+    HydroEngine& operator=(const HydroEngine&) = delete;
+
+    //! Upload a physics mesh once: pass Mesh::getVertexDataPointer(), getVertexSize(), getNumOfVertices(),
+    //! getFaceDataPointer(), faces.size() (OpenGLDataStructs.h:120-262).
+    uint32_t UploadMesh(const void* vertexData, size_t vertexSize, size_t numVertices, const void* faceData, size_t numFaces)
+    {
+        uint32_t id = 0;
+        Check(sfh_mesh_upload(ctx, vertexData, vertexSize, (uint32_t)numVertices, static_cast<const uint32_t*>(faceData), (uint32_t)numFaces, 0, &id),
+              "sfh_mesh_upload");
+        return id;
+    }
+
+    //! settings = {true, true} and recompute = true reproduce Ocean::ApplyFluidForces (Ocean.cpp:246-254) for every
+    //! body of the batch: CheckBodyFluidPosition, the Surface/Submerged integrators, CorrectHydrodynamicForces.
+    //! Results land in bodies[i]->info; buoyancy/damping members the reference would leave untouched stay untouched.
+    void ComputeHydrodynamicForces(const HydrodynamicsSettings& settings, Ocean& ocn, const std::vector<SolidBody*>& bodies)
+    {
+        sfh_waves w;
+        if (ocn.TakeWavesDirty(w)) Check(sfh_waves_upload(ctx, &w), "sfh_waves_upload");
+        ocn.Fill(ocean);
+        states.resize(bodies.size());
+        infos.resize(bodies.size());
+        for (size_t i = 0; i < bodies.size(); ++i) {
+            const SolidBody& b = *bodies[i];
+            sfh_body_state& s = states[i];
+            std::memset(&s, 0, sizeof(s));
+            s.mesh_id = b.meshId;
+            s.mode = SFH_POS_AUTO;
+            s.flags = (uint32_t)SFH_F_DISPATCH | (settings.dampingForces ? (uint32_t)SFH_F_DAMPING : 0u) |
+                      (settings.reallisticBuoyancy ? (uint32_t)SFH_F_BUOYANCY : 0u) | (b.buoyant ? (uint32_t)SFH_F_BUOYANT : 0u);
+            std::memcpy(s.T_CG, b.T_CG.m, sizeof(s.T_CG));
+            std::memcpy(s.T_C, b.T_C.m, sizeof(s.T_C));
+            std::memcpy(s.T_O_basis, b.T_O.m, sizeof(s.T_O_basis));
+            Put(s.v, b.v); Put(s.omega, b.omega); Put(s.aabb_min, b.aabbMin); Put(s.aabb_max, b.aabbMax);
+            Put(s.Cd, b.fdCd); Put(s.Cf, b.fdCf); Put(s.P_CB, b.P_CB);
+            s.volume = b.volume; s.surface = b.surface;
+        }
+        Check(sfh_step(ctx, &ocean, states.data(), (uint32_t)states.size(), infos.data()), "sfh_step");
+        for (size_t i = 0; i < bodies.size(); ++i) Scatter(infos[i], bodies[i]->info);
+    }
+
+    //! Batched Ocean::GetDepth(glm::vec3) / Ocean::GetFluidVelocity(glm::vec3) (Ocean.cpp:149-168, 198-201).
+    void GetDepth(Ocean& ocn, const float* xyz, size_t n, float* depth)
+    {
+        sfh_waves w;
+        if (ocn.TakeWavesDirty(w)) Check(sfh_waves_upload(ctx, &w), "sfh_waves_upload");
+        ocn.Fill(ocean);
+        Check(sfh_query_depth(ctx, &ocean, xyz, (uint32_t)n, depth), "sfh_query_depth");
+    }
+    void GetFluidVelocity(Ocean& ocn, const float* xyz, size_t n, float* vel)
+    {
+        ocn.Fill(ocean);
+        Check(sfh_query_fluid_velocity(ctx, &ocean, xyz, (uint32_t)n, vel), "sfh_query_fluid_velocity");
+    }
+
+    sfh_ctx* raw() { return ctx; }
+
+private:
+    static void Put(double* d, const Vector3& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
+    static Vector3 Get(const double* d) { return Vector3(d[0], d[1], d[2]); }
+    void Check(int rc, const char* what)
+    {
+        if (rc != SFH_OK) throw std::runtime_error(std::string(what) + ": " + sfh_last_error(ctx));
+    }
+    static void Scatter(const sfh_info& r, HydrodynamicsInfo& o)
+    {
+        if (r.wrote_buoyancy) { o.Fb = Get(r.Fb); o.Tb = Get(r.Tb); }
+        // Vsub follows the reference: written with the buoyancy by the Surface integrator, zeroed when OUTSIDE,
+        // untouched when INSIDE (SolidEntity.cpp:1692,1819,1840)
+        if (r.wrote_buoyancy && r.position != SFH_POS_INSIDE) o.Vsub = r.Vsub;
+        if (r.wrote_damping) { o.Fdq = Get(r.Fdq); o.Tdq = Get(r.Tdq); o.Fdf = Get(r.Fdf); o.Tdf = Get(r.Tdf); }
+        o.Swet = r.Swet;
+        o.position = (BodyFluidPosition)r.position;
+        o.faces = r.n_faces; o.degenerate = r.n_degenerate; o.quadratic = r.n_quadratic; o.skin = r.n_skin;
+        for (int k = 0; k < 8; ++k) o.classCount[k] = r.class_count[k];
+    }
+
+    sfh_ctx* ctx = nullptr;
+    sfh_ocean ocean;
+    std::vector<sfh_body_state> states;
+    std::vector<sfh_info> infos;
+};
+
+} // namespace sfb

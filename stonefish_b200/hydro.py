@@ -72,6 +72,7 @@ class Jet(VelocityField):  # Jet.cpp:31-75
     def __init__(self, point, direction, radius, outletVelocity):
         super().__init__()
         d = _v3(direction)
+        self.direction = d.copy()  # constructor argument, kept so scenes can be replayed through other bindings
         self.c = _v3(point)
         # btVector3::normalized(): *this / length() == *this * (1.0 / sqrt(x*x + y*y + z*z))
         self.n = d * (1.0 / np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
@@ -93,6 +94,7 @@ class Pipe(VelocityField):  # Pipe.cpp:31-78
     def __init__(self, point1, point2, radius1, radius2, inletVelocity, exponent):
         super().__init__()
         p1, p2 = _v3(point1), _v3(point2)
+        self.p2 = p2.copy()
         d = p2 - p1
         self.p1 = p1
         self.l = float(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))

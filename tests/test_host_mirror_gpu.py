@@ -1,0 +1,76 @@
+"""The C++ host mirror (stonefish_b200/host/StonefishHydro.hpp: sfb::Ocean, sfb::Jet/Pipe/Uniform, sfb::HydroEngine::
+ComputeHydrodynamicForces) driven by the demo executable on a FluidDynamicsTest-style scene, against the CPU oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from stonefish_b200 import Jet, Pipe, Uniform, scenes
+from stonefish_b200.hydro import INFO_DTYPE
+from tests.parity import REL_TOL, max_rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEMO = os.path.join(ROOT, "stonefish_b200", "host", "demo_fluid_dynamics")
+
+
+def write_scene(path, sc):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<IIIddII", 0x53484653, len(sc.meshes), sc.n_bodies, sc.ocean.density, sc.ocean.gravity,
+                            1 if sc.ocean.currentsEnabled else 0, len(sc.ocean.currents)))
+        for c in sc.ocean.currents:
+            if isinstance(c, Uniform):
+                t, a = 0, list(c.v) + [0.0] * 7
+            elif isinstance(c, Jet):
+                t, a = 1, list(c.c) + list(c.direction) + [c.r, c.vout, 0.0, 0.0]
+            else:
+                assert isinstance(c, Pipe)
+                t, a = 2, list(c.p1) + list(c.p2) + [c.r1, c.r2, c.vin, c.gamma]
+            f.write(struct.pack("<II10d", t, 1 if c.isEnabled() else 0, *a))
+        for m in sc.meshes:
+            f.write(struct.pack("<III", m.n_verts, m.stride_bytes, m.n_faces))
+            f.write(m.vertex_data.tobytes())
+            f.write(m.faces.tobytes())
+        st = sc.states
+        for k in range(sc.n_bodies):
+            f.write(struct.pack("<II", int(sc.body_mesh[k]), 1 if st["flags"][k] & 4 else 0))
+            T_O = np.concatenate([st["T_O_basis"][k], np.zeros(3)])
+            for arr in (st["T_CG"][k], st["T_C"][k], T_O, st["v"][k], st["omega"][k], st["aabb_min"][k], st["aabb_max"][k], st["Cd"][k],
+                        st["Cf"][k], [st["volume"][k], st["surface"][k]], st["P_CB"][k]):
+                f.write(np.asarray(arr, dtype=np.float64).tobytes())
+
+
+def read_results(path, n):
+    rec = np.dtype([("d", np.float64, 20), ("u", np.uint32, 13)])
+    raw = np.fromfile(path, dtype=rec, count=n)
+    out = np.zeros(n, dtype=INFO_DTYPE)
+    for i, k in enumerate(("Fb", "Tb", "Fdq", "Tdq", "Fdf", "Tdf")):
+        out[k] = raw["d"][:, 3 * i:3 * i + 3]
+    out["Swet"], out["Vsub"] = raw["d"][:, 18], raw["d"][:, 19]
+    out["position"], out["n_faces"] = raw["u"][:, 0], raw["u"][:, 1]
+    out["class_count"] = raw["u"][:, 2:10]
+    out["n_degenerate"], out["n_quadratic"], out["n_skin"] = raw["u"][:, 10], raw["u"][:, 11], raw["u"][:, 12]
+    return out
+
+
+def test_cpp_host_mirror_runs_the_fluid_dynamics_scene(tmp_path, oracle):
+    assert os.path.exists(DEMO), "build the host mirror demo first (make -C stonefish_b200/host)"
+    sc = scenes.config1()
+    sc.ocean.AddVelocityField(Uniform((0.2, -0.1, 0.0)))
+    sc.ocean.AddVelocityField(Jet((0.0, -3.0, 1.0), (0.1, 1.0, 0.05), 0.3, 5.0))
+    sc.ocean.AddVelocityField(Pipe((-6.0, 0.5, 1.5), (6.0, -0.5, 2.0), 2.0, 3.0, 2.0, 2.0))
+    sc.ocean.EnableCurrents()
+    scene, res = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(scene, sc)
+    txt = subprocess.check_output([DEMO, scene, res, "5"], text=True)
+    assert txt.startswith("Hydrodynamics time: ")  # the reference's only live output (FluidDynamicsTestManager.cpp:166)
+    got = read_results(res, sc.n_bodies)
+    ref, _ = oracle.OracleScene(sc.meshes, sc.body_mesh, sc.ocean, sc.states).step(1, n_threads=4)
+    for k in ("class_count", "n_degenerate", "n_faces", "position"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.abs(got["n_quadratic"].astype(int) - ref["n_quadratic"].astype(int)).max() <= 1  # exp/pow 1-2 ulp, see DESIGN.md
+    err, where = max_rel_err(got, ref)
+    assert err <= REL_TOL, (err, where)
+    assert set(np.unique(got["position"])) == {0, 1, 2}
