@@ -158,7 +158,7 @@ namespace sfh {
 // acc: [0..11] Fdq Tdq Fdf Tdf | [12..14] Fb | [15..17] Tb | [18] Swet | [19] Vsub | [20..22] CBsub
 // ---------------------------------------------------------------------------------------------
 template <bool WAVES, int CUR, bool DEBUG>
-__global__ void __launch_bounds__(SFH_BLOCK) k_surface(StepParams P)
+__global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
 {
     __shared__ ChunkPipe s_pipe;
     __shared__ float4 s_v[SFH_CH_VERTS]; // world x,y,z and depth

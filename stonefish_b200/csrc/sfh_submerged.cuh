@@ -51,6 +51,7 @@ __device__ __forceinline__ void acc6(double* a, float x0, float x1, float x2, fl
 
 struct BodyP2 { // per-body constants broadcast to both lanes
     V3P p, v, omega, cur;
+    float R[9], t[3]; // T_C, for the per-chunk vertex transform
 };
 
 // Damping block for a pair of faces (SolidEntity.cpp:1771-1790 / 1661-1683). mA/mB: the face exists and is not
@@ -85,7 +86,7 @@ __device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_curr
     }
     const P2 vt2 = dot(vt, vt);
     const bool sA = mA && lo(vt2) > 1e-9f, sB = mB && hi(vt2) > 1e-9f;
-    if (__any_sync(SFH_FULL, sA | sB)) {
+    { // nearly every face has tangential flow: no warp vote
         const V3P s = vt * A;
         const V3P ts = cross(r, s);
         if (sA) acc6(acc + 6, lo(s.x), lo(s.y), lo(s.z), lo(ts.x), lo(ts.y), lo(ts.z));
@@ -178,6 +179,10 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
         B.v = V3P{pk1(s_body.v[0]), pk1(s_body.v[1]), pk1(s_body.v[2])};
         B.omega = V3P{pk1(s_body.omega[0]), pk1(s_body.omega[1]), pk1(s_body.omega[2])};
         B.cur = V3P{pk1(s_body.cur[0]), pk1(s_body.cur[1]), pk1(s_body.cur[2])};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) B.R[k] = s_body.R[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) B.t[k] = s_body.t[k];
     };
     auto flush = [&](uint32_t body) {
         spill_epack(epack, s_cnt);
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
         for (int k = 0; k < 2; ++k) {
             const uint32_t i = tid + k * SFH_BLOCK;
             if (i < cv.nv) {
-                const F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
+                const F3 pw = xform(B.R, B.t, cv.x[i], cv.y[i], cv.z[i]);
                 s_v[i] = make_float4(pw.x, pw.y, pw.z, 0.f);
             }
         }
@@ -229,17 +234,26 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
             const bool dA = lo(len2) < 1e-12f, dB = hi(len2) < 1e-12f; // SolidEntity.cpp:1764
             const bool mA = vA && !dA, mB = vB && !dB;
             epack += (vA && dA ? 1u : 0u) + (vB && dB ? 1u : 0u);
-            uint32_t code = 0;
-            if (__any_sync(SFH_FULL, mA | mB)) {
-                // len2 >= 1e-12 > 2^-101 on every lane that is used
+            uint32_t code;
+            {
+                // len2 >= 1e-12 > 2^-101 on every lane that is used (unused lanes compute garbage that is masked out)
                 const P2 len = ieee_sqrt2(len2);
                 const P2 A = len * pk1(0.5f); // len / 2.f, exact scaling
                 const V3P csum = (p1 + p2) + p3;
-                if ((min_key(fn) >= SFH_NUM_KEY) & (min_key(csum) >= SFH_TINY_KEY)) {
+                // Range guard of the shared-reciprocal / multiply-by-1/3 forms, cheap test first: every |fn_i| >= 2^-36
+                // (its square, already needed for len2, >= 2^-72) and every |csum_i| >= 2^-100. Faces with an exactly
+                // zero component (axis-aligned geometry) fail it and take the exact integer test, which accepts zeros.
+                const P2 sx = fn.x * fn.x, sy = fn.y * fn.y, sz = fn.z * fn.z;
+                const float m_fn = fminf(fminf(fminf(lo(sx), lo(sy)), lo(sz)), fminf(fminf(hi(sx), hi(sy)), hi(sz)));
+                const float m_cs = fminf(fminf(fminf(fabsf(lo(csum.x)), fabsf(lo(csum.y))), fabsf(lo(csum.z))),
+                                         fminf(fminf(fabsf(hi(csum.x)), fabsf(hi(csum.y))), fabsf(hi(csum.z))));
+                bool fast = (m_fn >= 0x1p-72f) & (m_cs >= 0x1p-100f);
+                if (!fast) fast = (min_key(fn) >= SFH_NUM_KEY) & (min_key(csum) >= SFH_TINY_KEY);
+                if (fast) {
                     const V3P fn1 = normalize_fast(fn, len);
                     const V3P fc = {ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)};
                     code = damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
-                } else { // operands outside the proven range of the shared-reciprocal / multiply-by-1/3 forms
+                } else { // operands outside the proven range: hardware divisions
                     V3P fn1, fc;
                     normalize_centroid_slow(fn, len, csum, fn1, fc);
                     code = damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
