@@ -78,10 +78,11 @@ __global__ void k_selftest(uint32_t which, uint64_t n, unsigned long long* misma
             };
             const float a0 = rnd(h, -20, 20), a1 = rnd(mix64(h + 1), -20, 20), b0 = rnd(g, -20, 20), b1 = rnd(mix64(g + 1), -20, 20);
             const float c0 = rnd(mix64(h + 2), -20, 20), c1 = rnd(mix64(g + 2), -20, 20);
-            const P2 A = pk(a0, a1), Bv = pk(b0, b1), Cv = pk(c0, c1);
-            const P2 s = A + Bv, d = A - Bv, m = A * Bv;
+            // always the packed f32x2 carrier, whatever the build's default pair type is
+            const PairX A = PairX::make(a0, a1), Bv = PairX::make(b0, b1), Cv = PairX::make(c0, c1);
+            const PairX s = A + Bv, d = A - Bv, m = A * Bv;
             // the patterns ptxas would like to contract: product feeding a sum / a difference
-            const P2 ms = A * Bv + Cv, md = A * Bv - Cv * A, dt = (A * A + Bv * Bv) + Cv * Cv;
+            const PairX ms = A * Bv + Cv, md = A * Bv - Cv * A, dt = (A * A + Bv * Bv) + Cv * Cv;
             bool ok = same_bits(lo(s), __fadd_rn(a0, b0)) && same_bits(hi(s), __fadd_rn(a1, b1));
             ok &= same_bits(lo(d), __fsub_rn(a0, b0)) && same_bits(hi(d), __fsub_rn(a1, b1));
             ok &= same_bits(lo(m), __fmul_rn(a0, b0)) && same_bits(hi(m), __fmul_rn(a1, b1));
@@ -89,12 +90,12 @@ __global__ void k_selftest(uint32_t which, uint64_t n, unsigned long long* misma
             ok &= same_bits(lo(md), __fsub_rn(__fmul_rn(a0, b0), __fmul_rn(c0, a0))) && same_bits(hi(md), __fsub_rn(__fmul_rn(a1, b1), __fmul_rn(c1, a1)));
             ok &= same_bits(lo(dt), __fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(b0, b0)), __fmul_rn(c0, c0)));
             ok &= same_bits(hi(dt), __fadd_rn(__fadd_rn(__fmul_rn(a1, a1), __fmul_rn(b1, b1)), __fmul_rn(c1, c1)));
-            const P2 x2 = pk(fabsf(a0), fabsf(a1));
-            const P2 sq = ieee_sqrt2(x2), d3 = ieee_div3_2(A);
+            const PairX x2 = PairX::make(fabsf(a0), fabsf(a1));
+            const PairX sq = ieee_sqrt2(x2), d3 = ieee_div3_2(A);
             ok &= same_bits(lo(sq), __fsqrt_rn(fabsf(a0))) && same_bits(hi(sq), __fsqrt_rn(fabsf(a1)));
             ok &= same_bits(lo(d3), __fdiv_rn(a0, 3.f)) && same_bits(hi(d3), __fdiv_rn(a1, 3.f));
-            const P2 len = pk(fabsf(b0), fabsf(b1)), nlen = neg(len);
-            const P2 q = ieee_div_r2(A, nlen, refined_rcp2(len, nlen));
+            const PairX len = PairX::make(fabsf(b0), fabsf(b1)), nlen = neg(len);
+            const PairX q = ieee_div_r2(A, nlen, refined_rcp2(len, nlen));
             if (fabsf(a0) <= 2.f * fabsf(b0) && fabsf(a1) <= 2.f * fabsf(b1))
                 ok &= same_bits(lo(q), __fdiv_rn(a0, fabsf(b0))) && same_bits(hi(q), __fdiv_rn(a1, fabsf(b1)));
             if (!ok) { ++bad; first_bad = i; }

@@ -1,11 +1,11 @@
 // sfh_submerged.cuh — k_submerged: SolidEntity::ComputeHydrodynamicForcesSubmerged (SolidEntity.cpp:1749-1791)
-// over (body, chunk) work items, two faces per thread on the packed fp32 pipe.
+// over (body, chunk) work items, two faces per thread (two independent fp32 streams; FMUL2/FFMA2 with -DSFH_PACKED_F32X2).
 //
 // Per chunk a block of 128 threads
 //   1. transforms the chunk's <=256 vertices ONCE into shared memory (reference: once per incident face,
 //      SolidEntity.cpp:1755-1757 — identical bits),
 //   2. has the NEXT chunk (of this or of the next body) already in flight as one bulk async copy (sfh_chunkpipe.cuh),
-//   3. evaluates faces tid and tid+128 as the two lanes of FADD2/FMUL2/FFMA2 instructions, with the IEEE
+//   3. evaluates faces tid and tid+128 side by side (P2 = one value per face), with the IEEE
 //      divisions and square roots written out (sfh_packed.cuh),
 //   4. adds the fp32 per-face terms into per-thread fp64 accumulators.
 // Accumulators are reduced per (block, body) and written as one partial record (see sfh_kernels.cuh).
@@ -211,7 +211,11 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
         for (int k = 0; k < 2; ++k) {
             const uint32_t i = tid + k * SFH_BLOCK;
             if (i < cv.nv) {
+                #ifndef SFH_PACKED_F32X2
+                const F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]); // keeps the default build at 96 registers
+#else
                 const F3 pw = xform(B.R, B.t, cv.x[i], cv.y[i], cv.z[i]);
+#endif
                 s_v[i] = make_float4(pw.x, pw.y, pw.z, 0.f);
             }
         }

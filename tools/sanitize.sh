@@ -1,0 +1,20 @@
+#!/bin/bash
+# compute-sanitizer memcheck + racecheck + synccheck of every kernel (prologue, scan, submerged, surface with waves and
+# Jet/Pipe currents, epilogue) through the C++ host mirror demo on a small mixed scene. Run on the GPU box:
+#   bash tools/sanitize.sh > gpurun_out/sanitize.log
+set -e
+cd "$(dirname "$0")/.."
+python - <<'PY'
+import sys
+sys.path.insert(0, ".")
+from stonefish_b200 import scenes
+from tests.test_host_mirror_gpu import write_scene
+sc = scenes.mixed_small(3, False, "jetpipe")
+sc.states["mode"] = 3            # AUTO, as the host mirror sends it
+write_scene("/tmp/sanitize_scene.bin", sc)
+print("scene written:", sc.n_bodies, "bodies", sc.faces_per_step(), "faces")
+PY
+for tool in memcheck racecheck synccheck; do
+  echo "== compute-sanitizer --tool $tool"
+  compute-sanitizer --tool $tool --error-exitcode 9 stonefish_b200/host/demo_fluid_dynamics /tmp/sanitize_scene.bin /tmp/sanitize_out.bin 2 2>&1 | tail -4
+done
