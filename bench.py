@@ -102,11 +102,14 @@ class ClockSampler:
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.thread, self.idx = [], None, None, gpu_index
+        self.rows, self.proc, self.thread, self.idx, self.first = [], None, None, gpu_index, 0
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -121,14 +124,14 @@ class ClockSampler:
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in (self.rows[self.first:] or self.rows):  # a very short timed region: fall back to warm-up samples
             if len(r) < 9:
                 continue
             try:
@@ -257,11 +260,12 @@ def run_ours(args):
 
     # ---- value: device-resident, CUDA events on the launching stream
     with torch.cuda.stream(stream):
+        sampler = ClockSampler(local_rank)
+        sampler.start()  # nvidia-smi needs ~0.1-0.3 s to start streaming: launch it before the warm-up
         for _ in range(args.warmup):
             step_device()
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler.mark()   # samples from here to stop() are inside the timed regions (device, kernel and e2e loops)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
@@ -353,7 +357,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg4-shared", "cfg2", "cfg3", "cfg3-flat", "cfg5"])
