@@ -2,8 +2,10 @@
 (Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:168-249) and against hand-computable cases of the wave lookup."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
+import pytest
 
 from stonefish_b200 import _abi, meshes, scenes
 from stonefish_b200.hydro import Mesh, Ocean, Uniform, make_transform, new_body_states, quat_to_basis
@@ -168,3 +170,21 @@ def test_step_schedule_one_task_per_body_matches_serial(oracle):
     assert a.tobytes() == b.tobytes() and secs > 0
     split, _ = o.body_split(1, 3)
     np.testing.assert_allclose(split["Fdq"], o.body(1, 1)["Fdq"], rtol=1e-12, atol=1e-12)
+
+
+REF_DATA = "/root/reference/Tests/Data"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DATA, "hull_hydro.obj")), reason="reference checkout not mounted")
+def test_reference_hull_volume_known_answer(oracle):
+    """The one number the reference's (commented-out) checks pin on this path's geometry: the volume of
+    Tests/Data/hull_hydro.obj is 0.096699 (FluidDynamicsTestManager.cpp:207, tolerance 1e-6 in sf::testScalar). Pushed
+    through the Surface integrator fully under a flat sea, the tetrahedron sum must reproduce it, in both modes."""
+    m = meshes.load_obj(os.path.join(REF_DATA, "hull_hydro.obj"))
+    assert m.n_faces == 2880
+    q = scenes.euler_zyx_quat(0.0, 0.5, 0.0)  # the pose FluidDynamicsTest gives the hull, lowered under water
+    o = oracle.OracleScene(*_scene(m, make_transform(quat_to_basis(q), (8.0, 0.0, 5.0)), _abi.SFH_POS_CROSSING, 3))
+    for mode, tol in ((1, 1e-6), (0, 1e-6)):
+        r = o.body(0, mode)
+        assert abs(r["Vsub"] - 0.096699) < tol, (mode, r["Vsub"])
+        assert r["Fb"][2] == -r["Vsub"] * 1000.0 * 9.81

@@ -1,0 +1,17 @@
+"""Where does k_surface spend its time? Same 16 x 1M-face vessels with waves / Jet+Pipe currents switched off in turn."""
+import sys, numpy as np
+sys.path.insert(0, ".")
+from stonefish_b200 import HydroContext, scenes
+ctx = HydroContext(0)
+sc = scenes.config5(16, 1000, 501, unique_meshes=False)
+st = sc.bind(ctx)
+ctx.set_profiling(True)
+def run(tag):
+    for _ in range(3): ctx.compute(sc.ocean, st)
+    t = [ctx.timings().surface_ms for _ in range(5) if ctx.compute(sc.ocean, st) is not None]
+    print(f"{tag:40s} k_surface {np.mean(t):.3f} ms  ({16e6/np.mean(t)/1e6:.1f} G faces/s)")
+run("waves + Jet+Pipe")
+sc.ocean.DisableCurrents(); run("waves, no currents")
+sc.ocean.EnableCurrents(); sc.ocean.setWaves(None); run("flat, Jet+Pipe")
+sc.ocean.DisableCurrents(); run("flat, no currents")
+st2 = st.copy(); st2["flags"] = 1; run("flat, no currents (same)")
