@@ -320,6 +320,15 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of the same
+        # kernel on the same meshes (profiles/ncu_traffic_r01.json: dram__bytes_read.sum + dram__bytes_write.sum at
+        # 1024 bodies), scaled by face count; null for workloads that capture does not describe.
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+        if args.workload == "cfg4" and dominant == "k_submerged" and os.path.exists(tpath):
+            t = json.load(open(tpath))
+            traffic = int(t["dram_bytes_per_face"] * faces)
+            traffic_src = f"{t['dram_bytes_per_face']:.2f} B/face measured by ncu ({t['report']}) x {faces} faces"
         line = {
             "metric": METRIC, "value": total_faces * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -332,7 +341,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
                          "kernel_ms": kern_ms, "prologue_ms": float(np.mean(pro_ms)), "epilogue_ms": float(np.mean(epi_ms)),
                          "bytes_per_face": ALGO_BYTES_PER_FACE_NOTE},
             "clocks": clocks,

@@ -87,6 +87,23 @@ struct sfh_ctx {
     int occ_sub[2] = {0, 0};
     int occ_surf[2][2] = {{0, 0}, {0, 0}};
 
+    // CUDA-graph replay of small steps (launch-latency bound): see step_host
+    struct GraphKey {
+        uint32_t n, n_currents, n_meshes, flags; // flags: general | waves<<1 | may_sub<<2 | may_surf<<3
+        uint64_t chunks_ub;
+        const void *d_states, *d_info, *h_states, *h_info, *h_ocean, *d_ocean, *d_meshes, *d_bodies, *d_part_sub, *d_part_surf, *wave_ch0;
+        int32_t wave_n;
+        float wave_gx, wave_gy;
+    };
+    struct GraphEntry {
+        GraphKey key;
+        cudaGraphExec_t exec;
+    };
+    std::vector<GraphEntry> graphs;
+    GraphKey last_key{};
+    bool last_key_valid = false;
+    uint64_t graph_launches = 0;
+
     // profiling
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -175,8 +192,11 @@ int occupancy(sfh_ctx* ctx, K kernel, int* cache)
     return SFH_OK;
 }
 
-// Fill the device ocean record (pinned staging -> device) and report which kernel variants the step needs.
-int stage_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
+#define SFH_GRAPH_MAX_BODIES 1024u
+
+// Write the ocean record into the pinned staging buffer (no CUDA call after the first) and report whether some
+// enabled current needs the per-face fp64 evaluation.
+int fill_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
 {
     if (o->n_currents > SFH_MAX_CURRENTS) return fail(ctx, SFH_ERR_INVALID, "n_currents %u > %u", o->n_currents, SFH_MAX_CURRENTS);
     if (o->has_waves && !ctx->have_waves) return fail(ctx, SFH_ERR_STATE, "ocean.has_waves set but sfh_waves_upload was never called");
@@ -197,8 +217,16 @@ int stage_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
     }
     h->cur_general = general ? 1u : 0u;
     *cur_general = general;
+    return SFH_OK;
+}
+
+// fill_ocean + the (stream-ordered) copy to the device
+int stage_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
+{
+    int rc = fill_ocean(ctx, o, cur_general);
+    if (rc != SFH_OK) return rc;
     const size_t bytes = offsetof(OceanDev, currents) + sizeof(sfh_current) * (o->n_currents ? o->n_currents : 1);
-    CU(ctx, cudaMemcpyAsync(ctx->d_ocean.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_ocean.p, ctx->h_ocean.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return SFH_OK;
 }
 
@@ -366,8 +394,76 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
     if ((rc = ensure_dev(ctx, ctx->d_states, n)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_info, n)) != SFH_OK) return rc;
 
-    if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     const size_t sbytes = (size_t)n * sizeof(sfh_body_state);
+    const size_t obytes = (size_t)n * sizeof(sfh_info);
+
+    // Small steps are launch-latency bound (2 copies in, 5 kernels, 2 copies out): once the same step shape has been
+    // seen twice in a row it is captured into a CUDA graph and replayed with one launch. Everything a graph node
+    // reads is at a fixed address: states/results/ocean go through the context's pinned staging buffers.
+    const bool graphable = !debug && !ctx->profiling && n <= SFH_GRAPH_MAX_BODIES;
+    if (graphable) {
+        if ((rc = ensure_pin(ctx, ctx->h_states, sbytes)) != SFH_OK) return rc;
+        if ((rc = ensure_pin(ctx, ctx->h_info, obytes)) != SFH_OK) return rc;
+        if ((rc = ensure_pin(ctx, ctx->h_status, 16)) != SFH_OK) return rc;
+        if ((rc = sync_mesh_table(ctx)) != SFH_OK) return rc; // may synchronise: never inside a capture
+        bool general = false;
+        for (uint32_t i = 0; i < ocean->n_currents && i < SFH_MAX_CURRENTS; ++i)
+            if (ocean->currents_enabled && ocean->currents[i].enabled && ocean->currents[i].type != SFH_CURRENT_UNIFORM) general = true;
+        sfh_ctx::GraphKey key;
+        std::memset(&key, 0, sizeof(key));
+        key.n = n; key.n_currents = ocean->n_currents; key.n_meshes = (uint32_t)ctx->meshes.size();
+        key.flags = (general ? 1u : 0u) | (ocean->has_waves ? 2u : 0u) | (plan.may_sub ? 4u : 0u) | (plan.may_surf ? 8u : 0u);
+        key.chunks_ub = plan.chunks_ub;
+        key.d_states = ctx->d_states.p; key.d_info = ctx->d_info.p; key.h_states = ctx->h_states.p; key.h_info = ctx->h_info.p;
+        key.h_ocean = ctx->h_ocean.p; key.d_ocean = ctx->d_ocean.p; key.d_meshes = ctx->d_meshes.p; key.d_bodies = ctx->d_bodies.p;
+        key.d_part_sub = ctx->d_part_sub.p; key.d_part_surf = ctx->d_part_surf.p;
+        key.wave_ch0 = ctx->waves.ch0; key.wave_n = ctx->waves.N; key.wave_gx = ctx->waves.gx; key.wave_gy = ctx->waves.gy;
+
+        std::memcpy(ctx->h_states.p, states, sbytes);
+        cudaGraphExec_t exec = nullptr;
+        for (auto& g : ctx->graphs)
+            if (std::memcmp(&g.key, &key, sizeof(key)) == 0) exec = g.exec;
+        const bool capture = !exec && ctx->last_key_valid && std::memcmp(&ctx->last_key, &key, sizeof(key)) == 0 && ctx->d_status.p;
+        ctx->last_key = key;
+        ctx->last_key_valid = true;
+        if (exec) {
+            if ((rc = fill_ocean(ctx, ocean, &general)) != SFH_OK) return rc;
+            CU(ctx, cudaGraphLaunch(exec, ctx->stream));
+            ++ctx->graph_launches;
+        } else {
+            if (capture) CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            cudaError_t e = cudaMemcpyAsync(ctx->d_states.p, ctx->h_states.p, sbytes, cudaMemcpyHostToDevice, ctx->stream);
+            rc = (e == cudaSuccess) ? run_step(ctx, ocean, ctx->d_states.p, n, ctx->d_info.p, plan) : fail(ctx, SFH_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
+            if (rc == SFH_OK) {
+                e = cudaMemcpyAsync(ctx->h_info.p, ctx->d_info.p, obytes, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e != cudaSuccess) rc = fail(ctx, SFH_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
+            }
+            if (capture) {
+                cudaGraph_t graph = nullptr;
+                e = cudaStreamEndCapture(ctx->stream, &graph);
+                if (rc != SFH_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (e != cudaSuccess) return fail(ctx, SFH_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+                e = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) return fail(ctx, SFH_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+                if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+                ctx->graphs.push_back({key, exec});
+                CU(ctx, cudaGraphLaunch(exec, ctx->stream));
+                ++ctx->graph_launches;
+            } else if (rc != SFH_OK) {
+                return rc;
+            }
+        }
+        ctx->pending_out = out;
+        ctx->pending_out_bytes = obytes;
+        ctx->pending_codes = nullptr;
+        ctx->step_in_flight = true;
+        ctx->ev_valid = false;
+        return SFH_OK;
+    }
+
+    if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     const void* src = states;
     if (!is_pinned_host(states)) {
         if ((rc = ensure_pin(ctx, ctx->h_states, sbytes)) != SFH_OK) return rc;
@@ -387,7 +483,6 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
 
     if ((rc = run_step(ctx, ocean, ctx->d_states.p, n, ctx->d_info.p, plan)) != SFH_OK) return rc;
 
-    const size_t obytes = (size_t)n * sizeof(sfh_info);
     ctx->pending_out = nullptr;
     if (is_pinned_host(out)) {
         CU(ctx, cudaMemcpyAsync(out, ctx->d_info.p, obytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -471,6 +566,7 @@ void sfh_destroy(sfh_ctx* ctx)
     cudaFree(ctx->d_ocean.p); cudaFree(ctx->d_codes.p); cudaFree(ctx->d_code_base.p);
     for (PinBuf* b : {&ctx->h_mesh_table, &ctx->h_wave, &ctx->h_ocean, &ctx->h_states, &ctx->h_info, &ctx->h_status, &ctx->h_codes, &ctx->h_code_base})
         if (b->p) cudaFreeHost(b->p);
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

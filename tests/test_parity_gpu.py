@@ -190,3 +190,27 @@ def test_full_size_properties_config4(ctx):
     assert np.array_equal(a["n_quadratic"], b["n_quadratic"])
     np.testing.assert_allclose(b["Fdq"], 8 * a["Fdq"], rtol=1e-6, atol=0)  # vc * |vc| * (vc.n) * A: cubic in speed
     np.testing.assert_allclose(b["Fdf"], 2 * a["Fdf"], rtol=1e-6, atol=0)
+
+
+def test_graph_replay_of_small_steps_tracks_inputs(ctx, oracle):
+    """Steps with <=1024 bodies are captured into a CUDA graph on the second identical-shape call and replayed afterwards
+    (stonefish_b200/csrc/sfh.cu:step_host). Replays must see the new body states and ocean parameters of every step."""
+    sc = scenes.mixed_small(21, True, "jetpipe")
+    st = sc.bind(ctx)
+    first = ctx.compute(sc.ocean, st)
+    for rep in range(3):  # normal run, capture, replay: bit-identical
+        assert ctx.compute(sc.ocean, st).tobytes() == first.tobytes()
+    # new velocities and a retuned current, same shapes: the replayed graph must pick both up
+    st2 = st.copy()
+    st2["v"] *= 1.5
+    sc.ocean.currents[0].setVelocity((0.4, 0.0, -0.1))
+    sc.ocean.currents[1].setOutletVelocity(3.0)
+    got = ctx.compute(sc.ocean, st2)
+    sc2 = scenes.Scene(sc.name, sc.meshes, sc.body_mesh, sc.ocean, sc.states.copy())
+    sc2.states["v"] *= 1.5
+    ref, _ = oracle.OracleScene(sc2.meshes, sc2.body_mesh, sc2.ocean, sc2.states).step(1, n_threads=4)
+    for k in ("class_count", "n_degenerate", "n_faces", "position"):
+        assert np.array_equal(got[k], ref[k]), k
+    err, where = max_rel_err(got, ref)
+    assert err <= REL_TOL, (err, where)
+    assert got.tobytes() != first.tobytes()
