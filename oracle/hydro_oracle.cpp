@@ -708,6 +708,97 @@ void orc_body(const orc_mesh* mesh, const sfh_ocean* o, const sfh_waves* w, cons
         orc_correct(o->density, out->Fdq, out->Tdq, out->Fdf, out->Tdf, st->Cd, st->Cf, st->T_O_basis);
 }
 
+/* Compound::ComputeHydrodynamicForces (Compound.cpp:291-437) */
+void orc_compound(const orc_mesh* const* part_meshes, const sfh_body_state* parts, const uint32_t* external, uint32_t n_parts,
+                  const sfh_ocean* o, const sfh_waves* w, const sfh_body_state* compound, int acc_mode, sfh_info* out)
+{
+    zero_info(out);
+    uint32_t pos = compound->mode;
+    if (pos == SFH_POS_AUTO) pos = orc_check_body_fluid_position(o, w, compound->aabb_min, compound->aabb_max); /* :299 */
+    out->position = pos;
+    if (pos == SFH_POS_OUTSIDE) { /* :302-313 */
+        out->wrote_buoyancy = out->wrote_damping = 1;
+        return;
+    }
+    const bool damping = (compound->flags & SFH_F_DAMPING) != 0, rb = (compound->flags & SFH_F_BUOYANCY) != 0;
+    auto add3 = [](double* a, const double* b) { a[0] += b[0]; a[1] += b[1]; a[2] += b[2]; }; /* btVector3 += */
+    auto part_state = [&](uint32_t i, bool p_rb, bool p_df) {
+        sfh_body_state s = parts[i];
+        std::memcpy(s.T_CG, compound->T_CG, sizeof(s.T_CG)); /* getCGTransform() of the compound for every part */
+        std::memcpy(s.v, compound->v, sizeof(s.v));
+        std::memcpy(s.omega, compound->omega, sizeof(s.omega));
+        s.flags = (p_rb ? (uint32_t)SFH_F_BUOYANCY : 0u) | (p_df ? (uint32_t)SFH_F_DAMPING : 0u);
+        return s;
+    };
+    auto add_counters = [&](const sfh_info& r) {
+        for (int k = 0; k < 8; ++k) out->class_count[k] += r.class_count[k];
+        out->n_degenerate += r.n_degenerate; out->n_quadratic += r.n_quadratic; out->n_skin += r.n_skin; out->n_faces += r.n_faces;
+    };
+
+    if (pos == SFH_POS_INSIDE) { /* :315-363 */
+        if (compound->flags & SFH_F_BUOYANT) {
+            D3 gravity{0.0, 0.0, o->gravity_z};
+            D3 Fb = -compound->volume * o->density * gravity;
+            const double* B = compound->T_CG;
+            D3 pcb{compound->P_CB[0], compound->P_CB[1], compound->P_CB[2]}, org{B[9], B[10], B[11]};
+            D3 wcb{ddot(D3{B[0], B[1], B[2]}, pcb) + org.x, ddot(D3{B[3], B[4], B[5]}, pcb) + org.y, ddot(D3{B[6], B[7], B[8]}, pcb) + org.z};
+            D3 Tb = dcross(wcb - org, Fb);
+            out->Fb[0] = Fb.x; out->Fb[1] = Fb.y; out->Fb[2] = Fb.z;
+            out->Tb[0] = Tb.x; out->Tb[1] = Tb.y; out->Tb[2] = Tb.z;
+            out->wrote_buoyancy = 1;
+        }
+        if (damping) {
+            out->wrote_damping = 1;
+            for (uint32_t i = 0; i < n_parts; ++i) {
+                if (!external[i]) continue; /* drag only for external parts, :342-345 */
+                sfh_body_state s = part_state(i, false, true);
+                sfh_info r;
+                orc_submerged(part_meshes[i], o, &s, acc_mode, &r, nullptr);
+                orc_correct(o->density, r.Fdq, r.Tdq, r.Fdf, r.Tdf, parts[i].Cd, parts[i].Cf, parts[i].T_O_basis);
+                add3(out->Fdq, r.Fdq); add3(out->Tdq, r.Tdq); add3(out->Fdf, r.Fdf); add3(out->Tdf, r.Tdf);
+                add_counters(r);
+            }
+        }
+        out->Swet = compound->surface;
+        out->Vsub = compound->volume; /* :361-362 */
+        return;
+    }
+
+    /* CROSSING (compound body but not necessarily all parts!), :364-435 */
+    if (!(rb || damping)) return;
+    if (rb) out->wrote_buoyancy = 1;       /* Fb, Tb set to zero and accumulated below */
+    if (damping) out->wrote_damping = 1;
+    double Fbp[3] = {0, 0, 0}, Tbp[3] = {0, 0, 0}, Fdqp[3] = {0, 0, 0}, Tdqp[3] = {0, 0, 0}, Fdfp[3] = {0, 0, 0}, Tdfp[3] = {0, 0, 0};
+    double Swetp = 0, Vsubp = 0; /* temporaries that persist across parts (:391-398) */
+    for (uint32_t i = 0; i < n_parts; ++i) {
+        const bool p_rb = rb && (parts[i].flags & SFH_F_BUOYANT) != 0; /* pSettings.reallisticBuoyancy &= isBuoyant(), :409 */
+        auto run_surface = [&](bool p_df) {
+            sfh_body_state s = part_state(i, p_rb, p_df);
+            sfh_info r;
+            orc_surface(part_meshes[i], o, w, &s, acc_mode, &r, nullptr);
+            if (r.wrote_buoyancy) { std::memcpy(Fbp, r.Fb, sizeof(Fbp)); std::memcpy(Tbp, r.Tb, sizeof(Tbp)); Vsubp = r.Vsub; }
+            if (r.wrote_damping) {
+                std::memcpy(Fdqp, r.Fdq, sizeof(Fdqp)); std::memcpy(Tdqp, r.Tdq, sizeof(Tdqp));
+                std::memcpy(Fdfp, r.Fdf, sizeof(Fdfp)); std::memcpy(Tdfp, r.Tdf, sizeof(Tdfp));
+            }
+            Swetp = r.Swet;
+            add_counters(r);
+        };
+        if (external[i]) { /* buoyancy and drag, :411-425 */
+            run_surface(damping);
+            orc_correct(o->density, Fdqp, Tdqp, Fdfp, Tdfp, parts[i].Cd, parts[i].Cf, parts[i].T_O_basis);
+            add3(out->Fb, Fbp); add3(out->Tb, Tbp);
+            add3(out->Fdq, Fdqp); add3(out->Tdq, Tdqp); add3(out->Fdf, Fdfp); add3(out->Tdf, Tdfp);
+            out->Swet += Swetp;
+            out->Vsub += Vsubp;
+        } else if (p_rb) { /* only buoyancy, :426-433 */
+            run_surface(false);
+            add3(out->Fb, Fbp); add3(out->Tb, Tbp);
+            out->Vsub += Vsubp;
+        }
+    }
+}
+
 double orc_step(const orc_mesh* const* meshes, const sfh_ocean* o, const sfh_waves* w, const sfh_body_state* states,
                 uint32_t n_bodies, int acc_mode, int n_threads, sfh_info* out)
 {

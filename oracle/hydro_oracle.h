@@ -71,6 +71,15 @@ void orc_surface(const orc_mesh* mesh, const sfh_ocean* o, const sfh_waves* w, c
 void orc_body(const orc_mesh* mesh, const sfh_ocean* o, const sfh_waves* w, const sfh_body_state* st,
               int acc_mode, sfh_info* out, uint8_t* face_codes);
 
+/* Compound::ComputeHydrodynamicForces (Library/src/entities/solids/Compound.cpp:291-437).
+ * `compound` carries what belongs to the whole body: mode (incl. AUTO with the compound's AABB), flags
+ * (SFH_F_DAMPING/BUOYANCY = settings, SFH_F_BUOYANT = Compound::isBuoyant()), T_CG, v, omega, volume, surface, P_CB.
+ * parts[i] carries what belongs to part i: T_C = T_O * origin_i * O2C_i, T_O_basis of T_O * origin_i, Cd, Cf, and in
+ * flags SFH_F_BUOYANT = parts[i].solid->isBuoyant(); external[i] = parts[i].isExternal. Parts whose physics mode is not
+ * SUBMERGED/FLOATING are simply not passed. The temporaries Fbp..Vsubp persist across parts as in the reference. */
+void orc_compound(const orc_mesh* const* part_meshes, const sfh_body_state* parts, const uint32_t* external, uint32_t n_parts,
+                  const sfh_ocean* o, const sfh_waves* w, const sfh_body_state* compound, int acc_mode, sfh_info* out);
+
 /* Whole step, scheduled like the reference: one task per body on a pool of n_threads
  * (SimulationManager.cpp:1641-1651, utils/ThreadPool.hpp). meshes[i] is the mesh of body i.
  * Returns wall seconds spent between the first enqueue and waitAll (the PerformanceMonitor bracket,

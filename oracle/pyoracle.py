@@ -128,3 +128,23 @@ class OracleScene:
             infos.append(info)
             codes.append(c)
         return np.array(infos, dtype=INFO_DTYPE), np.concatenate(codes) if codes else np.zeros(0, np.uint8)
+
+
+def compound(meshes, part_mesh_idx, parts: np.ndarray, external, ocean: Ocean, compound_state: np.ndarray, acc_mode: int = ORC_F64_ACC):
+    """Compound::ComputeHydrodynamicForces through the oracle (orc_compound)."""
+    L = lib()
+    if not hasattr(L, "_compound_ready"):
+        L.orc_compound.restype = None
+        L.orc_compound.argtypes = [C.POINTER(C.POINTER(orc_mesh)), C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(_abi.sfh_ocean),
+                                   C.POINTER(_abi.sfh_waves), C.c_void_p, C.c_int, C.c_void_p]
+        L._compound_ready = True
+    ms = [mesh_struct(meshes[int(i)]) for i in part_mesh_idx]
+    arr = (C.POINTER(orc_mesh) * len(ms))(*[C.pointer(m) for m in ms])
+    o = ocean.to_struct()
+    w = ocean.waves_struct() if ocean.hasWaves() else _abi.sfh_waves()
+    ext = np.ascontiguousarray(np.asarray(external, dtype=np.uint32))
+    parts = np.ascontiguousarray(parts)
+    cs = np.ascontiguousarray(np.atleast_1d(compound_state))
+    out = np.zeros(1, dtype=INFO_DTYPE)
+    L.orc_compound(arr, parts.ctypes.data, ext.ctypes.data, len(ms), C.byref(o), C.byref(w), cs.ctypes.data, acc_mode, out.ctypes.data)
+    return out[0]

@@ -65,6 +65,7 @@ struct HydrodynamicsInfo {
     Scalar Swet = 0, Vsub = 0;
     BodyFluidPosition position = BodyFluidPosition::OUTSIDE;
     uint32_t faces = 0, classCount[8] = {0, 0, 0, 0, 0, 0, 0, 0}, degenerate = 0, quadratic = 0, skin = 0;
+    bool buoyancyAssigned = false, dampingAssigned = false; // did the last step assign Fb/Tb/Vsub resp. Fdq..Tdf (Appendix B.1)
     //! SolidEntity::ApplyHydrodynamicForces (SolidEntity.cpp:1958-1962): what goes to ApplyCentralForce / ApplyTorque
     Vector3 Force() const { return Fb + Fdq + Fdf; }
     Vector3 Torque() const { return Tb + Tdq + Tdf; }
@@ -295,6 +296,8 @@ private:
         if (r.wrote_buoyancy && r.position != SFH_POS_INSIDE) o.Vsub = r.Vsub;
         if (r.wrote_damping) { o.Fdq = Get(r.Fdq); o.Tdq = Get(r.Tdq); o.Fdf = Get(r.Fdf); o.Tdf = Get(r.Tdf); }
         o.Swet = r.Swet;
+        o.buoyancyAssigned = r.wrote_buoyancy != 0;
+        o.dampingAssigned = r.wrote_damping != 0;
         o.position = (BodyFluidPosition)r.position;
         o.faces = r.n_faces; o.degenerate = r.n_degenerate; o.quadratic = r.n_quadratic; o.skin = r.n_skin;
         for (int k = 0; k < 8; ++k) o.classCount[k] = r.class_count[k];
@@ -305,5 +308,70 @@ private:
     std::vector<sfh_body_state> states;
     std::vector<sfh_info> infos;
 };
+
+// ------------------------------------------------------------------------------------------------ compounds
+//! One part of a sf::Compound as submitted to HydroEngine: `body` carries the part's mesh, T_C = T_O * origin_i * O2C_i,
+//! T_O = T_O * origin_i, fdCd/fdCf and isBuoyant(), plus the COMPOUND's T_CG, v, omega and AABB (so that every part
+//! resolves to the compound's BodyFluidPosition). Internal parts are submitted with dampingForces = false.
+struct CompoundPart {
+    SolidBody* body;
+    bool isExternal;
+};
+
+//! Host half of Compound::ComputeHydrodynamicForces (Compound.cpp:315-435): combines the parts' results in part order,
+//! with the temporaries that persist across parts (a part whose buoyancy is not assigned re-adds the previous part's
+//! Fbp/Tbp/Vsubp, as the reference does) and the compound-level analytic buoyancy when INSIDE. `out` keeps the members
+//! the reference would leave untouched.
+inline void SumCompoundParts(const std::vector<CompoundPart>& parts, const HydrodynamicsSettings& settings, bool compoundBuoyant,
+                             Scalar volume, Scalar surface, const Vector3& P_CB, const Transform& T_CG, const Ocean& ocn,
+                             HydrodynamicsInfo& out)
+{
+    if (parts.empty()) return;
+    const BodyFluidPosition pos = parts.front().body->info.position;
+    out.position = pos;
+    auto add = [](Vector3& a, const Vector3& b) { a.x += b.x; a.y += b.y; a.z += b.z; };
+    if (pos == BodyFluidPosition::OUTSIDE) { // :302-313
+        out.Fb = out.Tb = out.Fdq = out.Tdq = out.Fdf = out.Tdf = Vector3();
+        out.Swet = out.Vsub = 0;
+        return;
+    }
+    if (pos == BodyFluidPosition::INSIDE) { // :315-363
+        if (compoundBuoyant) {
+            const Scalar s = -volume * ocn.getLiquidDensity();
+            const Vector3 Fb(Scalar(0) * s, Scalar(0) * s, ocn.getGravity() * s);
+            const Scalar* T = T_CG.m;
+            const Vector3 d(T[0] * P_CB.x + T[1] * P_CB.y + T[2] * P_CB.z + T[9] - T[9], T[3] * P_CB.x + T[4] * P_CB.y + T[5] * P_CB.z + T[10] - T[10],
+                            T[6] * P_CB.x + T[7] * P_CB.y + T[8] * P_CB.z + T[11] - T[11]);
+            out.Fb = Fb;
+            out.Tb = Vector3(d.y * Fb.z - d.z * Fb.y, d.z * Fb.x - d.x * Fb.z, d.x * Fb.y - d.y * Fb.x);
+        }
+        if (settings.dampingForces) {
+            out.Fdq = out.Tdq = out.Fdf = out.Tdf = Vector3();
+            for (const CompoundPart& p : parts)
+                if (p.isExternal) { add(out.Fdq, p.body->info.Fdq); add(out.Tdq, p.body->info.Tdq); add(out.Fdf, p.body->info.Fdf); add(out.Tdf, p.body->info.Tdf); }
+        }
+        out.Swet = surface;
+        out.Vsub = volume;
+        return;
+    }
+    if (!(settings.reallisticBuoyancy || settings.dampingForces)) return; // :366
+    if (settings.reallisticBuoyancy) out.Fb = out.Tb = Vector3();
+    if (settings.dampingForces) out.Fdq = out.Tdq = out.Fdf = out.Tdf = Vector3();
+    out.Swet = out.Vsub = 0;
+    Vector3 Fbp, Tbp;
+    Scalar Vsubp = 0;
+    for (const CompoundPart& p : parts) {
+        const HydrodynamicsInfo& r = p.body->info;
+        const bool pRb = settings.reallisticBuoyancy && p.body->buoyant;
+        if (!p.isExternal && !pRb) continue;
+        if (r.buoyancyAssigned) { Fbp = r.Fb; Tbp = r.Tb; Vsubp = r.Vsub; }
+        add(out.Fb, Fbp); add(out.Tb, Tbp);
+        out.Vsub += Vsubp;
+        if (p.isExternal) {
+            add(out.Fdq, r.Fdq); add(out.Tdq, r.Tdq); add(out.Fdf, r.Fdf); add(out.Tdf, r.Tdf);
+            out.Swet += r.Swet;
+        }
+    }
+}
 
 } // namespace sfb

@@ -381,3 +381,81 @@ class HydroContext:
         t = _abi.sfh_timings()
         self._check(self.lib.sfh_get_timings(self.ctx, C.byref(t)), "sfh_get_timings")
         return t
+
+
+# ------------------------------------------------------------------------------------------------ compounds
+def compound_part_states(compound: np.ndarray, parts: np.ndarray, external) -> np.ndarray:
+    """Body states to submit for the parts of ONE compound (Compound.cpp:291-437): every part is evaluated with the
+    compound's T_CG, velocities and AABB (so all parts resolve to the compound's BodyFluidPosition), its own T_C /
+    T_O_basis / Cd / Cf / mesh, the full dispatcher (SFH_F_DISPATCH: reallisticBuoyancy &= part.isBuoyant(), per-part
+    CorrectHydrodynamicForces), and no damping for internal parts."""
+    st = parts.copy()
+    c = compound
+    for k in ("T_CG", "v", "omega", "aabb_min", "aabb_max"):
+        st[k] = c[k]
+    st["mode"] = c["mode"]
+    base = int(c["flags"]) & (SFH_F_DAMPING | SFH_F_BUOYANCY)
+    for i in range(len(st)):
+        f = base | SFH_F_DISPATCH | (int(parts["flags"][i]) & SFH_F_BUOYANT)
+        if not external[i]:
+            f &= ~SFH_F_DAMPING
+        st["flags"][i] = f
+    return st
+
+
+def sum_compound(part_infos: np.ndarray, parts: np.ndarray, external, compound: np.ndarray, ocean: Ocean) -> np.ndarray:
+    """Host half of Compound::ComputeHydrodynamicForces: combine the per-part results of `compound_part_states` in part
+    order exactly like Compound.cpp:315-435, including the temporaries that persist across parts (Fbp, Tbp, Vsubp keep
+    the previous part's value when a part's buoyancy is not assigned) and the compound-level analytic buoyancy when INSIDE."""
+    out = np.zeros((), dtype=INFO_DTYPE)
+    pos = int(part_infos["position"][0]) if len(part_infos) else SFH_POS_OUTSIDE
+    out["position"] = pos
+    flags = int(compound["flags"])
+    damping, rb = bool(flags & SFH_F_DAMPING), bool(flags & SFH_F_BUOYANCY)
+    def count(r):  # validation counters of the parts the reference actually evaluates
+        for k in ("class_count", "n_degenerate", "n_quadratic", "n_skin", "n_faces"):
+            out[k] = out[k] + r[k]
+
+    if pos == SFH_POS_OUTSIDE:
+        out["wrote_buoyancy"] = out["wrote_damping"] = 1
+        return out
+    if pos == SFH_POS_INSIDE:
+        if flags & SFH_F_BUOYANT:  # Compound.cpp:318-322, fp64 Bullet expressions
+            s = -float(compound["volume"]) * ocean.density
+            Fb = np.array([0.0 * s, 0.0 * s, ocean.gravity * s])
+            T = compound["T_CG"]
+            pcb, org = compound["P_CB"], T[9:12]
+            wcb = np.array([T[3 * r] * pcb[0] + T[3 * r + 1] * pcb[1] + T[3 * r + 2] * pcb[2] + org[r] for r in range(3)])
+            d = wcb - org
+            out["Fb"] = Fb
+            out["Tb"] = [d[1] * Fb[2] - d[2] * Fb[1], d[2] * Fb[0] - d[0] * Fb[2], d[0] * Fb[1] - d[1] * Fb[0]]
+            out["wrote_buoyancy"] = 1
+        if damping:
+            out["wrote_damping"] = 1
+            for i in range(len(part_infos)):
+                if external[i]:
+                    for k in ("Fdq", "Tdq", "Fdf", "Tdf"):
+                        out[k] = out[k] + part_infos[k][i]
+                    count(part_infos[i])
+        out["Swet"], out["Vsub"] = compound["surface"], compound["volume"]
+        return out
+    if not (rb or damping):
+        return out
+    out["wrote_buoyancy"], out["wrote_damping"] = int(rb), int(damping)
+    Fbp, Tbp, Vsubp = np.zeros(3), np.zeros(3), 0.0
+    for i in range(len(part_infos)):
+        r = part_infos[i]
+        p_rb = rb and bool(int(parts["flags"][i]) & SFH_F_BUOYANT)
+        if not external[i] and not p_rb:
+            continue
+        count(r)
+        if r["wrote_buoyancy"]:
+            Fbp, Tbp, Vsubp = r["Fb"].copy(), r["Tb"].copy(), float(r["Vsub"])
+        out["Fb"] = out["Fb"] + Fbp
+        out["Tb"] = out["Tb"] + Tbp
+        out["Vsub"] = out["Vsub"] + Vsubp
+        if external[i]:
+            for k in ("Fdq", "Tdq", "Fdf", "Tdf"):
+                out[k] = out[k] + r[k]
+            out["Swet"] = out["Swet"] + r["Swet"]
+    return out

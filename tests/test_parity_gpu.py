@@ -214,3 +214,56 @@ def test_graph_replay_of_small_steps_tracks_inputs(ctx, oracle):
     err, where = max_rel_err(got, ref)
     assert err <= REL_TOL, (err, where)
     assert got.tobytes() != first.tobytes()
+
+
+@pytest.mark.parametrize("depth,waves", [(0.05, False), (0.1, True), (4.0, False), (-6.0, False)])
+def test_compound_parts_sum_like_the_reference(ctx, oracle, depth, waves):
+    """Row a10, Compound::ComputeHydrodynamicForces (Compound.cpp:291-437): parts go through the C ABI as bodies sharing
+    the compound's T_CG / velocities / AABB, the host sums them in part order (hydro.sum_compound) — against the oracle's
+    restatement of the whole method, for crossing (flat and waves), inside and outside compounds, with an internal part,
+    a non-buoyant part and one whose buoyancy is not assigned (stale temporaries re-added)."""
+    from stonefish_b200 import meshes as M
+    from stonefish_b200.hydro import compound_part_states, make_transform, new_body_states, quat_to_basis, sum_compound, transform_mul
+    from stonefish_b200._abi import SFH_F_BUOYANCY, SFH_F_BUOYANT, SFH_F_DAMPING, SFH_POS_AUTO
+
+    meshes_ = [M.icosphere(0.5, 2), M.box(1.0, 0.5, 0.2, 2), M.uv_ellipsoid(0.9, 0.18, 0.18, 24, 13)]
+    ocean = scenes.Ocean(1000.0, 9.81)
+    if waves:
+        ocean.setWaves(scenes.wave_field())
+    ocean.AddVelocityField(scenes.Uniform((0.3, -0.2, 0.05)))
+    ocean.EnableCurrents()
+    T_CG = make_transform(quat_to_basis(scenes.euler_zyx_quat(0.4, 0.1, -0.2)), (1.0, -2.0, depth))
+    T_O = transform_mul(T_CG, make_transform(None, (0.05, 0.0, -0.02)))
+    # (mesh, origin in the compound frame, external, buoyant)
+    layout = [(0, (0.0, 0.0, 0.0), 1, 1), (1, (1.2, 0.0, 0.0), 1, 1), (2, (0.0, 0.9, -1.5), 1, 1), (1, (-1.0, 0.0, 0.1), 1, 0),
+              (0, (0.3, 0.3, 0.2), 0, 1), (1, (0.0, -0.8, 0.0), 0, 0)]
+    parts = new_body_states(len(layout))
+    external, part_mesh = [], []
+    lo, hi = np.full(3, 1e30), np.full(3, -1e30)
+    for i, (mi, org, ext, buoy) in enumerate(layout):
+        T_O_part = transform_mul(T_O, make_transform(quat_to_basis(scenes.euler_zyx_quat(0.1 * i, 0, 0)), org))
+        parts["T_C"][i] = transform_mul(T_O_part, make_transform(None, (0.01, 0.0, 0.0)))
+        parts["T_O_basis"][i] = T_O_part[:9]
+        parts["Cd"][i], parts["Cf"][i] = (1.0 + 0.1 * i, 0.9, 1.1), (0.05, 0.06 + 0.01 * i, 0.07)
+        parts["flags"][i] = SFH_F_BUOYANT if buoy else 0
+        a, b = scenes.world_aabb(meshes_[mi], parts["T_C"][i])
+        lo, hi = np.minimum(lo, a), np.maximum(hi, b)
+        external.append(ext)
+        part_mesh.append(mi)
+    comp = new_body_states(1)[0]
+    comp["T_CG"], comp["v"], comp["omega"] = T_CG, (0.5, 0.1, -0.2), (0.05, 0.02, 0.1)
+    comp["mode"], comp["flags"] = SFH_POS_AUTO, SFH_F_DAMPING | SFH_F_BUOYANCY | SFH_F_BUOYANT
+    comp["aabb_min"], comp["aabb_max"] = lo, hi
+    comp["volume"], comp["surface"], comp["P_CB"] = 1.234, 5.678, (0.02, 0.0, -0.03)
+
+    st = compound_part_states(comp, parts, external)
+    ids = [ctx.upload_mesh(m) for m in meshes_]
+    st["mesh_id"] = [ids[mi] for mi in part_mesh]
+    got = sum_compound(ctx.compute(ocean, st), parts, external, comp, ocean)
+    ref = oracle.compound(meshes_, part_mesh, parts, external, ocean, comp)
+    for k in ("position", "wrote_buoyancy", "wrote_damping", "class_count", "n_degenerate", "n_quadratic", "n_skin", "n_faces"):
+        assert np.array_equal(got[k], ref[k]), (k, got[k], ref[k])
+    err, where = max_rel_err(np.atleast_1d(got), np.atleast_1d(ref))
+    assert err <= REL_TOL, (err, where)
+    expected = {0.05: 2, 0.1: 2, 4.0: 1, -6.0: 0}[depth]
+    assert int(got["position"]) == expected
