@@ -267,3 +267,40 @@ def test_compound_parts_sum_like_the_reference(ctx, oracle, depth, waves):
     assert err <= REL_TOL, (err, where)
     expected = {0.05: 2, 0.1: 2, 4.0: 1, -6.0: 0}[depth]
     assert int(got["position"]) == expected
+
+
+def test_ragged_and_chunk_boundary_meshes(ctx, oracle):
+    """Mesh sizes around the 256-face / 256-vertex chunk limits, triangle soup (vertex-limited chunks), a single face,
+    all in one step next to each other, crossing a wavy surface with Jet+Pipe currents."""
+    from stonefish_b200 import meshes as M
+    from stonefish_b200.hydro import Mesh, make_transform, new_body_states, quat_to_basis
+
+    base = M.uv_ellipsoid(1.0, 0.4, 0.3, 40, 21)  # 1600 faces
+    meshes_ = []
+    for nf in (1, 2, 85, 86, 255, 256, 257, 511, 512, 513, 1600):
+        meshes_.append(Mesh(base.positions.copy(), base.faces[:nf].copy()))
+    r = M.splitmix_uniform(99, 300 * 9).reshape(-1, 3).astype(np.float32) - 0.5   # soup: 300 faces, 900 private vertices
+    meshes_.append(Mesh(r, np.arange(900, dtype=np.uint32).reshape(-1, 3)))
+    ocean = scenes.Ocean(1000.0, 9.81)
+    ocean.setWaves(scenes.wave_field())
+    ocean.AddVelocityField(scenes.Jet((0.0, -3.0, 1.0), (0.1, 1.0, 0.05), 0.3, 5.0))
+    ocean.AddVelocityField(scenes.Pipe((-6.0, 0.5, 1.5), (6.0, -0.5, 2.0), 2.0, 3.0, 2.0, 2.0))
+    ocean.EnableCurrents()
+    n = 2 * len(meshes_)
+    st = new_body_states(n)
+    body_mesh = np.arange(n) % len(meshes_)
+    q = scenes.random_unit_quats(5, n)
+    for k in range(n):
+        T = make_transform(quat_to_basis(q[k]), (0.3 * k - 3.0, 0.2 * k - 2.0, 0.05 if k < len(meshes_) else 2.5))
+        st["T_CG"][k], st["T_C"][k] = T, T
+        st["mode"][k] = 2 if k < len(meshes_) else 1
+        st["flags"][k] = 3
+        st["v"][k], st["omega"][k] = (0.5, -0.2, 0.1), (0.1, 0.05, -0.2)
+    sc = scenes.Scene("ragged", meshes_, body_mesh, ocean, st)
+    gi, gc, ri, rc = run_both(ctx, oracle, sc)
+    for k in ("class_count", "n_degenerate", "n_faces", "position", "wrote_buoyancy", "wrote_damping"):
+        assert np.array_equal(gi[k], ri[k]), k
+    assert np.array_equal(gc & 15, rc & 15) and (gc != rc).sum() <= 1
+    err, where = max_rel_err(gi, ri)
+    assert err <= REL_TOL, (err, where)
+    assert gi["n_faces"].tolist() == [meshes_[i].n_faces for i in body_mesh]
