@@ -107,6 +107,22 @@ int sfh_step_debug(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* s
 int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies,
                     sfh_info* d_out);
 
+/* Aerodynamic twin: one recompute of the air drag of n_bodies bodies — replaces the
+ * `for each atmosphere-ghost pair: atmosphere->ApplyFluidForces(...)` recompute, i.e.
+ * SolidEntity::ComputeAerodynamicForces (SolidEntity.cpp:1852-1923, Atmosphere.cpp:160-193), up to, not including,
+ * ApplyAerodynamicForces. Same buffers and rules as sfh_step. Of each sfh_body_state it reads mesh_id, T_CG, T_C, v,
+ * omega (mode is ignored: every face is evaluated) and, with SFH_F_DISPATCH, CorrectAerodynamicForces' inputs:
+ * T_O_basis = T_CG2H.getBasis(), Cd = the proxy's coefficient vector ((0.5,0.5,1) for a cylinder, (1/a,1/b,1/c)/max for
+ * an ellipsoid) and SFH_F_AERO_CD. Results: Fda -> out.Fdq, Tda -> out.Tdq, wrote_damping = 1, n_quadratic = faces that
+ * took the drag branch; everything else is zero. Without SFH_F_DISPATCH the result is the static integrator's
+ * (0.5 * density * sum, uncorrected). */
+int sfh_aero_step(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_state* states, uint32_t n_bodies, sfh_info* out);
+int sfh_aero_step_debug(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_state* states, uint32_t n_bodies,
+                        sfh_info* out, uint8_t* face_codes, size_t face_codes_bytes);
+/* Device-resident variant (see sfh_step_device). */
+int sfh_aero_step_device(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_state* d_states, uint32_t n_bodies,
+                         sfh_info* d_out);
+
 /* Batched point queries with the same arithmetic as the per-face kernels (host buffers, synchronous):
  *   sfh_query_depth          = Ocean::GetDepth(const glm::vec3&)          (Ocean.cpp:149-168), n points -> n floats
  *   sfh_query_fluid_velocity = Ocean::GetFluidVelocity(const glm::vec3&)  (Ocean.cpp:198-201), n points -> 3n floats

@@ -43,11 +43,14 @@ enum {
     SFH_F_DAMPING   = 1u << 0, /* HydrodynamicsSettings::dampingForces     (Ocean.h:36-40) */
     SFH_F_BUOYANCY  = 1u << 1, /* HydrodynamicsSettings::reallisticBuoyancy                */
     SFH_F_BUOYANT   = 1u << 2, /* SolidEntity::isBuoyant()                                 */
-    SFH_F_DISPATCH  = 1u << 3  /* 0: raw static integrator selected by `mode`
+    SFH_F_DISPATCH  = 1u << 3, /* 0: raw static integrator selected by `mode`
                                      (INSIDE -> ...Submerged, CROSSING -> ...Surface), outputs uncorrected.
                                   1: whole SolidEntity::ComputeHydrodynamicForces (SolidEntity.cpp:1799-1850):
                                      analytic INSIDE buoyancy, Swet=surface, reallisticBuoyancy&=isBuoyant,
                                      CorrectHydrodynamicForces with Cd/Cf/T_O. */
+    /* --- read only by sfh_aero_step ------------------------------------------------------------------- */
+    SFH_F_AERO_CD   = 1u << 4  /* CorrectAerodynamicForces (SolidEntity.cpp:1925-1956) scales by |Cd . Fdan|
+                                  (GeometryApproxType CYLINDER / ELLIPSOID); clear: factor 1 (AUTO / SPHERE) */
 };
 
 typedef struct sfh_current {
@@ -71,6 +74,16 @@ typedef struct sfh_ocean {
     uint32_t reserved;
     sfh_current currents[SFH_MAX_CURRENTS];
 } sfh_ocean;
+
+/* What the aerodynamic integrator reads from sf::Atmosphere: getGas().density and the wind list, which
+ * Atmosphere::GetFluidVelocity sums WITHOUT looking at VelocityField::isEnabled() (Atmosphere.cpp:146-157):
+ * winds[i].enabled is ignored. */
+typedef struct sfh_atmosphere {
+    double density;
+    uint32_t n_winds; /* <= SFH_MAX_CURRENTS */
+    uint32_t reserved;
+    sfh_current winds[SFH_MAX_CURRENTS];
+} sfh_atmosphere;
 
 typedef struct sfh_waves {
     int32_t fft_size;     /* OceanParams::fftSize (256) */

@@ -139,6 +139,43 @@ void btc_correct(double density, double Fdq_[3], double Tdq_[3], double Fdf_[3],
     for (int k = 0; k < 3; ++k) { Fdq_[k] = _Fdq[k]; Tdq_[k] = _Tdq[k]; Fdf_[k] = _Fdf[k]; Tdf_[k] = _Tdf[k]; }
 }
 
+/* SolidEntity.cpp:1925-1956. approx_type: 0 AUTO, 1 SPHERE, 2 CYLINDER, 3 ELLIPSOID (SolidEntity.h:39) */
+void btc_correct_aero(double Fda_[3], double Tda_[3], int approx_type, const double params[3], const double B[9])
+{
+    Transform T_CG2H(Matrix3(B[0], B[1], B[2], B[3], B[4], B[5], B[6], B[7], B[8]), Vector3(0, 0, 0));
+    Vector3 _Fda(Fda_[0], Fda_[1], Fda_[2]), _Tda(Tda_[0], Tda_[1], Tda_[2]);
+    const double* fdApproxParams = params;
+
+    Vector3 Fdan = (T_CG2H.getBasis().inverse() * _Fda).safeNormalize();
+    Scalar corFactor(1.0);
+    switch (approx_type) {
+    case 0:
+    case 1:
+        break;
+    case 2: {
+        Vector3 Cd(0.5, 0.5, 1.0);
+        corFactor = Cd.dot(Fdan);
+    } break;
+    case 3: {
+        Vector3 Cd(Scalar(1) / fdApproxParams[0], Scalar(1) / fdApproxParams[1], Scalar(1) / fdApproxParams[2]);
+        Scalar maxCd = btMax(btMax(Cd.x(), Cd.y()), Cd.z());
+        Cd /= maxCd;
+        corFactor = Cd.dot(Fdan);
+    } break;
+    }
+    _Fda *= btFabs(corFactor);
+    _Tda *= btFabs(corFactor);
+    for (int k = 0; k < 3; ++k) { Fda_[k] = _Fda[k]; Tda_[k] = _Tda[k]; }
+}
+/* the ELLIPSOID coefficient vector alone (SolidEntity.cpp:1945-1947), for the host mirrors */
+void btc_ellipsoid_cd(const double params[3], double cd_out[3])
+{
+    Vector3 Cd(Scalar(1) / params[0], Scalar(1) / params[1], Scalar(1) / params[2]);
+    Scalar maxCd = btMax(btMax(Cd.x(), Cd.y()), Cd.z());
+    Cd /= maxCd;
+    for (int k = 0; k < 3; ++k) cd_out[k] = Cd[k];
+}
+
 /* OpenGLDataStructs.cpp:148-156: getOpenGLMatrix then (GLfloat) per element */
 void btc_gl_matrix(const double T[12], float out[16])
 {

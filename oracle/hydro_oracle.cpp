@@ -289,6 +289,43 @@ void orc_gl_matrix(const double T[12], float out[16])
     std::memcpy(out, M.m, sizeof(M.m));
 }
 
+/* Atmosphere::GetFluidVelocity, glm overload (Atmosphere.cpp:154-157) over the Vector3 one (:146-152) */
+void orc_wind_velocity_f(const sfh_atmosphere* atm, const float p[3], float out[3])
+{
+    const double pd[3] = {(double)p[0], (double)p[1], (double)p[2]};
+    D3 fv{0, 0, 0};
+    for (uint32_t i = 0; i < atm->n_winds; ++i) {
+        double v[3];
+        orc_current_velocity(&atm->winds[i], pd, v);
+        fv = fv + D3{v[0], v[1], v[2]};
+    }
+    out[0] = (float)fv.x; out[1] = (float)fv.y; out[2] = (float)fv.z;
+}
+
+/* SolidEntity::CorrectAerodynamicForces (SolidEntity.cpp:1925-1956) */
+void orc_correct_aero(double Fda[3], double Tda[3], const double Cd[3], const double B[9], int use_cd)
+{
+    auto el = [&](int r, int c) { return B[3 * r + c]; };
+    auto cofac = [&](int r1, int c1, int r2, int c2) { return el(r1, c1) * el(r2, c2) - el(r1, c2) * el(r2, c1); };
+    D3 co{cofac(1, 1, 2, 2), cofac(1, 2, 2, 0), cofac(1, 0, 2, 1)};
+    double det = ddot(D3{el(0, 0), el(0, 1), el(0, 2)}, co);
+    double s = 1.0 / det;
+    D3 r0{co.x * s, cofac(0, 2, 2, 1) * s, cofac(0, 1, 1, 2) * s};
+    D3 r1{co.y * s, cofac(0, 0, 2, 2) * s, cofac(0, 2, 1, 0) * s};
+    D3 r2{co.z * s, cofac(0, 1, 2, 0) * s, cofac(0, 0, 1, 1) * s};
+    D3 v{Fda[0], Fda[1], Fda[2]};
+    D3 Fdan{ddot(r0, v), ddot(r1, v), ddot(r2, v)};
+    double l2 = ddot(Fdan, Fdan);
+    if (l2 >= 2.2204460492503131e-16 * 2.2204460492503131e-16)
+        Fdan = Fdan * (1.0 / std::sqrt(l2));
+    else
+        Fdan = D3{1, 0, 0};
+    double corFactor = 1.0;
+    if (use_cd) corFactor = ddot(D3{Cd[0], Cd[1], Cd[2]}, Fdan);
+    const double k = std::fabs(corFactor);
+    for (int c = 0; c < 3; ++c) { Fda[c] *= k; Tda[c] *= k; }
+}
+
 } // extern "C"
 
 namespace {
@@ -594,6 +631,63 @@ void finalize_surface(Acc<T>& a, const sfh_ocean* o, const sfh_body_state* st, c
     copy_counters(a, out);
 }
 
+/* Face loop of the static ComputeAerodynamicForces (SolidEntity.cpp:1886-1919) over faces [f0,f1); Fda/Tda live in a.Fdq/a.Tdq */
+template <typename T>
+void aero_faces(Acc<T>& a, const orc_mesh* mesh, const sfh_atmosphere* atm, const Prologue& P, size_t f0, size_t f1, uint8_t* codes)
+{
+    for (size_t i = f0; i < f1; ++i) {
+        V3 p1 = xform(P.TC, vertex_pos(mesh, i, 0));
+        V3 p2 = xform(P.TC, vertex_pos(mesh, i, 1));
+        V3 p3 = xform(P.TC, vertex_pos(mesh, i, 2));
+        ++a.n_faces;
+        ++a.cls[7];
+        V3 fv1 = p2 - p1;
+        V3 fv2 = p3 - p1;
+        V3 fn = cross(fv1, fv2);
+        float len = length2(fn);
+        if (len < 1e-12f) {
+            ++a.n_degenerate;
+            if (codes) codes[i] = 7 | SFH_FACE_DEGENERATE;
+            continue;
+        }
+        len = std::sqrt(len);
+        V3 fn1 = fn / len;
+        float A = len / 2.f;
+        V3 fc = (p1 + p2 + p3) / 3.f;
+        float pf[3] = {fc.x, fc.y, fc.z}, wf[3];
+        orc_wind_velocity_f(atm, pf, wf);
+        V3 vc = V3{wf[0], wf[1], wf[2]} - (P.v + cross(P.omega, fc - P.p));
+        V3 vn = dot(vc, fn1) * fn1;
+        uint8_t code = 7;
+        if (dot(fn1, vn) < -1e-12f) {
+            /* `vn * vn.length() * A`: glm::vec3::length() is the component count (int 3); vec3 * int resolves to
+             * glm/gtx/scalar_multiplication.hpp (pulled in by glm/ext.hpp with GLM_ENABLE_EXPERIMENTAL,
+             * OpenGLDataStructs.h:30-32): lh *= static_cast<float>(3) */
+            V3 quadratic = vn * 3.f * A;
+            a.add3(a.Fdq, quadratic);
+            a.add3(a.Tdq, cross(fc - P.p, quadratic));
+            ++a.n_quadratic;
+            code |= SFH_FACE_QUADRATIC;
+        }
+        if (codes) codes[i] = code;
+    }
+}
+
+template <typename T>
+void run_aero(const orc_mesh* mesh, const sfh_atmosphere* atm, const sfh_body_state* st, sfh_info* out, uint8_t* codes)
+{
+    Prologue P = make_prologue(st);
+    Acc<T> a;
+    aero_faces(a, mesh, atm, P, 0, mesh->n_faces, codes);
+    /* SolidEntity.cpp:1921-1923: Scalar(0.5) * density * Vector3(Fda) */
+    const double k = 0.5 * atm->density;
+    for (int c = 0; c < 3; ++c) {
+        out->Fdq[c] = (double)a.Fdq[c] * k;
+        out->Tdq[c] = (double)a.Tdq[c] * k;
+    }
+    copy_counters(a, out);
+}
+
 template <typename T>
 void run_submerged(const orc_mesh* mesh, const sfh_ocean* o, const sfh_body_state* st, sfh_info* out, uint8_t* codes)
 {
@@ -647,6 +741,42 @@ void orc_surface(const orc_mesh* mesh, const sfh_ocean* o, const sfh_waves* w, c
         run_surface<float>(mesh, o, w, st, rb, df, out, codes);
     else
         run_surface<double>(mesh, o, w, st, rb, df, out, codes);
+}
+
+void orc_aero(const orc_mesh* mesh, const sfh_atmosphere* atm, const sfh_body_state* st, int acc_mode, sfh_info* out, uint8_t* codes)
+{
+    zero_info(out);
+    out->position = SFH_POS_OUTSIDE;
+    out->wrote_damping = 1;
+    if (mesh != nullptr) { /* :1868-1873: no mesh -> zero */
+        if (acc_mode == ORC_REF_F32_SEQ)
+            run_aero<float>(mesh, atm, st, out, codes);
+        else
+            run_aero<double>(mesh, atm, st, out, codes);
+    }
+    if (st->flags & SFH_F_DISPATCH) /* :1862 */
+        orc_correct_aero(out->Fdq, out->Tdq, st->Cd, st->T_O_basis, (st->flags & SFH_F_AERO_CD) != 0);
+}
+
+void orc_compound_aero(const orc_mesh* const* part_meshes, const sfh_body_state* parts, const uint32_t* external, uint32_t n_parts,
+                       const sfh_atmosphere* atm, const sfh_body_state* compound, int acc_mode, sfh_info* out)
+{
+    zero_info(out);
+    out->position = SFH_POS_OUTSIDE;
+    out->wrote_damping = 1; /* Compound.cpp:444-445 */
+    for (uint32_t i = 0; i < n_parts; ++i) {
+        if (!external[i]) continue; /* :456 */
+        sfh_body_state st = parts[i];
+        std::memcpy(st.T_CG, compound->T_CG, sizeof(st.T_CG));
+        std::memcpy(st.v, compound->v, sizeof(st.v));
+        std::memcpy(st.omega, compound->omega, sizeof(st.omega));
+        st.flags |= SFH_F_DISPATCH; /* :459-460: static integrator, then the part's CorrectAerodynamicForces */
+        sfh_info pi;
+        orc_aero(part_meshes[i], atm, &st, acc_mode, &pi, nullptr);
+        for (int c = 0; c < 3; ++c) { out->Fdq[c] += pi.Fdq[c]; out->Tdq[c] += pi.Tdq[c]; }
+        out->n_faces += pi.n_faces; out->n_degenerate += pi.n_degenerate; out->n_quadratic += pi.n_quadratic;
+        out->class_count[7] += pi.class_count[7];
+    }
 }
 
 /* The sfh_step contract for one body. With SFH_F_DISPATCH: SolidEntity::ComputeHydrodynamicForces

@@ -80,6 +80,23 @@ void orc_body(const orc_mesh* mesh, const sfh_ocean* o, const sfh_waves* w, cons
 void orc_compound(const orc_mesh* const* part_meshes, const sfh_body_state* parts, const uint32_t* external, uint32_t n_parts,
                   const sfh_ocean* o, const sfh_waves* w, const sfh_body_state* compound, int acc_mode, sfh_info* out);
 
+/* N2, the aerodynamic twin.
+ * orc_wind_velocity_f: Atmosphere::GetFluidVelocity(glm::vec3) (Atmosphere.cpp:146-157) — every wind, no isEnabled() test.
+ * orc_correct_aero:    SolidEntity::CorrectAerodynamicForces (SolidEntity.cpp:1925-1956); B = T_CG2H.getBasis(), Cd = the
+ *                      proxy vector, use_cd = CYLINDER/ELLIPSOID.
+ * orc_aero:            SolidEntity::ComputeAerodynamicForces, static (SolidEntity.cpp:1865-1923) and, with SFH_F_DISPATCH,
+ *                      the member (SolidEntity.cpp:1852-1863) = static + CorrectAerodynamicForces. Same contract as
+ *                      sfh_aero_step (include/sfh.h): Fda -> out->Fdq, Tda -> out->Tdq. */
+void orc_wind_velocity_f(const sfh_atmosphere* atm, const float p[3], float out[3]);
+void orc_correct_aero(double Fda[3], double Tda[3], const double Cd[3], const double B[9], int use_cd);
+void orc_aero(const orc_mesh* mesh, const sfh_atmosphere* atm, const sfh_body_state* st, int acc_mode, sfh_info* out,
+              uint8_t* face_codes);
+/* Compound::ComputeAerodynamicForces (Compound.cpp:439-464): external parts only, each corrected with its own proxy.
+ * parts[i]: T_C = T_O * origin_i * O2C_i, and (SFH_F_DISPATCH set) the part's T_O_basis = T_CG2H basis, Cd, SFH_F_AERO_CD;
+ * compound: T_CG, v, omega. */
+void orc_compound_aero(const orc_mesh* const* part_meshes, const sfh_body_state* parts, const uint32_t* external, uint32_t n_parts,
+                       const sfh_atmosphere* atm, const sfh_body_state* compound, int acc_mode, sfh_info* out);
+
 /* Whole step, scheduled like the reference: one task per body on a pool of n_threads
  * (SimulationManager.cpp:1641-1651, utils/ThreadPool.hpp). meshes[i] is the mesh of body i.
  * Returns wall seconds spent between the first enqueue and waitAll (the PerformanceMonitor bracket,

@@ -148,3 +148,54 @@ def compound(meshes, part_mesh_idx, parts: np.ndarray, external, ocean: Ocean, c
     out = np.zeros(1, dtype=INFO_DTYPE)
     L.orc_compound(arr, parts.ctypes.data, ext.ctypes.data, len(ms), C.byref(o), C.byref(w), cs.ctypes.data, acc_mode, out.ctypes.data)
     return out[0]
+
+
+def _aero_lib():
+    L = lib()
+    if not hasattr(L, "_aero_ready"):
+        P, D3 = C.POINTER, C.POINTER(C.c_double)
+        L.orc_wind_velocity_f.restype = None
+        L.orc_wind_velocity_f.argtypes = [P(_abi.sfh_atmosphere), P(C.c_float), P(C.c_float)]
+        L.orc_correct_aero.restype = None
+        L.orc_correct_aero.argtypes = [D3, D3, D3, D3, C.c_int]
+        L.orc_aero.restype = None
+        L.orc_aero.argtypes = [P(orc_mesh), P(_abi.sfh_atmosphere), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_compound_aero.restype = None
+        L.orc_compound_aero.argtypes = [P(P(orc_mesh)), C.c_void_p, C.c_void_p, C.c_uint32, P(_abi.sfh_atmosphere), C.c_void_p,
+                                        C.c_int, C.c_void_p]
+        L._aero_ready = True
+    return L
+
+
+def aero(meshes, body_mesh, atm, states: np.ndarray, acc_mode: int = ORC_F64_ACC, codes: bool = False):
+    """SolidEntity::ComputeAerodynamicForces for every body through the oracle (orc_aero); same contract as sfh_aero_step."""
+    L = _aero_lib()
+    a = atm.to_struct()
+    states = np.ascontiguousarray(states)
+    out = np.zeros(states.shape[0], dtype=INFO_DTYPE)
+    all_codes = []
+    for i in range(states.shape[0]):
+        m = meshes[int(body_mesh[i])]
+        ms = mesh_struct(m)
+        cbuf = np.zeros(max(m.n_faces, 1), dtype=np.uint8) if codes else None
+        L.orc_aero(C.byref(ms), C.byref(a), states[i:i + 1].ctypes.data, acc_mode, out[i:i + 1].ctypes.data,
+                   cbuf.ctypes.data if codes else None)
+        if codes:
+            all_codes.append(cbuf[: m.n_faces])
+    if codes:
+        return out, (np.concatenate(all_codes) if all_codes else np.zeros(0, np.uint8))
+    return out
+
+
+def compound_aero(meshes, part_mesh_idx, parts: np.ndarray, external, atm, compound_state: np.ndarray, acc_mode: int = ORC_F64_ACC):
+    """Compound::ComputeAerodynamicForces through the oracle (orc_compound_aero)."""
+    L = _aero_lib()
+    ms = [mesh_struct(meshes[int(i)]) for i in part_mesh_idx]
+    arr = (C.POINTER(orc_mesh) * len(ms))(*[C.pointer(m) for m in ms])
+    a = atm.to_struct()
+    ext = np.ascontiguousarray(np.asarray(external, dtype=np.uint32))
+    parts = np.ascontiguousarray(parts)
+    cs = np.ascontiguousarray(np.atleast_1d(compound_state))
+    out = np.zeros(1, dtype=INFO_DTYPE)
+    L.orc_compound_aero(arr, parts.ctypes.data, ext.ctypes.data, len(ms), C.byref(a), cs.ctypes.data, acc_mode, out.ctypes.data)
+    return out[0]

@@ -11,7 +11,7 @@ import os
 SFH_MAX_CURRENTS = 64
 SFH_CURRENT_UNIFORM, SFH_CURRENT_JET, SFH_CURRENT_PIPE = 0, 1, 2
 SFH_POS_OUTSIDE, SFH_POS_INSIDE, SFH_POS_CROSSING, SFH_POS_AUTO = 0, 1, 2, 3
-SFH_F_DAMPING, SFH_F_BUOYANCY, SFH_F_BUOYANT, SFH_F_DISPATCH = 1, 2, 4, 8
+SFH_F_DAMPING, SFH_F_BUOYANCY, SFH_F_BUOYANT, SFH_F_DISPATCH, SFH_F_AERO_CD = 1, 2, 4, 8, 16
 SFH_MESH_KEEP_ORDER = 1
 SFH_FACE_CLASS_MASK, SFH_FACE_DEGENERATE, SFH_FACE_QUADRATIC, SFH_FACE_SKIN = 7, 8, 16, 32
 SFH_OK = 0
@@ -26,6 +26,11 @@ class sfh_ocean(C.Structure):
     _fields_ = [("density", C.c_double), ("gravity_z", C.c_double), ("has_waves", C.c_uint32),
                 ("currents_enabled", C.c_uint32), ("n_currents", C.c_uint32), ("reserved", C.c_uint32),
                 ("currents", sfh_current * SFH_MAX_CURRENTS)]
+
+
+class sfh_atmosphere(C.Structure):
+    _fields_ = [("density", C.c_double), ("n_winds", C.c_uint32), ("reserved", C.c_uint32),
+                ("winds", sfh_current * SFH_MAX_CURRENTS)]
 
 
 class sfh_waves(C.Structure):
@@ -96,6 +101,9 @@ PROTOTYPES = {
     "sfh_step": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_step_debug": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sfh_step_device": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sfh_aero_step": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sfh_aero_step_debug": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sfh_aero_step_device": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_query_depth": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_query_fluid_velocity": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_selftest": (C.c_int, [_ctx, C.c_uint32, C.c_uint64, _P(C.c_uint64), _P(C.c_uint64)]),

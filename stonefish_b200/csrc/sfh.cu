@@ -85,6 +85,7 @@ struct sfh_ctx {
 
     // occupancy cache: blocks per SM for [kernel variant]
     int occ_sub[2] = {0, 0};
+    int occ_aero[2] = {0, 0};
     int occ_surf[2][2] = {{0, 0}, {0, 0}};
 
     // CUDA-graph replay of small steps (launch-latency bound): see step_host
@@ -251,13 +252,14 @@ int sync_mesh_table(sfh_ctx* ctx)
 struct StepPlan {
     bool host_states = true;     // states/out are host pointers
     bool debug = false;
+    bool aero = false;           // sfh_aero_step: the "ocean" is the atmosphere and every body runs the aero face loop
     bool may_sub = true, may_surf = true; // host knows no body can reach the kernel -> skip the launch
     uint64_t chunks_ub = 0;      // upper bound of work items (host variant), 0 = unknown
     uint64_t faces = 0;
 };
 
-template <int CUR, bool DEBUG>
-void launch_sub(const StepParams& P, int grid, cudaStream_t s) { k_submerged<CUR, DEBUG><<<grid, SFH_BLOCK, 0, s>>>(P); }
+template <int CUR, bool DEBUG, bool AERO = false>
+void launch_sub(const StepParams& P, int grid, cudaStream_t s) { k_submerged<CUR, DEBUG, AERO><<<grid, SFH_BLOCK, 0, s>>>(P); }
 template <bool WAVES, int CUR, bool DEBUG>
 void launch_surf(const StepParams& P, int grid, cudaStream_t s) { k_surface<WAVES, CUR, DEBUG><<<grid, SFH_BLOCK, 0, s>>>(P); }
 
@@ -270,8 +272,12 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     const bool waves = ocean->has_waves != 0;
 
     // persistent grids
-    if (general) { if ((rc = occupancy(ctx, k_submerged<1, false>, &ctx->occ_sub[1])) != SFH_OK) return rc; }
-    else         { if ((rc = occupancy(ctx, k_submerged<0, false>, &ctx->occ_sub[0])) != SFH_OK) return rc; }
+    if (plan.aero) {
+        if (general) rc = occupancy(ctx, k_submerged<1, false, true>, &ctx->occ_aero[1]); else rc = occupancy(ctx, k_submerged<0, false, true>, &ctx->occ_aero[0]);
+    } else {
+        if (general) rc = occupancy(ctx, k_submerged<1, false>, &ctx->occ_sub[1]); else rc = occupancy(ctx, k_submerged<0, false>, &ctx->occ_sub[0]);
+    }
+    if (rc != SFH_OK) return rc;
     int* occs = &ctx->occ_surf[waves ? 1 : 0][general ? 1 : 0];
     if (waves) {
         if (general) rc = occupancy(ctx, k_surface<true, 1, false>, occs); else rc = occupancy(ctx, k_surface<true, 0, false>, occs);
@@ -279,7 +285,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
         if (general) rc = occupancy(ctx, k_surface<false, 1, false>, occs); else rc = occupancy(ctx, k_surface<false, 0, false>, occs);
     }
     if (rc != SFH_OK) return rc;
-    uint64_t g_sub = (uint64_t)ctx->num_sms * (uint64_t)ctx->occ_sub[general ? 1 : 0];
+    uint64_t g_sub = (uint64_t)ctx->num_sms * (uint64_t)(plan.aero ? ctx->occ_aero : ctx->occ_sub)[general ? 1 : 0];
     uint64_t g_surf = (uint64_t)ctx->num_sms * (uint64_t)*occs;
     if (plan.chunks_ub) {
         if (g_sub > plan.chunks_ub) g_sub = plan.chunks_ub;
@@ -305,7 +311,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     PrologueParams pp;
     pp.states = d_states; pp.meshes = ctx->d_meshes.p; pp.n_meshes = (uint32_t)ctx->meshes.size(); pp.n_bodies = n;
     pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;
-    pp.off_sub = ctx->d_off_sub.p; pp.off_surf = ctx->d_off_surf.p; pp.status = ctx->d_status.p;
+    pp.off_sub = ctx->d_off_sub.p; pp.off_surf = ctx->d_off_surf.p; pp.status = ctx->d_status.p; pp.aero = plan.aero ? 1u : 0u;
     k_prologue<<<(n + 127) / 128, 128, 0, ctx->stream>>>(pp);
     k_scan_items<<<1, 1024, 0, ctx->stream>>>(ctx->d_off_sub.p, ctx->d_off_surf.p, n);
     uint32_t launches = 2;
@@ -318,8 +324,13 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     ctx->ev_sub = ctx->ev_surf = false;
     if (plan.may_sub && g_sub > 0) {
         sp.item_off = ctx->d_off_sub.p; sp.partials = ctx->d_part_sub.p;
-        if (plan.debug) { if (general) launch_sub<1, true>(sp, (int)g_sub, ctx->stream); else launch_sub<0, true>(sp, (int)g_sub, ctx->stream); }
-        else            { if (general) launch_sub<1, false>(sp, (int)g_sub, ctx->stream); else launch_sub<0, false>(sp, (int)g_sub, ctx->stream); }
+        if (plan.aero) {
+            if (plan.debug) { if (general) launch_sub<1, true, true>(sp, (int)g_sub, ctx->stream); else launch_sub<0, true, true>(sp, (int)g_sub, ctx->stream); }
+            else            { if (general) launch_sub<1, false, true>(sp, (int)g_sub, ctx->stream); else launch_sub<0, false, true>(sp, (int)g_sub, ctx->stream); }
+        } else {
+            if (plan.debug) { if (general) launch_sub<1, true>(sp, (int)g_sub, ctx->stream); else launch_sub<0, true>(sp, (int)g_sub, ctx->stream); }
+            else            { if (general) launch_sub<1, false>(sp, (int)g_sub, ctx->stream); else launch_sub<0, false>(sp, (int)g_sub, ctx->stream); }
+        }
         ++launches;
         ctx->ev_sub = true;
     }
@@ -343,7 +354,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     ep.states = d_states; ep.bodies = ctx->d_bodies.p; ep.n_bodies = n; ep.ocean = ctx->d_ocean.p;
     ep.off_sub = ctx->d_off_sub.p; ep.off_surf = ctx->d_off_surf.p;
     ep.part_sub = ctx->d_part_sub.p; ep.part_surf = ctx->d_part_surf.p;
-    ep.grid_sub = (uint32_t)g_sub; ep.grid_surf = (uint32_t)g_surf; ep.out = d_out;
+    ep.grid_sub = (uint32_t)g_sub; ep.grid_surf = (uint32_t)g_surf; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
     k_epilogue<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ep);
     ++launches;
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -354,7 +365,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
 }
 
 int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n, sfh_info* out, uint8_t* codes,
-              size_t codes_bytes, bool debug)
+              size_t codes_bytes, bool debug, bool aero = false)
 {
     if (!ctx) return SFH_ERR_INVALID;
     if (!ocean || (!states && n) || (!out && n)) return fail(ctx, SFH_ERR_INVALID, "null argument");
@@ -366,6 +377,7 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
     // host-side validation and work bound (the mesh table is host-visible)
     StepPlan plan;
     plan.debug = debug;
+    plan.aero = aero;
     plan.may_sub = plan.may_surf = false;
     std::vector<uint64_t> code_base;
     if (debug) code_base.resize(n);
@@ -379,6 +391,7 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
                 return fail(ctx, SFH_ERR_INVALID, "body %u: unknown mesh id %u", i, s.mesh_id);
             const HostMesh& m = ctx->meshes[s.mesh_id];
             if (debug) { code_base[i] = total_codes; total_codes += m.stats.n_faces; }
+            if (aero) { plan.chunks_ub += m.stats.n_chunks; plan.may_sub = true; plan.faces += m.stats.n_faces; continue; }
             if (s.mode == SFH_POS_OUTSIDE) continue;
             plan.chunks_ub += m.stats.n_chunks;
             if (s.mode != SFH_POS_CROSSING) plan.may_sub = true;
@@ -412,7 +425,7 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
         sfh_ctx::GraphKey key;
         std::memset(&key, 0, sizeof(key));
         key.n = n; key.n_currents = ocean->n_currents; key.n_meshes = (uint32_t)ctx->meshes.size();
-        key.flags = (general ? 1u : 0u) | (ocean->has_waves ? 2u : 0u) | (plan.may_sub ? 4u : 0u) | (plan.may_surf ? 8u : 0u);
+        key.flags = (general ? 1u : 0u) | (ocean->has_waves ? 2u : 0u) | (plan.may_sub ? 4u : 0u) | (plan.may_surf ? 8u : 0u) | (aero ? 16u : 0u);
         key.chunks_ub = plan.chunks_ub;
         key.d_states = ctx->d_states.p; key.d_info = ctx->d_info.p; key.h_states = ctx->h_states.p; key.h_info = ctx->h_info.p;
         key.h_ocean = ctx->h_ocean.p; key.d_ocean = ctx->d_ocean.p; key.d_meshes = ctx->d_meshes.p; key.d_bodies = ctx->d_bodies.p;
@@ -705,6 +718,44 @@ int sfh_step_debug(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* s
     return sfh_sync(ctx);
 }
 
+// sf::Atmosphere as the kernels' fluid record: wind = currents that are always enabled (Atmosphere.cpp:146-152)
+static int atmosphere_as_fluid(sfh_ctx* ctx, const sfh_atmosphere* atm, sfh_ocean* fluid)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!atm) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    if (atm->n_winds > SFH_MAX_CURRENTS) return fail(ctx, SFH_ERR_INVALID, "n_winds %u > %u", atm->n_winds, SFH_MAX_CURRENTS);
+    fluid->density = atm->density;
+    fluid->gravity_z = 0.0;
+    fluid->has_waves = 0;
+    fluid->currents_enabled = 1;
+    fluid->n_currents = atm->n_winds;
+    fluid->reserved = 0;
+    for (uint32_t i = 0; i < atm->n_winds; ++i) { fluid->currents[i] = atm->winds[i]; fluid->currents[i].enabled = 1; }
+    return SFH_OK;
+}
+
+int sfh_aero_step(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_state* states, uint32_t n_bodies, sfh_info* out)
+{
+    sfh_ocean fluid;
+    int rc = atmosphere_as_fluid(ctx, atm, &fluid);
+    if (rc != SFH_OK) return rc;
+    rc = step_host(ctx, &fluid, states, n_bodies, out, nullptr, 0, false, true);
+    if (rc != SFH_OK) return rc;
+    return sfh_sync(ctx);
+}
+
+int sfh_aero_step_debug(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_state* states, uint32_t n_bodies, sfh_info* out,
+                        uint8_t* face_codes, size_t face_codes_bytes)
+{
+    if (ctx && !face_codes && n_bodies) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    sfh_ocean fluid;
+    int rc = atmosphere_as_fluid(ctx, atm, &fluid);
+    if (rc != SFH_OK) return rc;
+    rc = step_host(ctx, &fluid, states, n_bodies, out, face_codes, face_codes_bytes, true, true);
+    if (rc != SFH_OK) return rc;
+    return sfh_sync(ctx);
+}
+
 int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies, sfh_info* d_out)
 {
     if (!ctx) return SFH_ERR_INVALID;
@@ -715,6 +766,24 @@ int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* 
     plan.host_states = false;
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = run_step(ctx, ocean, d_states, n_bodies, d_out, plan);
+    if (rc != SFH_OK) return rc;
+    ctx->ev_valid = ctx->profiling;
+    return SFH_OK;
+}
+
+int sfh_aero_step_device(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_state* d_states, uint32_t n_bodies, sfh_info* d_out)
+{
+    sfh_ocean fluid;
+    int rc = atmosphere_as_fluid(ctx, atm, &fluid);
+    if (rc != SFH_OK) return rc;
+    if ((!d_states && n_bodies) || (!d_out && n_bodies)) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n_bodies == 0) return SFH_OK;
+    StepPlan plan;
+    plan.host_states = false;
+    plan.aero = true;
+    if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = run_step(ctx, &fluid, d_states, n_bodies, d_out, plan);
     if (rc != SFH_OK) return rc;
     ctx->ev_valid = ctx->profiling;
     return SFH_OK;

@@ -344,6 +344,7 @@ struct PrologueParams {
     uint32_t* off_sub;  // n_bodies + 1
     uint32_t* off_surf; // n_bodies + 1
     uint32_t* status;   // [0] |= 1 if a body referenced an unknown mesh
+    uint32_t aero;      // sfh_aero_step: every body runs the (aero variant of the) submerged face loop
 };
 
 // SolidEntity::CheckBodyFluidPosition (SolidEntity.cpp:1239-1261); each corner narrowed to fp32 by
@@ -392,7 +393,10 @@ __global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
     const bool dispatch = (st.flags & SFH_F_DISPATCH) != 0;
     bool damping = (st.flags & SFH_F_DAMPING) != 0, buoyancy = (st.flags & SFH_F_BUOYANCY) != 0;
     uint32_t kind = KIND_NONE;
-    if (pos == SFH_POS_INSIDE) {
+    if (P.aero) { // SolidEntity::ComputeAerodynamicForces has no position test and no settings (SolidEntity.cpp:1852-1923)
+        pos = SFH_POS_OUTSIDE;
+        kind = KIND_SUBMERGED;
+    } else if (pos == SFH_POS_INSIDE) {
         // raw integrator: always runs (it has no settings); dispatcher: only `if(settings.dampingForces)`
         if (!dispatch || damping) kind = KIND_SUBMERGED;
         damping = true;
@@ -479,29 +483,44 @@ struct EpilogueParams {
     const PartialSub* part_sub;
     const PartialSurf* part_surf;
     uint32_t grid_sub, grid_surf;
+    uint32_t aero;
     sfh_info* out;
 };
 
-// SolidEntity::CorrectHydrodynamicForces (SolidEntity.cpp:1263-1287)
-__device__ inline void correct_forces(double density, double* Fdq, double* Tdq, double* Fdf, double* Tdf, const double* Cd,
-                                      const double* Cf, const double* B)
+// btMatrix3x3::inverse (cofactors / determinant) as three rows, and btVector3::safeNormalize of M^-1 * X
+struct Inv3 { D3 r0, r1, r2; };
+__device__ inline Inv3 basis_inverse(const double* B)
 {
 #define EL(r, c) B[3 * (r) + (c)]
 #define COFAC(r1, c1, r2, c2) dsub(dmul(EL(r1, c1), EL(r2, c2)), dmul(EL(r1, c2), EL(r2, c1)))
     const D3 co = {COFAC(1, 1, 2, 2), COFAC(1, 2, 2, 0), COFAC(1, 0, 2, 1)};
     const double det = ddot(D3{EL(0, 0), EL(0, 1), EL(0, 2)}, co);
     const double s = ddiv(1.0, det);
-    const D3 r0 = {dmul(co.x, s), dmul(COFAC(0, 2, 2, 1), s), dmul(COFAC(0, 1, 1, 2), s)};
-    const D3 r1 = {dmul(co.y, s), dmul(COFAC(0, 0, 2, 2), s), dmul(COFAC(0, 2, 1, 0), s)};
-    const D3 r2 = {dmul(co.z, s), dmul(COFAC(0, 1, 2, 0), s), dmul(COFAC(0, 0, 1, 1), s)};
+    Inv3 I;
+    I.r0 = D3{dmul(co.x, s), dmul(COFAC(0, 2, 2, 1), s), dmul(COFAC(0, 1, 1, 2), s)};
+    I.r1 = D3{dmul(co.y, s), dmul(COFAC(0, 0, 2, 2), s), dmul(COFAC(0, 2, 1, 0), s)};
+    I.r2 = D3{dmul(co.z, s), dmul(COFAC(0, 1, 2, 0), s), dmul(COFAC(0, 0, 1, 1), s)};
 #undef EL
 #undef COFAC
+    return I;
+}
+__device__ inline D3 to_frame_normalized(const Inv3& I, const double* X)
+{
+    const D3 v = {X[0], X[1], X[2]};
+    D3 q = {ddot(I.r0, v), ddot(I.r1, v), ddot(I.r2, v)};
+    const double l2 = ddot(q, q);
+    if (l2 >= 2.2204460492503131e-16 * 2.2204460492503131e-16) q = q * ddiv(1.0, __dsqrt_rn(l2));
+    else q = D3{1.0, 0.0, 0.0};
+    return q;
+}
+
+// SolidEntity::CorrectHydrodynamicForces (SolidEntity.cpp:1263-1287)
+__device__ inline void correct_forces(double density, double* Fdq, double* Tdq, double* Fdf, double* Tdf, const double* Cd,
+                                      const double* Cf, const double* B)
+{
+    const Inv3 I = basis_inverse(B);
     auto coeff = [&](const double* X, const double* C) {
-        D3 v = {X[0], X[1], X[2]};
-        D3 q = {ddot(r0, v), ddot(r1, v), ddot(r2, v)};
-        double l2 = ddot(q, q);
-        if (l2 >= 2.2204460492503131e-16 * 2.2204460492503131e-16) q = q * ddiv(1.0, __dsqrt_rn(l2));
-        else q = D3{1.0, 0.0, 0.0};
+        const D3 q = to_frame_normalized(I, X);
         return dadd(dadd(dmul(fabs(q.x), C[0]), dmul(fabs(q.y), C[1])), dmul(fabs(q.z), C[2]));
     };
     double k;
@@ -509,6 +528,17 @@ __device__ inline void correct_forces(double density, double* Fdq, double* Tdq, 
     k = dmul(dmul(0.5, density), coeff(Tdq, Cd)); Tdq[0] = dmul(Tdq[0], k); Tdq[1] = dmul(Tdq[1], k); Tdq[2] = dmul(Tdq[2], k);
     k = dmul(density, coeff(Fdf, Cf)); Fdf[0] = dmul(Fdf[0], k); Fdf[1] = dmul(Fdf[1], k); Fdf[2] = dmul(Fdf[2], k);
     k = dmul(density, coeff(Tdf, Cf)); Tdf[0] = dmul(Tdf[0], k); Tdf[1] = dmul(Tdf[1], k); Tdf[2] = dmul(Tdf[2], k);
+}
+
+// SolidEntity::CorrectAerodynamicForces (SolidEntity.cpp:1925-1956): B = T_CG2H.getBasis(); Cd = the proxy's vector,
+// used only for CYLINDER / ELLIPSOID (use_cd)
+__device__ inline void correct_aero(double* Fda, double* Tda, const double* Cd, const double* B, bool use_cd)
+{
+    const D3 Fdan = to_frame_normalized(basis_inverse(B), Fda);
+    double cor = 1.0;
+    if (use_cd) cor = dadd(dadd(dmul(Cd[0], Fdan.x), dmul(Cd[1], Fdan.y)), dmul(Cd[2], Fdan.z));
+    cor = fabs(cor);
+    for (int k = 0; k < 3; ++k) { Fda[k] = dmul(Fda[k], cor); Tda[k] = dmul(Tda[k], cor); }
 }
 
 __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
@@ -571,6 +601,15 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
     o.n_degenerate = cnt[0]; o.n_quadratic = cnt[1]; o.n_skin = cnt[2];
     for (int k = 0; k < 8; ++k) o.class_count[k] = cnt[3 + k];
 
+    if (P.aero) { // SolidEntity.cpp:1920-1922, then CorrectAerodynamicForces
+        const double k = dmul(0.5, oc.density);
+        for (int c = 0; c < 3; ++c) { o.Fdq[c] = dmul(acc[c], k); o.Tdq[c] = dmul(acc[3 + c], k); }
+        o.wrote_damping = 1;
+        o.class_count[7] = o.n_faces;
+        if (dispatch) correct_aero(o.Fdq, o.Tdq, st.Cd, st.T_O_basis, (st.flags & SFH_F_AERO_CD) != 0);
+        P.out[b] = o;
+        return;
+    }
     if (pos == SFH_POS_OUTSIDE) { // SolidEntity.cpp:1810-1821
         o.wrote_buoyancy = 1; o.wrote_damping = 1;
     } else if (pos == SFH_POS_INSIDE) {

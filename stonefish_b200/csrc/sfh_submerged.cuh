@@ -97,6 +97,36 @@ __device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_curr
     return code;
 }
 
+// Air-drag block for a pair of faces: SolidEntity::ComputeAerodynamicForces (SolidEntity.cpp:1909-1919). The reference
+// tests dot(fn1, vn), not dot(vc, fn1), and scales by vn.length() — glm's COMPONENT COUNT, 3 — through
+// glm/gtx/scalar_multiplication.hpp (vec3 * int -> vec3 *= 3.f); both are kept. acc[0..5] = Fda Tda.
+template <int CUR>
+__device__ __forceinline__ uint32_t aero_pair(const BodyP2& B, const sfh_current* s_cur, uint32_t n_cur, V3P fc, V3P fn1, P2 A,
+                                              bool mA, bool mB, double* acc, uint32_t& epack)
+{
+    V3P fluid = B.cur;
+    if (CUR) {
+        const F3 fa = fluid_velocity_general(s_cur, n_cur, F3{lo(fc.x), lo(fc.y), lo(fc.z)});
+        const F3 fb = fluid_velocity_general(s_cur, n_cur, F3{hi(fc.x), hi(fc.y), hi(fc.z)});
+        fluid = V3P{pk(fa.x, fb.x), pk(fa.y, fb.y), pk(fa.z, fb.z)};
+    }
+    const V3P r = fc - B.p;
+    const V3P vc = fluid - (B.v + cross(B.omega, r));
+    const V3P vn = fn1 * dot(vc, fn1);
+    const P2 t = dot(fn1, vn);
+    uint32_t code = 0;
+    const bool qA = mA && lo(t) < -1e-12f, qB = mB && hi(t) < -1e-12f;
+    if (__any_sync(SFH_FULL, qA | qB)) {
+        const V3P q = (vn * pk1(3.f)) * A;
+        const V3P tq = cross(r, q);
+        if (qA) acc6(acc, lo(q.x), lo(q.y), lo(q.z), lo(tq.x), lo(tq.y), lo(tq.z));
+        if (qB) acc6(acc, hi(q.x), hi(q.y), hi(q.z), hi(tq.x), hi(tq.y), hi(tq.z));
+        epack += (qA ? 1u << 10 : 0u) + (qB ? 1u << 10 : 0u);
+        code |= (qA ? (uint32_t)SFH_FACE_QUADRATIC : 0u) | (qB ? (uint32_t)SFH_FACE_QUADRATIC << 8 : 0u);
+    }
+    return code;
+}
+
 // State of the block-wide walk over work items, shared by k_submerged and k_surface.
 // Thread 0 alone tracks where the staged chunk came from so it can chain the next copy.
 struct ItemWalk {
@@ -138,7 +168,8 @@ __device__ __forceinline__ void walk_issue_next(const PipeAddr& pipe, ItemWalk& 
     pipe_issue(pipe, it.s ^ 1, nsrc, nbytes);
 }
 
-template <int CUR, bool DEBUG>
+// AERO: the same face loop with the air-drag block (SolidEntity::ComputeAerodynamicForces, SolidEntity.cpp:1886-1919)
+template <int CUR, bool DEBUG, bool AERO = false>
 __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
 {
     __shared__ ChunkPipe s_pipe;
@@ -256,11 +287,13 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
                 if (fast) {
                     const V3P fn1 = normalize_fast(fn, len);
                     const V3P fc = {ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)};
-                    code = damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
+                    code = AERO ? aero_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack)
+                                : damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
                 } else { // operands outside the proven range: hardware divisions
                     V3P fn1, fc;
                     normalize_centroid_slow(fn, len, csum, fn1, fc);
-                    code = damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
+                    code = AERO ? aero_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack)
+                                : damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
                 }
             }
             if (DEBUG) {

@@ -199,6 +199,33 @@ private:
     bool wavesDirty = false;
 };
 
+// ------------------------------------------------------------------------------------------------ atmosphere
+//! What the aerodynamic integrator reads from sf::Atmosphere (Atmosphere.cpp:72-75,117-157): the gas density and the
+//! wind fields, which the reference sums without consulting isEnabled(). Owns its fields like the reference.
+class Atmosphere {
+public:
+    explicit Atmosphere(Scalar gasDensity) : density(gasDensity) {}
+    void AddVelocityField(VelocityField* field) { wind.emplace_back(field); }
+    Scalar getGasDensity() const { return density; }
+    void Fill(sfh_atmosphere& a) const
+    {
+        if (wind.size() > SFH_MAX_CURRENTS) throw std::runtime_error("more than 64 velocity fields");
+        a.density = density; a.n_winds = (uint32_t)wind.size(); a.reserved = 0;
+        for (size_t i = 0; i < wind.size(); ++i) {
+            std::memset(&a.winds[i], 0, sizeof(sfh_current));
+            a.winds[i].enabled = wind[i]->isEnabled();
+            wind[i]->Fill(a.winds[i]);
+        }
+    }
+
+private:
+    Scalar density;
+    std::vector<std::unique_ptr<VelocityField>> wind;
+};
+
+//! sf::GeometryApproxType (SolidEntity.h:39)
+enum class GeometryApproxType { AUTO, SPHERE, CYLINDER, ELLIPSOID };
+
 // ------------------------------------------------------------------------------------------------ bodies
 //! The members SolidEntity::ComputeHydrodynamicForces reads from a body (SolidEntity.cpp:1799-1850).
 struct SolidBody {
@@ -212,6 +239,11 @@ struct SolidBody {
     Vector3 v, omega;              // getLinearVelocity(), getAngularVelocity()
     Vector3 aabbMin, aabbMax;      // getAABB()
     HydrodynamicsInfo info;        // outputs, with the reference's "leave untouched" semantics
+    // aerodynamics (SolidEntity.h:423-427,436): proxy type / parameters, T_CG2H, and the outputs Fda, Tda
+    GeometryApproxType fdApproxType = GeometryApproxType::AUTO;
+    Scalar fdApproxParams[3] = {1, 1, 1};
+    Transform T_CG2H;
+    Vector3 Fda, Tda;
 };
 
 //! One GPU worth of hydrodynamics: replaces the ThreadPool-driven loop of SimulationManager::SimulationTickCallback
@@ -265,6 +297,38 @@ public:
         for (size_t i = 0; i < bodies.size(); ++i) Scatter(infos[i], bodies[i]->info);
     }
 
+    //! Atmosphere::ApplyFluidForces' recompute for every body of the batch (Atmosphere.cpp:187-192):
+    //! SolidEntity::ComputeAerodynamicForces = static integrator + CorrectAerodynamicForces (SolidEntity.cpp:1852-1956).
+    //! Results land in bodies[i]->Fda / Tda. The caller filters on PhysicsMode::AERODYNAMIC like the reference (:1854).
+    void ComputeAerodynamicForces(const Atmosphere& atm, const std::vector<SolidBody*>& bodies)
+    {
+        atm.Fill(atmosphere);
+        states.resize(bodies.size());
+        infos.resize(bodies.size());
+        for (size_t i = 0; i < bodies.size(); ++i) {
+            const SolidBody& b = *bodies[i];
+            sfh_body_state& s = states[i];
+            std::memset(&s, 0, sizeof(s));
+            s.mesh_id = b.meshId;
+            s.flags = (uint32_t)SFH_F_DISPATCH;
+            std::memcpy(s.T_CG, b.T_CG.m, sizeof(s.T_CG));
+            std::memcpy(s.T_C, b.T_C.m, sizeof(s.T_C));
+            std::memcpy(s.T_O_basis, b.T_CG2H.m, sizeof(s.T_O_basis));
+            Put(s.v, b.v); Put(s.omega, b.omega);
+            if (b.fdApproxType == GeometryApproxType::CYLINDER) { // SolidEntity.cpp:1937-1941
+                s.Cd[0] = 0.5; s.Cd[1] = 0.5; s.Cd[2] = 1.0;
+                s.flags |= (uint32_t)SFH_F_AERO_CD;
+            } else if (b.fdApproxType == GeometryApproxType::ELLIPSOID) { // :1943-1950, Cd /= maxCd multiplies by 1/maxCd
+                const Scalar cx = Scalar(1) / b.fdApproxParams[0], cy = Scalar(1) / b.fdApproxParams[1], cz = Scalar(1) / b.fdApproxParams[2];
+                const Scalar mx = cx > cy ? cx : cy, maxCd = mx > cz ? mx : cz, inv = Scalar(1) / maxCd;
+                s.Cd[0] = cx * inv; s.Cd[1] = cy * inv; s.Cd[2] = cz * inv;
+                s.flags |= (uint32_t)SFH_F_AERO_CD;
+            }
+        }
+        Check(sfh_aero_step(ctx, &atmosphere, states.data(), (uint32_t)states.size(), infos.data()), "sfh_aero_step");
+        for (size_t i = 0; i < bodies.size(); ++i) { bodies[i]->Fda = Get(infos[i].Fdq); bodies[i]->Tda = Get(infos[i].Tdq); }
+    }
+
     //! Batched Ocean::GetDepth(glm::vec3) / Ocean::GetFluidVelocity(glm::vec3) (Ocean.cpp:149-168, 198-201).
     void GetDepth(Ocean& ocn, const float* xyz, size_t n, float* depth)
     {
@@ -305,6 +369,7 @@ private:
 
     sfh_ctx* ctx = nullptr;
     sfh_ocean ocean;
+    sfh_atmosphere atmosphere;
     std::vector<sfh_body_state> states;
     std::vector<sfh_info> infos;
 };
@@ -372,6 +437,19 @@ inline void SumCompoundParts(const std::vector<CompoundPart>& parts, const Hydro
             out.Swet += r.Swet;
         }
     }
+}
+
+//! Host half of Compound::ComputeAerodynamicForces (Compound.cpp:439-464): Fda/Tda of the external parts, each already
+//! corrected with its own proxy by HydroEngine::ComputeAerodynamicForces, summed in part order. Parts are submitted with
+//! the compound's T_CG, v, omega and T_C = T_O * origin_i * O2C_i.
+inline void SumCompoundPartsAero(const std::vector<CompoundPart>& parts, Vector3& Fda, Vector3& Tda)
+{
+    Fda = Tda = Vector3();
+    for (const CompoundPart& p : parts)
+        if (p.isExternal) {
+            Fda.x += p.body->Fda.x; Fda.y += p.body->Fda.y; Fda.z += p.body->Fda.z;
+            Tda.x += p.body->Tda.x; Tda.y += p.body->Tda.y; Tda.z += p.body->Tda.z;
+        }
 }
 
 } // namespace sfb

@@ -3,7 +3,9 @@
 //   print "Hydrodynamics time: <avg> us" like Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:166.
 // The scenario is read from a small binary file written by tests/test_host_mirror_gpu.py (so the same inputs can be
 // pushed through the Python binding and the oracle), results go to a binary file. Needs a CUDA device at run time.
-//   usage: demo_fluid_dynamics scene.bin out.bin [steps]
+//   usage: demo_fluid_dynamics scene.bin out.bin [steps [aero_out.bin]]
+// With aero_out.bin the same bodies also go through HydroEngine::ComputeAerodynamicForces once: wind = the scene's velocity
+// fields, gas density 1.2, proxy type cycling AUTO/SPHERE/CYLINDER/ELLIPSOID with fdCd as the ellipsoid radii, T_CG2H = T_O.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +38,7 @@ int main(int argc, char** argv)
     try {
         sfb::HydroEngine engine(0);
         sfb::Ocean ocean(density, gravity);
+        sfb::Atmosphere atmosphere(1.2);
         for (uint32_t i = 0; i < nCurrents; ++i) {
             const uint32_t type = rd<uint32_t>(in), enabled = rd<uint32_t>(in);
             double a[10];
@@ -46,6 +49,12 @@ int main(int argc, char** argv)
             else f = new sfb::Pipe(sfb::Vector3(a[0], a[1], a[2]), sfb::Vector3(a[3], a[4], a[5]), a[6], a[7], a[8], a[9]);
             f->setEnabled(enabled != 0);
             ocean.AddVelocityField(f);
+            sfb::VelocityField* w = nullptr; // the atmosphere owns its own copies
+            if (type == 0) w = new sfb::Uniform(sfb::Vector3(a[0], a[1], a[2]));
+            else if (type == 1) w = new sfb::Jet(sfb::Vector3(a[0], a[1], a[2]), sfb::Vector3(a[3], a[4], a[5]), a[6], a[7]);
+            else w = new sfb::Pipe(sfb::Vector3(a[0], a[1], a[2]), sfb::Vector3(a[3], a[4], a[5]), a[6], a[7], a[8], a[9]);
+            w->setEnabled(enabled != 0);
+            atmosphere.AddVelocityField(w);
         }
         if (currentsEnabled) ocean.EnableCurrents();
 
@@ -89,6 +98,20 @@ int main(int argc, char** argv)
             const uint32_t u[13] = {(uint32_t)r.position, r.faces, r.classCount[0], r.classCount[1], r.classCount[2], r.classCount[3],
                                     r.classCount[4], r.classCount[5], r.classCount[6], r.classCount[7], r.degenerate, r.quadratic, r.skin};
             out.write(reinterpret_cast<const char*>(u), sizeof(u));
+        }
+        if (argc > 4) {
+            for (size_t i = 0; i < bodies.size(); ++i) {
+                sfb::SolidBody& b = bodies[i];
+                b.fdApproxType = (sfb::GeometryApproxType)(i % 4);
+                b.fdApproxParams[0] = b.fdCd.x; b.fdApproxParams[1] = b.fdCd.y; b.fdApproxParams[2] = b.fdCd.z;
+                b.T_CG2H = b.T_O;
+            }
+            engine.ComputeAerodynamicForces(atmosphere, ptrs);
+            std::ofstream aout(argv[4], std::ios::binary);
+            for (const auto& b : bodies) {
+                const double d[6] = {b.Fda.x, b.Fda.y, b.Fda.z, b.Tda.x, b.Tda.y, b.Tda.z};
+                aout.write(reinterpret_cast<const char*>(d), sizeof(d));
+            }
         }
     } catch (const std::exception& e) {
         std::cerr << "error: " << e.what() << "\n";

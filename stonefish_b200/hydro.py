@@ -15,8 +15,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _abi
-from ._abi import (SFH_CURRENT_JET, SFH_CURRENT_PIPE, SFH_CURRENT_UNIFORM, SFH_F_BUOYANCY, SFH_F_BUOYANT, SFH_F_DAMPING,
-                   SFH_F_DISPATCH, SFH_POS_AUTO, SFH_POS_CROSSING, SFH_POS_INSIDE, SFH_POS_OUTSIDE)
+from ._abi import (SFH_CURRENT_JET, SFH_CURRENT_PIPE, SFH_CURRENT_UNIFORM, SFH_F_AERO_CD, SFH_F_BUOYANCY, SFH_F_BUOYANT,
+                   SFH_F_DAMPING, SFH_F_DISPATCH, SFH_POS_AUTO, SFH_POS_CROSSING, SFH_POS_INSIDE, SFH_POS_OUTSIDE)
 
 BODY_STATE_DTYPE = _abi.np_dtype(_abi.sfh_body_state)
 INFO_DTYPE = _abi.np_dtype(_abi.sfh_info)
@@ -175,6 +175,44 @@ class Ocean:
 
 
 # ------------------------------------------------------------------------------------------------ meshes
+class GeometryApproxType:  # sf::GeometryApproxType, SolidEntity.h:39
+    AUTO, SPHERE, CYLINDER, ELLIPSOID = 0, 1, 2, 3
+
+
+class Atmosphere:
+    """What the aerodynamic integrator reads from sf::Atmosphere (Atmosphere.cpp:72-75,117-157): the gas density and the
+    wind list, which the reference sums without consulting isEnabled()."""
+
+    def __init__(self, density: float = 1.2):
+        self.density = float(density)
+        self.wind: list[VelocityField] = []
+
+    def AddVelocityField(self, field: VelocityField):
+        self.wind.append(field)
+
+    def to_struct(self) -> _abi.sfh_atmosphere:
+        a = _abi.sfh_atmosphere()
+        a.density = self.density
+        if len(self.wind) > _abi.SFH_MAX_CURRENTS:
+            raise ValueError("more than 64 velocity fields")
+        a.n_winds = len(self.wind)
+        for i, f in enumerate(self.wind):
+            a.winds[i].enabled = 1 if f.isEnabled() else 0
+            f._fill(a.winds[i])
+        return a
+
+
+def aero_proxy(approx_type: int, params=()):
+    """(Cd vector, flag) that CorrectAerodynamicForces derives from fdApproxType / fdApproxParams
+    (SolidEntity.cpp:1931-1951), in the reference's own operation order (btVector3::operator/= multiplies by 1/s)."""
+    if approx_type == GeometryApproxType.CYLINDER:
+        return np.array([0.5, 0.5, 1.0]), SFH_F_AERO_CD
+    if approx_type == GeometryApproxType.ELLIPSOID:
+        cd = np.array([1.0 / float(params[0]), 1.0 / float(params[1]), 1.0 / float(params[2])])
+        return cd * (1.0 / max(max(cd[0], cd[1]), cd[2])), SFH_F_AERO_CD
+    return np.zeros(3), 0
+
+
 class Mesh:
     """sf::Mesh as the integrators see it (OpenGLDataStructs.h:120-262): vertex positions (possibly strided inside
     a Vertex / TexturableVertex array) and 3 vertex ids per face."""
@@ -335,6 +373,26 @@ class HydroContext:
                                             codes.ctypes.data, codes.size), "sfh_step_debug")
         return out, codes[:n_faces_total]
 
+    def compute_aero(self, atm: Atmosphere, states: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """One recompute of the air drag of all bodies (sfh_aero_step): Fda/Tda arrive in out['Fdq'] / out['Tdq']."""
+        assert states.dtype == BODY_STATE_DTYPE and states.flags.c_contiguous
+        if out is None:
+            out = np.zeros(states.shape[0], dtype=INFO_DTYPE)
+        a = atm.to_struct()
+        self._check(self.lib.sfh_aero_step(self.ctx, C.byref(a), states.ctypes.data, states.shape[0], out.ctypes.data), "sfh_aero_step")
+        return out
+
+    def compute_aero_debug(self, atm: Atmosphere, states: np.ndarray, n_faces_total: int):
+        out = np.zeros(states.shape[0], dtype=INFO_DTYPE)
+        codes = np.zeros(max(n_faces_total, 1), dtype=np.uint8)
+        a = atm.to_struct()
+        self._check(self.lib.sfh_aero_step_debug(self.ctx, C.byref(a), states.ctypes.data, states.shape[0], out.ctypes.data,
+                                                 codes.ctypes.data, codes.size), "sfh_aero_step_debug")
+        return out, codes[:n_faces_total]
+
+    def compute_aero_device(self, atm_struct, d_states_ptr: int, n: int, d_out_ptr: int):
+        self._check(self.lib.sfh_aero_step_device(self.ctx, C.byref(atm_struct), d_states_ptr, n, d_out_ptr), "sfh_aero_step_device")
+
     def compute_device(self, ocean_struct, d_states_ptr: int, n: int, d_out_ptr: int):
         """Device-resident step (sfh_step_device): asynchronous on the context's stream."""
         self._check(self.lib.sfh_step_device(self.ctx, C.byref(ocean_struct), d_states_ptr, n, d_out_ptr), "sfh_step_device")
@@ -458,4 +516,20 @@ def sum_compound(part_infos: np.ndarray, parts: np.ndarray, external, compound: 
             for k in ("Fdq", "Tdq", "Fdf", "Tdf"):
                 out[k] = out[k] + r[k]
             out["Swet"] = out["Swet"] + r["Swet"]
+    return out
+
+
+def sum_compound_aero(part_infos: np.ndarray, external) -> np.ndarray:
+    """Host half of Compound::ComputeAerodynamicForces (Compound.cpp:439-464): Fda/Tda of the external parts, each already
+    corrected with its own proxy by sfh_aero_step (SFH_F_DISPATCH), summed in part order."""
+    out = np.zeros(1, dtype=INFO_DTYPE)
+    out["wrote_damping"] = 1
+    for i in range(part_infos.shape[0]):
+        if not external[i]:
+            continue
+        out["Fdq"][0] += part_infos["Fdq"][i]
+        out["Tdq"][0] += part_infos["Tdq"][i]
+        for k in ("n_faces", "n_degenerate", "n_quadratic"):
+            out[k][0] += part_infos[k][i]
+        out["class_count"][0][7] += part_infos["class_count"][i][7]
     return out

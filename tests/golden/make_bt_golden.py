@@ -130,6 +130,24 @@ for i in range(8):
     lib.btc_flat_buoyancy((D * 12)(*Ts[i]), (D * 3)(*cb), D(vol), D(1000.0), D(9.81), Fb, Tb)
     out["flat_buoyancy"].append({"T_CG": hx(Ts[i]), "CB": hx(cb), "Vsub": vol.hex(), "Fb": hx(Fb), "Tb": hx(Tb)})
 
+# --- CorrectAerodynamicForces for every GeometryApproxType (SolidEntity.cpp:1925-1956), incl. a zero force and the
+# ELLIPSOID coefficient vector on its own (for the host mirrors)
+out["correct_aero"], out["ellipsoid_cd"] = [], []
+for i in range(12):
+    F, T = take(3, -30, 30), take(3, -30, 30)
+    if i == 5:
+        F = [0.0, 0.0, 0.0]
+    kind = i % 4
+    params = take(3, 0.05, 2.0)
+    B = Ts[i][:9]
+    bF, bT = (D * 3)(*F), (D * 3)(*T)
+    lib.btc_correct_aero(bF, bT, C.c_int(kind), (D * 3)(*params), (D * 9)(*B))
+    out["correct_aero"].append({"type": kind, "params": hx(params), "B": hx(B), "in": [hx(F), hx(T)], "out": [hx(bF), hx(bT)]})
+    cd = arr(3)
+    lib.btc_ellipsoid_cd((D * 3)(*params), cd)
+    out["ellipsoid_cd"].append({"params": hx(params), "cd": hx(cd)})
+assert k < len(u)
+
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bt_golden.json")
 json.dump(out, open(path, "w"), indent=0)
 print("wrote", path, {k: len(v) for k, v in out.items() if isinstance(v, list)})

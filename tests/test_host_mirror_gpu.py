@@ -74,3 +74,35 @@ def test_cpp_host_mirror_runs_the_fluid_dynamics_scene(tmp_path, oracle):
     err, where = max_rel_err(got, ref)
     assert err <= REL_TOL, (err, where)
     assert set(np.unique(got["position"])) == {0, 1, 2}
+
+
+def test_cpp_host_mirror_aerodynamics(tmp_path, oracle):
+    """sfb::Atmosphere + HydroEngine::ComputeAerodynamicForces (incl. the proxy vectors of CorrectAerodynamicForces built in
+    C++) on the same scene, against the oracle fed through the Python mirror's aero_proxy."""
+    from stonefish_b200._abi import SFH_F_DISPATCH
+    from stonefish_b200.hydro import Atmosphere, aero_proxy
+
+    assert os.path.exists(DEMO), "build the host mirror demo first (make -C stonefish_b200/host)"
+    sc = scenes.config1()
+    fields = [Uniform((4.0, -1.0, 0.0)), Jet((0.0, -3.0, 1.0), (0.1, 1.0, 0.05), 0.3, 9.0),
+              Pipe((-6.0, 0.5, 1.5), (6.0, -0.5, 2.0), 2.0, 3.0, 5.0, 2.0)]
+    fields[1].setEnabled(False)  # wind ignores it (Atmosphere.cpp:146-152)
+    atm = Atmosphere(1.2)
+    for f in fields:
+        sc.ocean.AddVelocityField(f)
+        atm.AddVelocityField(f)
+    scene, res, ares = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin"), str(tmp_path / "aero.bin")
+    write_scene(scene, sc)
+    subprocess.check_output([DEMO, scene, res, "2", ares], text=True)
+    raw = np.fromfile(ares, dtype=np.float64).reshape(sc.n_bodies, 6)
+    st = sc.states.copy()
+    for i in range(sc.n_bodies):
+        cd, flag = aero_proxy(i % 4, st["Cd"][i])
+        st["Cd"][i] = cd
+        st["flags"][i] = SFH_F_DISPATCH | flag
+    ref = oracle.aero(sc.meshes, sc.body_mesh, atm, st)
+    got = np.zeros(sc.n_bodies, dtype=INFO_DTYPE)
+    got["Fdq"], got["Tdq"] = raw[:, :3], raw[:, 3:]
+    err, where = max_rel_err(got, ref)
+    assert err <= REL_TOL, (err, where)
+    assert np.linalg.norm(ref["Fdq"], axis=1).min() > 0
