@@ -25,8 +25,12 @@
 #include <cstring>
 #include <vector>
 
+#ifndef SFH_CH_FACES
 #define SFH_CH_FACES 256u
+#endif
+#ifndef SFH_CH_VERTS
 #define SFH_CH_VERTS 256u
+#endif
 #define SFH_CH_HDR_BYTES 16u
 #define SFH_CH_MAX_BYTES (SFH_CH_HDR_BYTES + 12u * SFH_CH_VERTS + 4u * SFH_CH_FACES) /* 4112 */
 

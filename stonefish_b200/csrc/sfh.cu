@@ -183,11 +183,11 @@ int arena_alloc(sfh_ctx* ctx, size_t bytes, uint8_t** out)
 }
 
 template <typename K>
-int occupancy(sfh_ctx* ctx, K kernel, int* cache)
+int occupancy(sfh_ctx* ctx, K kernel, int* cache, int threads = SFH_BLOCK)
 {
     if (*cache == 0) {
         int n = 0;
-        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, SFH_BLOCK, 0));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0));
         *cache = n > 0 ? n : 1;
     }
     return SFH_OK;
@@ -259,7 +259,7 @@ struct StepPlan {
 };
 
 template <int CUR, bool DEBUG, bool AERO = false>
-void launch_sub(const StepParams& P, int grid, cudaStream_t s) { k_submerged<CUR, DEBUG, AERO><<<grid, SFH_BLOCK, 0, s>>>(P); }
+void launch_sub(const StepParams& P, int grid, cudaStream_t s) { k_submerged<CUR, DEBUG, AERO><<<grid, SFH_SUB_THREADS, 0, s>>>(P); }
 template <bool WAVES, int CUR, bool DEBUG>
 void launch_surf(const StepParams& P, int grid, cudaStream_t s) { k_surface<WAVES, CUR, DEBUG><<<grid, SFH_BLOCK, 0, s>>>(P); }
 
@@ -273,9 +273,11 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
 
     // persistent grids
     if (plan.aero) {
-        if (general) rc = occupancy(ctx, k_submerged<1, false, true>, &ctx->occ_aero[1]); else rc = occupancy(ctx, k_submerged<0, false, true>, &ctx->occ_aero[0]);
+        if (general) rc = occupancy(ctx, k_submerged<1, false, true>, &ctx->occ_aero[1], SFH_SUB_THREADS);
+        else         rc = occupancy(ctx, k_submerged<0, false, true>, &ctx->occ_aero[0], SFH_SUB_THREADS);
     } else {
-        if (general) rc = occupancy(ctx, k_submerged<1, false>, &ctx->occ_sub[1]); else rc = occupancy(ctx, k_submerged<0, false>, &ctx->occ_sub[0]);
+        if (general) rc = occupancy(ctx, k_submerged<1, false>, &ctx->occ_sub[1], SFH_SUB_THREADS);
+        else         rc = occupancy(ctx, k_submerged<0, false>, &ctx->occ_sub[0], SFH_SUB_THREADS);
     }
     if (rc != SFH_OK) return rc;
     int* occs = &ctx->occ_surf[waves ? 1 : 0][general ? 1 : 0];
@@ -287,18 +289,19 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     if (rc != SFH_OK) return rc;
     uint64_t g_sub = (uint64_t)ctx->num_sms * (uint64_t)(plan.aero ? ctx->occ_aero : ctx->occ_sub)[general ? 1 : 0];
     uint64_t g_surf = (uint64_t)ctx->num_sms * (uint64_t)*occs;
+    // g_sub counts BLOCKS; each block runs SFH_SUB_WPB independent streams (one partial record per stream and body)
     if (plan.chunks_ub) {
-        if (g_sub > plan.chunks_ub) g_sub = plan.chunks_ub;
+        if (g_sub * SFH_SUB_WPB > plan.chunks_ub) g_sub = (plan.chunks_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
         if (g_surf > plan.chunks_ub) g_surf = plan.chunks_ub;
     }
 
     // buffers (growing them requires the stream to be idle: older kernels may still read the old ones)
-    const bool grow = n > ctx->d_bodies.cap || n + 1 > ctx->d_off_sub.cap || g_sub + n > ctx->d_part_sub.cap || g_surf + n > ctx->d_part_surf.cap;
+    const bool grow = n > ctx->d_bodies.cap || n + 1 > ctx->d_off_sub.cap || g_sub * SFH_SUB_WPB + n > ctx->d_part_sub.cap || g_surf + n > ctx->d_part_surf.cap;
     if (grow) CU(ctx, cudaStreamSynchronize(ctx->stream));
     if ((rc = ensure_dev(ctx, ctx->d_bodies, n)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_off_sub, n + 1)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_off_surf, n + 1)) != SFH_OK) return rc;
-    if ((rc = ensure_dev(ctx, ctx->d_part_sub, g_sub + n)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_part_sub, g_sub * SFH_SUB_WPB + n)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_part_surf, g_surf + n)) != SFH_OK) return rc;
     if (!ctx->d_status.p) {
         if ((rc = ensure_dev(ctx, ctx->d_status, 4)) != SFH_OK) return rc;
@@ -354,7 +357,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     ep.states = d_states; ep.bodies = ctx->d_bodies.p; ep.n_bodies = n; ep.ocean = ctx->d_ocean.p;
     ep.off_sub = ctx->d_off_sub.p; ep.off_surf = ctx->d_off_surf.p;
     ep.part_sub = ctx->d_part_sub.p; ep.part_surf = ctx->d_part_surf.p;
-    ep.grid_sub = (uint32_t)g_sub; ep.grid_surf = (uint32_t)g_surf; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
+    ep.grid_sub = (uint32_t)(g_sub * SFH_SUB_WPB); ep.grid_surf = (uint32_t)g_surf; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
     k_epilogue<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ep);
     ++launches;
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));

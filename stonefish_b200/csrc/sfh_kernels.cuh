@@ -3,14 +3,14 @@
 //   k_prologue   1 thread/body  per-body: CheckBodyFluidPosition (a9), dispatcher gates (a10), fp64->fp32
 //                               narrowing of transforms/velocities, position-independent current sum,
 //   k_scan_items 1 block        exclusive scan of the per-body chunk counts -> two work lists (submerged / surface)
-//   k_submerged  persistent     per-face ComputeHydrodynamicForcesSubmerged (a1) over (body, chunk) items
+//   k_submerged  persistent     per-face ComputeHydrodynamicForcesSubmerged (a1) over (body, chunk) items, one stream per WARP
 //   k_surface    persistent     per-face ComputeHydrodynamicForcesSurface  (a2) incl. waves (a3/a4)
 //   k_epilogue   1 warp/body    fixed-order reduction of the per-block partials, finalisation (A.5),
 //                               INSIDE analytic buoyancy and CorrectHydrodynamicForces (a11)
 //
-// Work decomposition: the work list is the concatenation of every active body's chunks; block `blk` of a grid
-// of G blocks owns the contiguous item range [blk*W/G, (blk+1)*W/G). A block keeps fp64 partial sums in
-// registers and writes ONE record per (block, body) it touched at index blk + body — those indices are unique
+// Work decomposition: the work list is the concatenation of every active body's chunks; stream `blk` of G streams
+// (a stream = one block of k_surface, one warp of k_submerged) owns the contiguous item range [blk*W/G, (blk+1)*W/G).
+// A stream keeps fp64 partial sums in registers and writes ONE record per (stream, body) it touched at index blk + body — those indices are unique
 // because block ranges are contiguous and monotone in the body index — so no atomics, no zero-fill, and the
 // epilogue reduces each body's records in a fixed order: results are bitwise reproducible for a given G.
 #pragma once

@@ -1,14 +1,15 @@
 // sfh_submerged.cuh — k_submerged: SolidEntity::ComputeHydrodynamicForcesSubmerged (SolidEntity.cpp:1749-1791)
-// over (body, chunk) work items, two faces per thread (two independent fp32 streams; FMUL2/FFMA2 with -DSFH_PACKED_F32X2).
+// over (body, chunk) work items, two faces per lane side by side (two independent fp32 streams; FMUL2/FFMA2 with
+// -DSFH_PACKED_F32X2), and its aerodynamic twin (AERO).
 //
-// Per chunk a block of 128 threads
-//   1. transforms the chunk's <=256 vertices ONCE into shared memory (reference: once per incident face,
-//      SolidEntity.cpp:1755-1757 — identical bits),
+// Per chunk ONE WARP
+//   1. transforms the chunk's <=256 vertices ONCE into its private shared-memory buffer (reference: once per incident
+//      face, SolidEntity.cpp:1755-1757 — identical bits),
 //   2. has the NEXT chunk (of this or of the next body) already in flight as one bulk async copy (sfh_chunkpipe.cuh),
-//   3. evaluates faces tid and tid+128 side by side (P2 = one value per face), with the IEEE
-//      divisions and square roots written out (sfh_packed.cuh),
-//   4. adds the fp32 per-face terms into per-thread fp64 accumulators.
-// Accumulators are reduced per (block, body) and written as one partial record (see sfh_kernels.cuh).
+//   3. evaluates faces base+lane and base+lane+32 side by side (P2 = one value per face), 4 such pairs per lane per
+//      chunk, with the IEEE divisions and square roots written out (sfh_packed.cuh),
+//   4. adds the fp32 per-face terms into per-lane fp64 accumulators.
+// Accumulators are reduced per (warp, body) and written as one partial record (see sfh_kernels.cuh).
 #pragma once
 
 #include "sfh_chunkpipe.cuh"
@@ -168,41 +169,85 @@ __device__ __forceinline__ void walk_issue_next(const PipeAddr& pipe, ItemWalk& 
     pipe_issue(pipe, it.s ^ 1, nsrc, nbytes);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Work decomposition: one WARP per stream of work items. Each warp owns a private chunk pipeline and vertex buffer,
+// evaluates 4 face pairs per lane per chunk and never meets a block barrier (the first version gave one 128-thread
+// block per stream: two block barriers per chunk and 1 pair per thread, 6 % slower — DESIGN.md §7).
+// ---------------------------------------------------------------------------------------------------------------
+#define SFH_SUB_WPB 2u /* warps (streams) per block */
+#ifndef SFH_SUB_MIN_BLOCKS
+#define SFH_SUB_MIN_BLOCKS 8
+#endif
+#define SFH_SUB_THREADS (32u * SFH_SUB_WPB)
+
+struct WarpStage { // shared memory private to one warp
+    ChunkPipe pipe;
+    float4 v[SFH_CH_VERTS];
+    BodyDev body;
+};
+
+__device__ __forceinline__ PipeAddr warp_pipe_init(ChunkPipe& p, uint32_t lane)
+{
+    PipeAddr a;
+    a.bar0 = smem_addr(&p.bar[0]);
+    a.buf0 = smem_addr(&p.buf[0][0]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a.bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a.bar0 + 8u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    return a;
+}
+
+__device__ __forceinline__ void warp_load_body(BodyDev* sb, const BodyDev* __restrict__ src, uint32_t lane)
+{
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(sb);
+    for (uint32_t i = lane; i < sizeof(BodyDev) / 4; i += 32) d[i] = __ldg(s + i);
+    __syncwarp();
+}
+
 // AERO: the same face loop with the air-drag block (SolidEntity::ComputeAerodynamicForces, SolidEntity.cpp:1886-1919)
 template <int CUR, bool DEBUG, bool AERO = false>
-__global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
+__global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerged(StepParams P)
 {
-    __shared__ ChunkPipe s_pipe;
-    __shared__ float4 s_v[SFH_CH_VERTS];
-    __shared__ BodyDev s_body;
-    __shared__ double s_red[SFH_BLOCK / 32][SFH_NACC_SUB];
-    __shared__ uint32_t s_cnt[4];
+    __shared__ WarpStage s_stage[SFH_SUB_WPB];
     __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
 
-    const uint32_t tid = threadIdx.x;
-    const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x, W);
-    if (blockIdx.x >= G) return;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
+    if constexpr (CUR != 0) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.ocean->currents);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_cur);
+        for (uint32_t i = threadIdx.x; i < n_cur * (uint32_t)(sizeof(sfh_current) / 4); i += SFH_SUB_THREADS) dst[i] = __ldg(src + i);
+        __syncthreads(); // the only block barrier of the kernel, before any warp can leave
+    }
+    const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x * SFH_SUB_WPB, W);
+    const uint32_t wg = blockIdx.x * SFH_SUB_WPB + warp;
+    if (wg >= G) return;
+    WarpStage& S = s_stage[warp];
+    BodyDev& s_body = S.body;
+    float4* const s_v = S.v;
+
     ItemWalk it;
-    it.w = (uint32_t)((uint64_t)blockIdx.x * W / G);
-    it.w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
+    it.w = (uint32_t)((uint64_t)wg * W / G);
+    it.w1 = (uint32_t)(((uint64_t)wg + 1) * W / G);
     it.s = 0;
     it.parity = 0;
-
-    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
-    if (CUR) stage_currents(s_cur, P.ocean, n_cur);
-    if (tid < 4) s_cnt[tid] = 0;
 
     double acc[SFH_NACC_SUB];
 #pragma unroll
     for (int i = 0; i < SFH_NACC_SUB; ++i) acc[i] = 0.0;
     uint32_t epack = 0, since_spill = 0;
+    uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0; // degenerate, quadratic, skin of the current body (warp-uniform)
 
     it.b = body_of_item(P.item_off, P.n_bodies, it.w);
     it.b_begin = P.item_off[it.b];
     it.b_end = P.item_off[it.b + 1];
-    load_body(&s_body, P.bodies + it.b);
-    const PipeAddr pa = pipe_init(s_pipe); // includes the barrier that publishes s_body
-    if (tid == 0) walk_issue_first(pa, it, s_body);
+    warp_load_body(&s_body, P.bodies + it.b, lane);
+    const PipeAddr pa = warp_pipe_init(S.pipe, lane);
+    if (lane == 0) walk_issue_first(pa, it, s_body);
 
     BodyP2 B;
     auto fetch_regs = [&]() {
@@ -210,52 +255,55 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
         B.v = V3P{pk1(s_body.v[0]), pk1(s_body.v[1]), pk1(s_body.v[2])};
         B.omega = V3P{pk1(s_body.omega[0]), pk1(s_body.omega[1]), pk1(s_body.omega[2])};
         B.cur = V3P{pk1(s_body.cur[0]), pk1(s_body.cur[1]), pk1(s_body.cur[2])};
-#pragma unroll
-        for (int k = 0; k < 9; ++k) B.R[k] = s_body.R[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) B.t[k] = s_body.t[k];
     };
-    auto flush = [&](uint32_t body) {
-        spill_epack(epack, s_cnt);
+    auto spill = [&]() { // 3 x 10-bit per-lane event counters -> warp-uniform totals
+        cnt0 += __reduce_add_sync(SFH_FULL, epack & 1023u);
+        cnt1 += __reduce_add_sync(SFH_FULL, (epack >> 10) & 1023u);
+        cnt2 += __reduce_add_sync(SFH_FULL, (epack >> 20) & 1023u);
+        epack = 0;
         since_spill = 0;
-        PartialSub* rec = reinterpret_cast<PartialSub*>(P.partials) + (blockIdx.x + body);
-        __syncthreads();
-        block_reduce_store<SFH_NACC_SUB>(acc, s_red, rec->a);
-        if (tid < 3) (&rec->n_degenerate)[tid] = s_cnt[tid];
-        __syncthreads();
-        if (tid < 4) s_cnt[tid] = 0;
+    };
+    auto flush = [&](uint32_t body) { // one partial record per (warp, body)
+        spill();
+        PartialSub* rec = reinterpret_cast<PartialSub*>(P.partials) + (wg + body);
+#pragma unroll
+        for (int i = 0; i < SFH_NACC_SUB; ++i) {
+            const double v = warp_sum(acc[i]);
+            if (lane == 0) rec->a[i] = v;
+            acc[i] = 0.0;
+        }
+        if (lane == 0) { rec->n_degenerate = cnt0; rec->n_quadratic = cnt1; rec->n_skin = cnt2; }
+        cnt0 = cnt1 = cnt2 = 0;
     };
     fetch_regs();
 
     for (;;) {
         pipe_wait(pa, it.s, (it.parity >> it.s) & 1u);
         it.parity ^= 1u << it.s;
-        const uint8_t* buf = s_pipe.buf[it.s];
+        const uint8_t* buf = S.pipe.buf[it.s];
         const ChunkView cv = chunk_view(buf);
 
-        __syncthreads(); // every thread is done with the previous chunk: s_v and the other staging buffer are free
+        __syncwarp(); // every lane is done with the previous chunk: s_v and the other staging buffer are free
         const uint8_t* nsrc = nullptr;
         uint32_t nbytes = 0;
-        if (tid == 0) walk_issue_next(pa, it, P, cv.next_bytes, nsrc, nbytes);
+        if (lane == 0) walk_issue_next(pa, it, P, cv.next_bytes, nsrc, nbytes);
 
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t i = tid + k * SFH_BLOCK;
+        for (int k = 0; k < (int)(SFH_CH_VERTS / 32u); ++k) { // each vertex transformed once per chunk (SolidEntity.cpp:1755-1757)
+            const uint32_t i = lane + 32u * k;
             if (i < cv.nv) {
-                #ifndef SFH_PACKED_F32X2
-                const F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]); // keeps the default build at 96 registers
-#else
-                const F3 pw = xform(B.R, B.t, cv.x[i], cv.y[i], cv.z[i]);
-#endif
+                const F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
                 s_v[i] = make_float4(pw.x, pw.y, pw.z, 0.f);
             }
         }
-        __syncthreads();
+        __syncwarp();
 
-        {
-            const uint32_t nf = cv.nf;
-            const bool vA = tid < nf, vB = tid + SFH_BLOCK < nf;
-            const uint32_t fA = vA ? cv.faces[tid] : 0u, fB = vB ? cv.faces[tid + SFH_BLOCK] : 0u;
+        const uint32_t nf = cv.nf;
+#pragma unroll 1
+        for (uint32_t base = 0; base < nf; base += 64u) { // faces base+lane and base+lane+32 side by side
+            const uint32_t iA = base + lane, iB = iA + 32u;
+            const bool vA = iA < nf, vB = iB < nf;
+            const uint32_t fA = vA ? cv.faces[iA] : 0u, fB = vB ? cv.faces[iB] : 0u;
             // byte k of the packed face word -> vertex slot (PRMT) -> float4 in s_v (LEA)
             const float4 a1 = s_v[__byte_perm(fA, 0, 0x4440)], a2 = s_v[__byte_perm(fA, 0, 0x4441)], a3 = s_v[__byte_perm(fA, 0, 0x4442)];
             const float4 b1 = s_v[__byte_perm(fB, 0, 0x4440)], b2 = s_v[__byte_perm(fB, 0, 0x4441)], b3 = s_v[__byte_perm(fB, 0, 0x4442)];
@@ -298,11 +346,11 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
             }
             if (DEBUG) {
                 const uint32_t* of = s_body.orig_face + (size_t)(it.w - it.b_begin) * SFH_CH_FACES;
-                if (vA) P.codes[P.code_base[it.b] + of[tid]] = (uint8_t)(7u | (dA ? SFH_FACE_DEGENERATE : 0u) | (code & 255u));
-                if (vB) P.codes[P.code_base[it.b] + of[tid + SFH_BLOCK]] = (uint8_t)(7u | (dB ? SFH_FACE_DEGENERATE : 0u) | (code >> 8));
+                if (vA) P.codes[P.code_base[it.b] + of[iA]] = (uint8_t)(7u | (dA ? SFH_FACE_DEGENERATE : 0u) | (code & 255u));
+                if (vB) P.codes[P.code_base[it.b] + of[iB]] = (uint8_t)(7u | (dB ? SFH_FACE_DEGENERATE : 0u) | (code >> 8));
             }
         }
-        if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); since_spill = 0; }
+        if (++since_spill == SFH_SPILL_EVERY) spill(); // 8 faces per lane per chunk: the 10-bit fields stay below 1023
 
         if (++it.w >= it.w1) break;
         it.s ^= 1;
@@ -312,12 +360,13 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_submerged(StepParams P)
             flush(it.b);
             do { ++it.b; it.b_end = P.item_off[it.b + 1]; } while (it.w >= it.b_end);
             it.b_begin = P.item_off[it.b];
-            load_body(&s_body, P.bodies + it.b);
-            __syncthreads();
+            __syncwarp();
+            warp_load_body(&s_body, P.bodies + it.b, lane);
             fetch_regs();
         }
     }
     flush(it.b);
 }
+
 
 } // namespace sfh
