@@ -88,6 +88,21 @@ int sfh_mesh_get_stats(sfh_ctx* ctx, uint32_t mesh_id, sfh_mesh_stats* out);
  * the field changes. The copy is ordered before the next step on the context's stream. */
 int sfh_waves_upload(sfh_ctx* ctx, const sfh_waves* waves);
 
+/* Wave-field PRODUCER on the device: what OpenGLOcean::InitializeSimulation / Simulate do with fragment
+ * shaders and OpenGLRealOcean::Simulate reads back through a PBO (OpenGLOcean.cpp:414-534,857-1047, OpenGLRealOcean.cpp:333-356;
+ * shaders oceanInit.frag, oceanFFTX.frag, oceanFFTY.frag), so headless / batched runs have waves without OpenGL.
+ *   sfh_wavegen_init      GenerateWavesSpectrum + ComputeButterflyLookupTable for `params` (host, once), uploaded the way
+ *                         the reference's GL_RGBA16F textures store them (half precision, round to nearest even)
+ *   sfh_wavegen_simulate  the h(k,t) pass and the 2 x passes FFT passes at time t (the reference advances t by dt per rendered
+ *                         frame, OpenGLOcean.cpp:476-477; here the caller owns the clock). The result REPLACES the context's
+ *                         wave field exactly as sfh_waves_upload of that fftData would; asynchronous on the context's stream.
+ *   sfh_wavegen_download  fftData [4][N][N][4] floats (layer 3 zero) to the host = the PBO read-back; synchronises
+ *   sfh_wavegen_get_spectrum  spectrum12 / spectrum34 (N*N*4 floats each) as generated, before half storage */
+int sfh_wavegen_init(sfh_ctx* ctx, const sfh_wave_params* params);
+int sfh_wavegen_simulate(sfh_ctx* ctx, float t);
+int sfh_wavegen_download(sfh_ctx* ctx, float* fft_data, size_t n_floats);
+int sfh_wavegen_get_spectrum(sfh_ctx* ctx, float* spectrum12, float* spectrum34, size_t n_floats_each);
+
 /* One recompute of the hydrodynamic forces of n_bodies bodies:
  * replaces the `for each overlapping pair: ocean->ApplyFluidForces(...)` loop
  * (SimulationManager.cpp:1625-1651) up to, not including, ApplyHydrodynamicForces.

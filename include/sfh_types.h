@@ -94,6 +94,20 @@ typedef struct sfh_waves {
     size_t n_floats;      /* floats readable at `data`; texels beyond it read as 0 */
 } sfh_waves;
 
+/* Parameters of the wave-field producer: OceanParams as OpenGLOcean / OpenGLRealOcean set them
+ * (Library/src/graphics/OpenGLOcean.cpp:62-72, OpenGLRealOcean.cpp:41-45). */
+typedef struct sfh_wave_params {
+    float wind;          /* U10 [m/s]: OpenGLRealOcean: state * 5.f + 2.f                       */
+    float omega;         /* inverse wave age: 5.f * expf(-state) + 0.2f                         */
+    float A;             /* spectrum amplitude factor (1.f)                                     */
+    float km, cm;        /* 370.f, 0.23f                                                        */
+    uint32_t propagate;  /* 1: one-sided spectrum (kx < 0 removed, rest doubled)                 */
+    uint32_t passes;     /* log2(fftSize): 8                                                    */
+    float grid_sizes[4]; /* 893, 101, 21, 11 [m]                                                */
+    uint32_t reserved;
+    int64_t seed;        /* `static long seed = 1234` of OpenGLOcean::GetSpectrumSample (:1008) */
+} sfh_wave_params;
+
 typedef struct sfh_body_state {
     uint32_t mesh_id;
     uint32_t mode;  /* SFH_POS_* */

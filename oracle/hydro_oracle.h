@@ -97,6 +97,14 @@ void orc_aero(const orc_mesh* mesh, const sfh_atmosphere* atm, const sfh_body_st
 void orc_compound_aero(const orc_mesh* const* part_meshes, const sfh_body_state* parts, const uint32_t* external, uint32_t n_parts,
                        const sfh_atmosphere* atm, const sfh_body_state* compound, int acc_mode, sfh_info* out);
 
+/* N3, the wave-field producer (oracle/wave_oracle.cpp): OpenGLOcean::GenerateWavesSpectrum, ComputeButterflyLookupTable and
+ * Simulate (oceanInit.frag + 16 FFT passes). See the header of wave_oracle.cpp for what "parity" can mean for shader code. */
+float orc_half_round(float x);
+void orc_wave_spectrum(const sfh_wave_params* p, float* spectrum12, float* spectrum34);
+void orc_wave_butterfly(uint32_t size, uint32_t passes, float* table);
+void orc_wave_simulate(const sfh_wave_params* p, const float* spectrum12, const float* spectrum34, const float* butterfly, float t,
+                       int half_storage, float* fft_data);
+
 /* Whole step, scheduled like the reference: one task per body on a pool of n_threads
  * (SimulationManager.cpp:1641-1651, utils/ThreadPool.hpp). meshes[i] is the mesh of body i.
  * Returns wall seconds spent between the first enqueue and waitAll (the PerformanceMonitor bracket,

@@ -26,7 +26,8 @@ class orc_mesh(C.Structure):
 
 
 def build(force: bool = False):
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "hydro_oracle.cpp")):
+    srcs = [os.path.join(HERE, f) for f in ("hydro_oracle.cpp", "wave_oracle.cpp", "hydro_oracle.h")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/3rdparty/LinearMath"):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
@@ -199,3 +200,38 @@ def compound_aero(meshes, part_mesh_idx, parts: np.ndarray, external, atm, compo
     out = np.zeros(1, dtype=INFO_DTYPE)
     L.orc_compound_aero(arr, parts.ctypes.data, ext.ctypes.data, len(ms), C.byref(a), cs.ctypes.data, acc_mode, out.ctypes.data)
     return out[0]
+
+
+class WaveOracle:
+    """OpenGLOcean's wave-field producer through the oracle (oracle/wave_oracle.cpp): spectrum + butterfly table once,
+    then `simulate(t)` = oceanInit.frag + 16 FFT passes -> fftData [4, N, N, 4]."""
+
+    def __init__(self, params: "_abi.sfh_wave_params"):
+        L = lib()
+        if not hasattr(L, "_wave_ready"):
+            P = C.POINTER
+            L.orc_half_round.restype = C.c_float
+            L.orc_half_round.argtypes = [C.c_float]
+            L.orc_wave_spectrum.restype = None
+            L.orc_wave_spectrum.argtypes = [P(_abi.sfh_wave_params), C.c_void_p, C.c_void_p]
+            L.orc_wave_butterfly.restype = None
+            L.orc_wave_butterfly.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+            L.orc_wave_simulate.restype = None
+            L.orc_wave_simulate.argtypes = [P(_abi.sfh_wave_params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+            L._wave_ready = True
+        self.L = L
+        self.params = params
+        self.N = 1 << params.passes
+        self.spectrum12 = np.zeros(self.N * self.N * 4, dtype=np.float32)
+        self.spectrum34 = np.zeros(self.N * self.N * 4, dtype=np.float32)
+        L.orc_wave_spectrum(C.byref(params), self.spectrum12.ctypes.data, self.spectrum34.ctypes.data)
+        self.butterfly = np.zeros(self.N * params.passes * 4, dtype=np.float32)
+        L.orc_wave_butterfly(self.N, params.passes, self.butterfly.ctypes.data)
+
+    def simulate(self, t: float, half_storage: bool = True, spectrum12=None, spectrum34=None) -> np.ndarray:
+        s12 = self.spectrum12 if spectrum12 is None else np.ascontiguousarray(spectrum12, dtype=np.float32)
+        s34 = self.spectrum34 if spectrum34 is None else np.ascontiguousarray(spectrum34, dtype=np.float32)
+        out = np.zeros((4, self.N, self.N, 4), dtype=np.float32)
+        self.L.orc_wave_simulate(C.byref(self.params), s12.ctypes.data, s34.ctypes.data, self.butterfly.ctypes.data, float(t),
+                                 1 if half_storage else 0, out.ctypes.data)
+        return out

@@ -38,6 +38,12 @@ class sfh_waves(C.Structure):
                 ("n_floats", C.c_size_t)]
 
 
+class sfh_wave_params(C.Structure):
+    _fields_ = [("wind", C.c_float), ("omega", C.c_float), ("A", C.c_float), ("km", C.c_float), ("cm", C.c_float),
+                ("propagate", C.c_uint32), ("passes", C.c_uint32), ("grid_sizes", C.c_float * 4), ("reserved", C.c_uint32),
+                ("seed", C.c_int64)]
+
+
 class sfh_body_state(C.Structure):
     _fields_ = [("mesh_id", C.c_uint32), ("mode", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32),
                 ("T_CG", C.c_double * 12), ("T_C", C.c_double * 12), ("v", C.c_double * 3), ("omega", C.c_double * 3),
@@ -96,6 +102,10 @@ PROTOTYPES = {
     "sfh_mesh_release": (C.c_int, [_ctx, C.c_uint32]),
     "sfh_mesh_get_stats": (C.c_int, [_ctx, C.c_uint32, _P(sfh_mesh_stats)]),
     "sfh_waves_upload": (C.c_int, [_ctx, _P(sfh_waves)]),
+    "sfh_wavegen_init": (C.c_int, [_ctx, _P(sfh_wave_params)]),
+    "sfh_wavegen_simulate": (C.c_int, [_ctx, C.c_float]),
+    "sfh_wavegen_download": (C.c_int, [_ctx, C.c_void_p, C.c_size_t]),
+    "sfh_wavegen_get_spectrum": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sfh_step_async": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_sync": (C.c_int, [_ctx]),
     "sfh_step": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),

@@ -12,6 +12,7 @@
 
 #include "sfh_kernels.cuh"
 #include "sfh_selftest.cuh"
+#include "sfh_wavegen.cuh"
 
 using namespace sfh;
 
@@ -63,6 +64,14 @@ struct sfh_ctx {
     PinBuf h_wave;
     WavesDev waves{nullptr, nullptr, 0, 0.f, 0.f};
     bool have_waves = false;
+
+    // wave-field producer (row N3)
+    DevBuf<float4> d_wg_s12, d_wg_s34, d_wg_tmp, d_wg_fft;
+    DevBuf<int2> d_wg_bf_src;
+    DevBuf<float2> d_wg_bf_w;
+    std::vector<float> wg_s12, wg_s34; // fp32 spectrum as generated (before half storage)
+    sfh_wave_params wg_params{};
+    bool wg_ready = false;
 
     // per-step buffers
     DevBuf<sfh_body_state> d_states;
@@ -576,6 +585,8 @@ void sfh_destroy(sfh_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->slabs) cudaFree(s.base);
+    cudaFree(ctx->d_wg_s12.p); cudaFree(ctx->d_wg_s34.p); cudaFree(ctx->d_wg_tmp.p); cudaFree(ctx->d_wg_fft.p);
+    cudaFree(ctx->d_wg_bf_src.p); cudaFree(ctx->d_wg_bf_w.p);
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_wave_rgba.p); cudaFree(ctx->d_wave_ch0.p); cudaFree(ctx->d_wave_ch1.p);
     cudaFree(ctx->d_states.p); cudaFree(ctx->d_info.p); cudaFree(ctx->d_bodies.p); cudaFree(ctx->d_off_sub.p);
     cudaFree(ctx->d_off_surf.p); cudaFree(ctx->d_status.p); cudaFree(ctx->d_part_sub.p); cudaFree(ctx->d_part_surf.p);
@@ -678,6 +689,98 @@ int sfh_waves_upload(sfh_ctx* ctx, const sfh_waves* w)
     ctx->waves.gx = w->grid_sizes[0];
     ctx->waves.gy = w->grid_sizes[1];
     ctx->have_waves = true;
+    return SFH_OK;
+}
+
+int sfh_wavegen_init(sfh_ctx* ctx, const sfh_wave_params* p)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!p) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    if (p->passes < 2 || p->passes > 10) return fail(ctx, SFH_ERR_INVALID, "passes %u outside [2, 10]", p->passes);
+    for (int g = 0; g < 4; ++g)
+        if (!(p->grid_sizes[g] > 0.f)) return fail(ctx, SFH_ERR_INVALID, "grid_sizes[%d] must be positive", g);
+    if (!(p->wind > 0.f) || !(p->omega > 0.f)) return fail(ctx, SFH_ERR_INVALID, "wind and omega must be positive");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)1 << p->passes, NN = N * N;
+    wavegen_spectrum(*p, ctx->wg_s12, ctx->wg_s34);
+    std::vector<int2> bsrc;
+    std::vector<float2> bw;
+    wavegen_butterfly(p->passes, bsrc, bw);
+    std::vector<float> h12(ctx->wg_s12.size()), h34(ctx->wg_s34.size()); // as the GL_RGBA16F textures hold them
+    for (size_t i = 0; i < h12.size(); ++i) { h12[i] = half_storage(ctx->wg_s12[i]); h34[i] = half_storage(ctx->wg_s34[i]); }
+    int rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensure_dev(ctx, ctx->d_wg_s12, NN)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_wg_s34, NN)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_wg_tmp, 3 * NN)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_wg_fft, 4 * NN)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_wg_bf_src, N * p->passes)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_wg_bf_w, N * p->passes)) != SFH_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_wg_s12.p, h12.data(), NN * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_wg_s34.p, h34.data(), NN * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_wg_bf_src.p, bsrc.data(), bsrc.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_wg_bf_w.p, bw.data(), bw.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); // the staging vectors die with this scope
+    ctx->wg_params = *p;
+    ctx->wg_ready = true;
+    return SFH_OK;
+}
+
+int sfh_wavegen_simulate(sfh_ctx* ctx, float t)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!ctx->wg_ready) return fail(ctx, SFH_ERR_STATE, "sfh_wavegen_simulate before sfh_wavegen_init");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const sfh_wave_params& p = ctx->wg_params;
+    const int N = 1 << p.passes;
+    const size_t texels = (size_t)N * N + N + 1;
+    int rc;
+    if (texels > ctx->d_wave_ch0.cap) CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensure_dev(ctx, ctx->d_wave_ch0, texels)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_wave_ch1, texels)) != SFH_OK) return rc;
+    WaveGenDev G;
+    G.s12 = ctx->d_wg_s12.p; G.s34 = ctx->d_wg_s34.p; G.bf_src = ctx->d_wg_bf_src.p; G.bf_w = ctx->d_wg_bf_w.p;
+    G.tmp = ctx->d_wg_tmp.p; G.fft = ctx->d_wg_fft.p; G.N = N; G.passes = (int32_t)p.passes;
+    for (int g = 0; g < 4; ++g) G.inv_grid[g] = (float)(2.f * M_PI * (float)N / p.grid_sizes[g]); // OpenGLOcean.cpp:472-475
+    const dim3 grid((unsigned)N, 3);
+    const size_t smem = (size_t)2 * N * sizeof(float4);
+    k_wave_rows<<<grid, N, smem, ctx->stream>>>(G, t);
+    k_wave_cols<<<grid, N, smem, ctx->stream>>>(G);
+    // the per-face kernels read planar copies of channels 0 and 1 of layer 0 (+ one row and one texel of layer 1)
+    k_waves_planar<<<(unsigned)((texels + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(ctx->d_wg_fft.p),
+                                                                               (uint32_t)(texels * 4), (uint32_t)texels, ctx->d_wave_ch0.p,
+                                                                               ctx->d_wave_ch1.p);
+    CU(ctx, cudaGetLastError());
+    ctx->waves.ch0 = ctx->d_wave_ch0.p;
+    ctx->waves.ch1 = ctx->d_wave_ch1.p;
+    ctx->waves.N = N;
+    ctx->waves.gx = p.grid_sizes[0];
+    ctx->waves.gy = p.grid_sizes[1];
+    ctx->have_waves = true;
+    return SFH_OK;
+}
+
+int sfh_wavegen_download(sfh_ctx* ctx, float* fft_data, size_t n_floats)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!ctx->wg_ready) return fail(ctx, SFH_ERR_STATE, "sfh_wavegen_download before sfh_wavegen_init");
+    if (!fft_data) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = (size_t)1 << ctx->wg_params.passes, all = 4 * N * N * 4;
+    const size_t n = n_floats < all ? n_floats : all;
+    CU(ctx, cudaMemcpyAsync(fft_data, ctx->d_wg_fft.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SFH_OK;
+}
+
+int sfh_wavegen_get_spectrum(sfh_ctx* ctx, float* spectrum12, float* spectrum34, size_t n_floats_each)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!ctx->wg_ready) return fail(ctx, SFH_ERR_STATE, "sfh_wavegen_get_spectrum before sfh_wavegen_init");
+    if (!spectrum12 || !spectrum34) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    const size_t n = n_floats_each < ctx->wg_s12.size() ? n_floats_each : ctx->wg_s12.size();
+    std::memcpy(spectrum12, ctx->wg_s12.data(), n * sizeof(float));
+    std::memcpy(spectrum34, ctx->wg_s34.data(), n * sizeof(float));
     return SFH_OK;
 }
 

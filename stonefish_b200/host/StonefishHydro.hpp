@@ -156,7 +156,9 @@ public:
     void AddVelocityField(VelocityField* field) { currents.emplace_back(field); }
     void EnableCurrents() { currentsEnabled = true; }
     void DisableCurrents() { currentsEnabled = false; }
-    bool hasWaves() const { return fftData != nullptr; }
+    bool hasWaves() const { return fftData != nullptr || generatedWaves; }
+    //! The wave field is the one HydroEngine::SimulateWaves left on the device: no fftData, no read-back, no upload.
+    void useGeneratedWaves(bool on) { generatedWaves = on; }
     //! OpenGLRealOcean::fftData (float[fftSize*fftSize*4*layers]); nullptr = flat sea. Not owned. Call again when the
     //! render thread refreshes it (OpenGLRealOcean.cpp:333-356).
     void setWaveData(const float* data, size_t nFloats, int fftSize = 256, const float gridSizes[4] = nullptr)
@@ -197,7 +199,23 @@ private:
     int fftSize = 256;
     float grid[4] = {893.f, 101.f, 21.f, 11.f}; // OpenGLOcean.cpp:70
     bool wavesDirty = false;
+    bool generatedWaves = false;
 };
+
+//! OceanParams as OpenGLOcean / OpenGLRealOcean set them for a sea state (OpenGLOcean.cpp:62-72, OpenGLRealOcean.cpp:41-45).
+inline sfh_wave_params WaveParamsFromSeaState(float state, int64_t seed = 1234)
+{
+    sfh_wave_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.wind = state * 5.f + 2.f;
+    p.A = 1.f;
+    p.omega = 5.f * expf(-state) + 0.2f;
+    p.km = 370.f; p.cm = 0.23f;
+    p.propagate = 1; p.passes = 8;
+    p.grid_sizes[0] = 893.f; p.grid_sizes[1] = 101.f; p.grid_sizes[2] = 21.f; p.grid_sizes[3] = 11.f;
+    p.seed = seed;
+    return p;
+}
 
 // ------------------------------------------------------------------------------------------------ atmosphere
 //! What the aerodynamic integrator reads from sf::Atmosphere (Atmosphere.cpp:72-75,117-157): the gas density and the
@@ -328,6 +346,14 @@ public:
         Check(sfh_aero_step(ctx, &atmosphere, states.data(), (uint32_t)states.size(), infos.data()), "sfh_aero_step");
         for (size_t i = 0; i < bodies.size(); ++i) { bodies[i]->Fda = Get(infos[i].Fdq); bodies[i]->Tda = Get(infos[i].Tdq); }
     }
+
+    //! Wave-field producer on the device (OpenGLOcean::InitializeSimulation / Simulate without OpenGL): InitWaves once,
+    //! SimulateWaves(t) whenever the sea should advance (the reference does it once per rendered frame with t += dt,
+    //! OpenGLOcean.cpp:476-477). Pair with Ocean::useGeneratedWaves(true).
+    void InitWaves(const sfh_wave_params& p) { Check(sfh_wavegen_init(ctx, &p), "sfh_wavegen_init"); }
+    void SimulateWaves(float t) { Check(sfh_wavegen_simulate(ctx, t), "sfh_wavegen_simulate"); }
+    //! = the PBO read-back of OpenGLRealOcean::Simulate (OpenGLRealOcean.cpp:333-356): fftData, 4*N*N*4 floats
+    void DownloadWaves(float* fftData, size_t nFloats) { Check(sfh_wavegen_download(ctx, fftData, nFloats), "sfh_wavegen_download"); }
 
     //! Batched Ocean::GetDepth(glm::vec3) / Ocean::GetFluidVelocity(glm::vec3) (Ocean.cpp:149-168, 198-201).
     void GetDepth(Ocean& ocn, const float* xyz, size_t n, float* depth)

@@ -3,7 +3,7 @@
 //   print "Hydrodynamics time: <avg> us" like Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:166.
 // The scenario is read from a small binary file written by tests/test_host_mirror_gpu.py (so the same inputs can be
 // pushed through the Python binding and the oracle), results go to a binary file. Needs a CUDA device at run time.
-//   usage: demo_fluid_dynamics scene.bin out.bin [steps [aero_out.bin]]
+//   usage: demo_fluid_dynamics scene.bin out.bin [steps [aero_out.bin [sea_state waves_out.bin]]]
 // With aero_out.bin the same bodies also go through HydroEngine::ComputeAerodynamicForces once: wind = the scene's velocity
 // fields, gas density 1.2, proxy type cycling AUTO/SPHERE/CYLINDER/ELLIPSOID with fdCd as the ellipsoid radii, T_CG2H = T_O.
 #include <chrono>
@@ -111,6 +111,18 @@ int main(int argc, char** argv)
             for (const auto& b : bodies) {
                 const double d[6] = {b.Fda.x, b.Fda.y, b.Fda.z, b.Tda.x, b.Tda.y, b.Tda.z};
                 aout.write(reinterpret_cast<const char*>(d), sizeof(d));
+            }
+        }
+        if (argc > 6) { // waves produced on the device (InitWaves / SimulateWaves), then the same hydrodynamic step on them
+            engine.InitWaves(sfb::WaveParamsFromSeaState((float)std::atof(argv[5])));
+            engine.SimulateWaves(1.5f);
+            ocean.useGeneratedWaves(true);
+            engine.ComputeHydrodynamicForces(settings, ocean, ptrs);
+            std::ofstream wout(argv[6], std::ios::binary);
+            for (const auto& b : bodies) {
+                const sfb::HydrodynamicsInfo& r = b.info;
+                const double d[8] = {r.Fb.x, r.Fb.y, r.Fb.z, r.Tb.x, r.Tb.y, r.Tb.z, r.Swet, r.Vsub};
+                wout.write(reinterpret_cast<const char*>(d), sizeof(d));
             }
         }
     } catch (const std::exception& e) {

@@ -128,6 +128,7 @@ class Ocean:
         self.fft_size = 256
         self.grid_sizes = (893.0, 101.0, 21.0, 11.0)  # OpenGLOcean.cpp:70
         self.waves_version = 0  # process-unique token of the current wave field (0 = none)
+        self.generated_waves = False  # wave field produced on the device by HydroContext.wavegen_simulate
 
     def AddVelocityField(self, field: VelocityField):
         self.currents.append(field)
@@ -149,8 +150,12 @@ class Ocean:
         Ocean._wave_token += 1
         self.waves_version = Ocean._wave_token
 
+    def useGeneratedWaves(self, on: bool = True):
+        """The wave field is the one HydroContext.wavegen_simulate left on the device (no fftData upload)."""
+        self.generated_waves = bool(on)
+
     def hasWaves(self) -> bool:
-        return self.fft_data is not None
+        return self.fft_data is not None or self.generated_waves
 
     def to_struct(self) -> _abi.sfh_ocean:
         o = _abi.sfh_ocean()
@@ -211,6 +216,30 @@ def aero_proxy(approx_type: int, params=()):
         cd = np.array([1.0 / float(params[0]), 1.0 / float(params[1]), 1.0 / float(params[2])])
         return cd * (1.0 / max(max(cd[0], cd[1]), cd[2])), SFH_F_AERO_CD
     return np.zeros(3), 0
+
+
+def _libm_expf(x: float) -> float:
+    """The C library's expf, so that parameters derived here equal the ones the C++ mirror derives (numpy's float32 exp is a
+    different implementation and may differ in the last bit)."""
+    import ctypes.util
+
+    m = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    m.expf.restype, m.expf.argtypes = C.c_float, [C.c_float]
+    return float(m.expf(x))
+
+
+def wave_params(sea_state: float, seed: int = 1234) -> _abi.sfh_wave_params:
+    """OceanParams as OpenGLOcean / OpenGLRealOcean set them for a sea state (OpenGLOcean.cpp:62-72,
+    OpenGLRealOcean.cpp:41-45), in the reference's float arithmetic."""
+    f = np.float32
+    p = _abi.sfh_wave_params()
+    p.wind = float(f(sea_state) * f(5.0) + f(2.0))
+    p.omega = float(f(5.0) * f(_libm_expf(-float(f(sea_state)))) + f(0.2))
+    p.A, p.km, p.cm = 1.0, 370.0, 0.23
+    p.propagate, p.passes = 1, 8
+    p.grid_sizes[:] = [893.0, 101.0, 21.0, 11.0]
+    p.seed = seed
+    return p
 
 
 class Mesh:
@@ -342,10 +371,32 @@ class HydroContext:
 
     # -- per step
     def _sync_waves(self, ocean: Ocean):
-        if ocean.hasWaves() and self._waves_version != ocean.waves_version:
+        if ocean.hasWaves() and not ocean.generated_waves and self._waves_version != ocean.waves_version:
             w = ocean.waves_struct()
             self._check(self.lib.sfh_waves_upload(self.ctx, C.byref(w)), "sfh_waves_upload")
             self._waves_version = ocean.waves_version
+
+    # --- wave-field producer (row N3): OpenGLOcean::InitializeSimulation / Simulate on the device
+    def wavegen_init(self, params: _abi.sfh_wave_params):
+        self._check(self.lib.sfh_wavegen_init(self.ctx, C.byref(params)), "sfh_wavegen_init")
+        self._wavegen_n = 1 << params.passes
+
+    def wavegen_simulate(self, t: float):
+        """h(k,t) + FFT at time t; the result becomes the context's wave field (as if its fftData had been uploaded)."""
+        self._check(self.lib.sfh_wavegen_simulate(self.ctx, float(t)), "sfh_wavegen_simulate")
+        self._waves_version = -1  # an uploaded field, if any, is no longer resident
+
+    def wavegen_download(self) -> np.ndarray:
+        n = self._wavegen_n
+        out = np.zeros((4, n, n, 4), dtype=np.float32)
+        self._check(self.lib.sfh_wavegen_download(self.ctx, out.ctypes.data, out.size), "sfh_wavegen_download")
+        return out
+
+    def wavegen_spectrum(self):
+        n = self._wavegen_n
+        s12, s34 = np.zeros(n * n * 4, dtype=np.float32), np.zeros(n * n * 4, dtype=np.float32)
+        self._check(self.lib.sfh_wavegen_get_spectrum(self.ctx, s12.ctypes.data, s34.ctypes.data, s12.size), "sfh_wavegen_get_spectrum")
+        return s12, s34
 
     def compute(self, ocean: Ocean, states: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """One recompute of all bodies: host buffers in, host buffers out (sfh_step)."""

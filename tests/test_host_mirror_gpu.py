@@ -106,3 +106,29 @@ def test_cpp_host_mirror_aerodynamics(tmp_path, oracle):
     err, where = max_rel_err(got, ref)
     assert err <= REL_TOL, (err, where)
     assert np.linalg.norm(ref["Fdq"], axis=1).min() > 0
+
+
+def test_cpp_host_mirror_generated_waves(tmp_path, ctx):
+    """sfb::HydroEngine::InitWaves / SimulateWaves + Ocean::useGeneratedWaves in C++ give the step the Python mirror gives
+    on the same generated field (same library underneath: bitwise)."""
+    from stonefish_b200.hydro import wave_params
+
+    assert os.path.exists(DEMO), "build the host mirror demo first (make -C stonefish_b200/host)"
+    sc = scenes.config1()
+    scene = str(tmp_path / "scene.bin")
+    outs = [str(tmp_path / n) for n in ("out.bin", "aero.bin", "waves.bin")]
+    write_scene(scene, sc)
+    subprocess.check_output([DEMO, scene, outs[0], "2", outs[1], "1.0", outs[2]], text=True)  # sea state 1: decimetre waves
+    raw = np.fromfile(outs[2], dtype=np.float64).reshape(sc.n_bodies, 8)
+    ctx.wavegen_init(wave_params(1.0))
+    ctx.wavegen_simulate(1.5)
+    sc.ocean.useGeneratedWaves(True)
+    st = sc.bind(ctx)
+    st["mode"] = 3  # SFH_POS_AUTO, flags as HydroEngine::ComputeHydrodynamicForces sets them
+    st["flags"] = (st["flags"] & 4) | 8 | 1 | 2
+    got = ctx.compute(sc.ocean, st)
+    crossing = got["position"] == 2
+    assert crossing.any()
+    assert np.array_equal(raw[crossing, 0:3], got["Fb"][crossing]) and np.array_equal(raw[crossing, 6], got["Swet"][crossing])
+    flat = read_results(outs[0], sc.n_bodies)
+    assert not np.array_equal(flat["Fb"][crossing], got["Fb"][crossing])  # the waves changed the answer
