@@ -138,6 +138,14 @@ int sfh_aero_step_debug(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_
 int sfh_aero_step_device(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_state* d_states, uint32_t n_bodies,
                          sfh_info* d_out);
 
+/* Cables (row N4): CableEntity::ComputeHydrodynamicForces (CableEntity.cpp:239-372, called from the same
+ * Ocean::ApplyFluidForces loop, Ocean.cpp:257-266) for n_cables cables whose nodes lie in node_pos / node_vel (3 doubles per
+ * node, n_nodes_total nodes; host buffers). Writes one sfh_node_forces per node (nodes not covered by a cable: zeros);
+ * ApplyHydrodynamicForces (:374-381) stays on the host. fp64 throughout like the reference; the circular-segment geometry uses
+ * atan/cos/sin/acos, whose last bit differs between CUDA and glibc: parity is 1e-12 relative, not bit-exact. Synchronous. */
+int sfh_cable_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_cable* cables, uint32_t n_cables, const double* node_pos,
+                   const double* node_vel, uint32_t n_nodes_total, sfh_node_forces* out);
+
 /* Batched point queries with the same arithmetic as the per-face kernels (host buffers, synchronous):
  *   sfh_query_depth          = Ocean::GetDepth(const glm::vec3&)          (Ocean.cpp:149-168), n points -> n floats
  *   sfh_query_fluid_velocity = Ocean::GetFluidVelocity(const glm::vec3&)  (Ocean.cpp:198-201), n points -> 3n floats

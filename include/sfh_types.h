@@ -126,6 +126,21 @@ typedef struct sfh_body_state {
     double P_CB[3];      /* centre of buoyancy in the CG frame                              */
 } sfh_body_state;
 
+/* Cables: what CableEntity::ComputeHydrodynamicForces reads (Library/src/entities/CableEntity.cpp:239-372).
+ * A cable is a run of consecutive nodes in the step's node arrays (btSoftBody::m_nodes[i].m_x / m_v). */
+typedef struct sfh_cable {
+    uint32_t first_node; /* index of node 0 of this cable in the node arrays                                  */
+    uint32_t n_nodes;    /* >= 2                                                                               */
+    uint32_t flags;      /* SFH_F_DAMPING / SFH_F_BUOYANCY = settings, SFH_F_BUOYANT = phy_.buoyancy           */
+    uint32_t reserved;
+    double radius;       /* radius_                                                                            */
+} sfh_cable;
+
+/* CableEntity::NodalForces (CableEntity.h:42-55), one per node */
+typedef struct sfh_node_forces {
+    double Fb[3], Fdq[3], Fdf[3];
+} sfh_node_forces;
+
 typedef struct sfh_info {
     double Fb[3], Tb[3], Fdq[3], Tdq[3], Fdf[3], Tdf[3];
     double Swet, Vsub;

@@ -17,6 +17,9 @@
 #include "LinearMath/btTransform.h"
 #include "LinearMath/btVector3.h"
 
+#include <algorithm>
+#include <vector>
+
 typedef btScalar Scalar;
 typedef btVector3 Vector3;
 typedef btMatrix3x3 Matrix3;
@@ -174,6 +177,125 @@ void btc_ellipsoid_cd(const double params[3], double cd_out[3])
     Scalar maxCd = btMax(btMax(Cd.x(), Cd.y()), Cd.z());
     Cd /= maxCd;
     for (int k = 0; k < 3; ++k) cd_out[k] = Cd[k];
+}
+
+/* CableEntity.cpp:217-372 with the real btVector3 / btScalar helpers, flat sea (Ocean::GetDepth(Vector3) narrows to float,
+ * Ocean.cpp:149-173). flags: SFH_F_DAMPING, SFH_F_BUOYANCY (settings), SFH_F_BUOYANT (phy_.buoyancy). */
+static Scalar btc_circularSegmentArea(Scalar radius_, Scalar h)
+{
+    if (h <= Scalar(0))
+        return Scalar(0);
+    else if (h >= Scalar(2) * radius_)
+        return Scalar(M_PI) * radius_ * radius_;
+    else {
+        if (h > radius_) {
+            h = Scalar(2) * radius_ - h;
+            Scalar theta = Scalar(2) * btAcos((radius_ - h) / radius_);
+            return radius_ * radius_ * (Scalar(M_PI) - (theta - btSin(theta)) / Scalar(2));
+        } else {
+            Scalar theta = Scalar(2) * btAcos((radius_ - h) / radius_);
+            return (radius_ * radius_ / Scalar(2)) * (theta - btSin(theta));
+        }
+    }
+}
+
+void btc_cable(const sfh_ocean* ocn, uint32_t n_nodes, double radius_, uint32_t flags, const double* pos, const double* vel, double* out9)
+{
+    struct NodalForces { Vector3 Fb, Fdq, Fdf; };
+    std::vector<NodalForces> nodalForces_(n_nodes);
+    for (size_t i = 0; i < nodalForces_.size(); ++i) { nodalForces_[i].Fb.setZero(); nodalForces_[i].Fdq.setZero(); nodalForces_[i].Fdf.setZero(); }
+    auto GetDepth = [](const Vector3& point) { return Scalar((float)point.getZ()); };
+    const Vector3 gravity(0, 0, ocn->gravity_z);
+    const bool buoyancy = (flags & SFH_F_BUOYANT) != 0, reallisticBuoyancy = (flags & SFH_F_BUOYANCY) != 0, dampingForces = (flags & SFH_F_DAMPING) != 0;
+
+    for (size_t i = 0; i < n_nodes - 1; ++i) {
+        Vector3 p1(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        Vector3 p2(pos[3 * i + 3], pos[3 * i + 4], pos[3 * i + 5]);
+        Scalar d1 = GetDepth(p1);
+        Scalar d2 = GetDepth(p2);
+        if (d1 > d2) {
+            std::swap(p1, p2);
+            std::swap(d1, d2);
+        }
+        Scalar dz = d2 - d1;
+        Scalar dxy = Vector3(p2.getX() - p1.getX(), p2.getY() - p1.getY(), 0.0).safeNorm();
+        Vector3 segmentVec = p2 - p1;
+        Scalar segmentLength = segmentVec.length();
+        Scalar alpha = btAtan(dz / dxy);
+        Scalar margin = btFuzzyZero(dxy) ? Scalar(0) : radius_ * btCos(alpha);
+        Scalar submergedV{0};
+        if (d2 < -margin) {
+            continue;
+        } else if (d1 > margin) {
+            submergedV = Scalar(M_PI) * radius_ * radius_ * segmentLength;
+        } else {
+            if (btFuzzyZero(dxy)) {
+                Scalar submergedL = btMin(d2, dz);
+                submergedV = Scalar(M_PI) * radius_ * radius_ * submergedL;
+            } else if (btFuzzyZero(dz)) {
+                Scalar submergedA = btc_circularSegmentArea(radius_, d1 + radius_);
+                submergedV = submergedA * segmentLength;
+            } else if (btFabs(d1) <= margin && btFabs(d2) <= margin) {
+                Scalar A1 = btc_circularSegmentArea(radius_, d1 / btCos(alpha) + radius_);
+                Scalar A2 = btc_circularSegmentArea(radius_, d2 / btCos(alpha) + radius_);
+                submergedV = (A1 + A2) / Scalar(2) * segmentLength;
+            } else if (d1 < -margin && d2 > margin) {
+                Scalar l1 = (d2 - radius_ * btCos(alpha)) / btSin(alpha);
+                Scalar l2 = Scalar(2) * radius_ * btCos(alpha);
+                submergedV = Scalar(M_PI) * radius_ * radius_ * (l1 + l2 / Scalar(2));
+            } else if (d2 <= margin) {
+                Scalar a = radius_ + d2 / btCos(alpha);
+                Scalar l = a / btSin(alpha);
+                submergedV = btc_circularSegmentArea(radius_, a) * l / Scalar(2);
+            } else if (d1 >= -margin) {
+                Scalar a = radius_ - d1 / btCos(alpha);
+                Scalar l = a / btSin(alpha);
+                submergedV = Scalar(M_PI) * radius_ * radius_ * segmentLength - btc_circularSegmentArea(radius_, a) * l / Scalar(2);
+            }
+        }
+        if (buoyancy && reallisticBuoyancy) {
+            Vector3 b = -submergedV * ocn->density * gravity;
+            nodalForces_[i].Fb += b / Scalar(2);
+            nodalForces_[i + 1].Fb += b / Scalar(2);
+        }
+        if (dampingForces && submergedV > Scalar(0)) {
+            Vector3 p = (p1 + p2) / Scalar(2);
+            Vector3 v1(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+            Vector3 v2(vel[3 * i + 3], vel[3 * i + 4], vel[3 * i + 5]);
+            Vector3 v = (v1 + v2) / Scalar(2);
+            double pp[3] = {p.x(), p.y(), p.z()}, wv[3];
+            btc_fluid_velocity(ocn, pp, wv);
+            Vector3 waterV(wv[0], wv[1], wv[2]);
+            Vector3 relV = v - waterV;
+            const Scalar Cd{0.5};
+            Scalar f1 = btFabs(segmentVec.dot(relV));
+            Scalar f2 = submergedV / (Scalar(M_PI) * radius_ * radius_ * segmentLength);
+            {
+                Scalar S = Scalar(2) * radius_ * segmentLength;
+                Vector3 Fdq = -(Scalar(1) - f1) * f2 * Scalar(0.5) * ocn->density * Scalar(Cd) * S * relV.length() * relV;
+                nodalForces_[i].Fdq += Fdq / Scalar(2);
+                nodalForces_[i + 1].Fdq += Fdq / Scalar(2);
+            }
+            {
+                Scalar S = f2 * (Scalar(2 * M_PI) * radius_ * segmentLength);
+                Vector3 Fdf = -S * relV;
+                nodalForces_[i].Fdf += Fdf / Scalar(2);
+                nodalForces_[i + 1].Fdf += Fdf / Scalar(2);
+            }
+        }
+    }
+    nodalForces_[0].Fb *= Scalar(2);
+    nodalForces_[n_nodes - 1].Fb *= Scalar(2);
+    nodalForces_[0].Fdq *= Scalar(2);
+    nodalForces_[n_nodes - 1].Fdq *= Scalar(2);
+    nodalForces_[0].Fdf *= Scalar(2);
+    nodalForces_[n_nodes - 1].Fdf *= Scalar(2);
+    for (uint32_t i = 0; i < n_nodes; ++i)
+        for (int k = 0; k < 3; ++k) {
+            out9[9 * i + k] = nodalForces_[i].Fb[k];
+            out9[9 * i + 3 + k] = nodalForces_[i].Fdq[k];
+            out9[9 * i + 6 + k] = nodalForces_[i].Fdf[k];
+        }
 }
 
 /* OpenGLDataStructs.cpp:148-156: getOpenGLMatrix then (GLfloat) per element */

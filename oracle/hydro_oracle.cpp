@@ -995,4 +995,128 @@ int orc_selftest_unfused(void)
     return r == 0.0f;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * N4: cables. fp64 with Bullet's operator order (btVector3.h), libm transcendentals as btAtan/btCos/btSin/btAcos are.
+ */
+double orc_circular_segment_area(double radius_, double h) /* CableEntity.cpp:217-237 */
+{
+    if (h <= 0.0)
+        return 0.0;
+    else if (h >= 2.0 * radius_)
+        return M_PI * radius_ * radius_;
+    else {
+        if (h > radius_) {
+            h = 2.0 * radius_ - h;
+            double theta = 2.0 * std::acos((radius_ - h) / radius_);
+            return radius_ * radius_ * (M_PI - (theta - std::sin(theta)) / 2.0);
+        } else {
+            double theta = 2.0 * std::acos((radius_ - h) / radius_);
+            return (radius_ * radius_ / 2.0) * (theta - std::sin(theta));
+        }
+    }
+}
+
+void orc_cable(const sfh_ocean* o, const sfh_waves* w, const sfh_cable* cable, const double* pos, const double* vel,
+               sfh_node_forces* out)
+{
+    const uint32_t n = cable->n_nodes;
+    const double radius_ = cable->radius;
+    const bool buoyancy = (cable->flags & SFH_F_BUOYANT) && (cable->flags & SFH_F_BUOYANCY);
+    const bool damping = (cable->flags & SFH_F_DAMPING) != 0;
+    const double EPS = 2.2204460492503131e-16; /* SIMD_EPSILON = DBL_EPSILON (btScalar.h:536) */
+    auto fuzzy_zero = [&](double x) { return std::fabs(x) < EPS; };
+    auto add_half = [](double* acc, D3 F) { /* nodalForces_[k].X += F / Scalar(2): operator/ multiplies by 1/s (btVector3.h:853-858) */
+        D3 hF = F * (1.0 / 2.0);
+        acc[0] += hF.x; acc[1] += hF.y; acc[2] += hF.z;
+    };
+    std::memset(out, 0, sizeof(sfh_node_forces) * n); /* :244-245 clearForces */
+
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+        D3 p1{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+        D3 p2{pos[3 * i + 3], pos[3 * i + 4], pos[3 * i + 5]};
+        double pp1[3] = {p1.x, p1.y, p1.z}, pp2[3] = {p2.x, p2.y, p2.z};
+        double d1 = orc_get_depth_d(o, w, pp1);
+        double d2 = orc_get_depth_d(o, w, pp2);
+        if (d1 > d2) { /* the shallower point first */
+            std::swap(p1, p2);
+            std::swap(d1, d2);
+        }
+        double dz = d2 - d1;
+        D3 hv{p2.x - p1.x, p2.y - p1.y, 0.0};
+        double hl2 = ddot(hv, hv);
+        double dxy = hl2 > EPS ? std::sqrt(hl2) : 0.0; /* btVector3::safeNorm (btVector3.h:269-276) */
+        D3 segmentVec = p2 - p1;
+        double segmentLength = dnorm(segmentVec);
+        double alpha = std::atan(dz / dxy);
+        double margin = fuzzy_zero(dxy) ? 0.0 : radius_ * std::cos(alpha);
+
+        double submergedV = 0.0;
+        if (d2 < -margin) {
+            continue;
+        } else if (d1 > margin) {
+            submergedV = M_PI * radius_ * radius_ * segmentLength;
+        } else {
+            if (fuzzy_zero(dxy)) {
+                double submergedL = std::min(d2, dz);
+                submergedV = M_PI * radius_ * radius_ * submergedL;
+            } else if (fuzzy_zero(dz)) {
+                double submergedA = orc_circular_segment_area(radius_, d1 + radius_);
+                submergedV = submergedA * segmentLength;
+            } else if (std::fabs(d1) <= margin && std::fabs(d2) <= margin) {
+                double A1 = orc_circular_segment_area(radius_, d1 / std::cos(alpha) + radius_);
+                double A2 = orc_circular_segment_area(radius_, d2 / std::cos(alpha) + radius_);
+                submergedV = (A1 + A2) / 2.0 * segmentLength;
+            } else if (d1 < -margin && d2 > margin) {
+                double l1 = (d2 - radius_ * std::cos(alpha)) / std::sin(alpha);
+                double l2 = 2.0 * radius_ * std::cos(alpha);
+                submergedV = M_PI * radius_ * radius_ * (l1 + l2 / 2.0);
+            } else if (d2 <= margin) {
+                double a = radius_ + d2 / std::cos(alpha);
+                double l = a / std::sin(alpha);
+                submergedV = orc_circular_segment_area(radius_, a) * l / 2.0;
+            } else if (d1 >= -margin) {
+                double a = radius_ - d1 / std::cos(alpha);
+                double l = a / std::sin(alpha);
+                submergedV = M_PI * radius_ * radius_ * segmentLength - orc_circular_segment_area(radius_, a) * l / 2.0;
+            }
+        }
+
+        if (buoyancy) { /* :319-326 */
+            D3 gravity{0.0, 0.0, o->gravity_z};
+            D3 b = -submergedV * o->density * gravity;
+            add_half(out[i].Fb, b);
+            add_half(out[i + 1].Fb, b);
+        }
+        if (damping && submergedV > 0.0) { /* :329-359 */
+            D3 p = (p1 + p2) * (1.0 / 2.0);
+            D3 v1{vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]}, v2{vel[3 * i + 3], vel[3 * i + 4], vel[3 * i + 5]};
+            D3 v = (v1 + v2) * (1.0 / 2.0);
+            double pp[3] = {p.x, p.y, p.z}, wv[3];
+            orc_fluid_velocity_d(o, pp, wv);
+            D3 relV = v - D3{wv[0], wv[1], wv[2]};
+            const double Cd = 0.5;
+            double f1 = std::fabs(ddot(segmentVec, relV));
+            double f2 = submergedV / (M_PI * radius_ * radius_ * segmentLength);
+            {
+                double S = 2.0 * radius_ * segmentLength;
+                D3 Fdq = -(1.0 - f1) * f2 * 0.5 * o->density * Cd * S * dnorm(relV) * relV;
+                add_half(out[i].Fdq, Fdq);
+                add_half(out[i + 1].Fdq, Fdq);
+            }
+            {
+                double S = f2 * ((2 * M_PI) * radius_ * segmentLength);
+                D3 Fdf = -S * relV;
+                add_half(out[i].Fdf, Fdf);
+                add_half(out[i + 1].Fdf, Fdf);
+            }
+        }
+    }
+    /* :363-371: end nodes carry one segment only */
+    for (int c = 0; c < 3; ++c) {
+        out[0].Fb[c] *= 2.0; out[n - 1].Fb[c] *= 2.0;
+        out[0].Fdq[c] *= 2.0; out[n - 1].Fdq[c] *= 2.0;
+        out[0].Fdf[c] *= 2.0; out[n - 1].Fdf[c] *= 2.0;
+    }
+}
+
 } // extern "C"

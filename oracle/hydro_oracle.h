@@ -105,6 +105,12 @@ void orc_wave_butterfly(uint32_t size, uint32_t passes, float* table);
 void orc_wave_simulate(const sfh_wave_params* p, const float* spectrum12, const float* spectrum34, const float* butterfly, float t,
                        int half_storage, float* fft_data);
 
+/* N4: CableEntity::ComputeHydrodynamicForces (CableEntity.cpp:239-372) for one cable; pos/vel = that cable's nodes
+ * (3 doubles each), out = n_nodes records. circularSegmentArea: CableEntity.cpp:217-237. */
+void orc_cable(const sfh_ocean* o, const sfh_waves* w, const sfh_cable* cable, const double* pos, const double* vel,
+               sfh_node_forces* out);
+double orc_circular_segment_area(double radius, double h);
+
 /* Whole step, scheduled like the reference: one task per body on a pool of n_threads
  * (SimulationManager.cpp:1641-1651, utils/ThreadPool.hpp). meshes[i] is the mesh of body i.
  * Returns wall seconds spent between the first enqueue and waitAll (the PerformanceMonitor bracket,

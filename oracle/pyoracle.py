@@ -235,3 +235,23 @@ class WaveOracle:
         self.L.orc_wave_simulate(C.byref(self.params), s12.ctypes.data, s34.ctypes.data, self.butterfly.ctypes.data, float(t),
                                  1 if half_storage else 0, out.ctypes.data)
         return out
+
+
+def cable(ocean: Ocean, radius: float, flags: int, pos: np.ndarray, vel: np.ndarray) -> np.ndarray:
+    """CableEntity::ComputeHydrodynamicForces for one cable through the oracle (orc_cable): (n_nodes, 9) = Fb, Fdq, Fdf."""
+    L = lib()
+    if not hasattr(L, "_cable_ready"):
+        L.orc_cable.restype = None
+        L.orc_cable.argtypes = [C.POINTER(_abi.sfh_ocean), C.POINTER(_abi.sfh_waves), C.POINTER(_abi.sfh_cable), C.c_void_p, C.c_void_p,
+                                C.c_void_p]
+        L.orc_circular_segment_area.restype = C.c_double
+        L.orc_circular_segment_area.argtypes = [C.c_double, C.c_double]
+        L._cable_ready = True
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+    vel = np.ascontiguousarray(vel, dtype=np.float64).reshape(-1, 3)
+    c = _abi.sfh_cable(0, pos.shape[0], flags, 0, float(radius))
+    o = ocean.to_struct()
+    w = ocean.waves_struct() if ocean.hasWaves() else _abi.sfh_waves()
+    out = np.zeros((pos.shape[0], 9), dtype=np.float64)
+    L.orc_cable(C.byref(o), C.byref(w), C.byref(c), pos.ctypes.data, vel.ctypes.data, out.ctypes.data)
+    return out

@@ -52,6 +52,15 @@ class sfh_body_state(C.Structure):
                 ("P_CB", C.c_double * 3)]
 
 
+class sfh_cable(C.Structure):
+    _fields_ = [("first_node", C.c_uint32), ("n_nodes", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("radius", C.c_double)]
+
+
+class sfh_node_forces(C.Structure):
+    _fields_ = [("Fb", C.c_double * 3), ("Fdq", C.c_double * 3), ("Fdf", C.c_double * 3)]
+
+
 class sfh_info(C.Structure):
     _fields_ = [("Fb", C.c_double * 3), ("Tb", C.c_double * 3), ("Fdq", C.c_double * 3), ("Tdq", C.c_double * 3),
                 ("Fdf", C.c_double * 3), ("Tdf", C.c_double * 3), ("Swet", C.c_double), ("Vsub", C.c_double),
@@ -114,6 +123,7 @@ PROTOTYPES = {
     "sfh_aero_step": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_aero_step_debug": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sfh_aero_step_device": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sfh_cable_step": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_query_depth": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_query_fluid_velocity": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_selftest": (C.c_int, [_ctx, C.c_uint32, C.c_uint64, _P(C.c_uint64), _P(C.c_uint64)]),

@@ -13,6 +13,7 @@
 #include "sfh_kernels.cuh"
 #include "sfh_selftest.cuh"
 #include "sfh_wavegen.cuh"
+#include "sfh_cable.cuh"
 
 using namespace sfh;
 
@@ -64,6 +65,11 @@ struct sfh_ctx {
     PinBuf h_wave;
     WavesDev waves{nullptr, nullptr, 0, 0.f, 0.f};
     bool have_waves = false;
+
+    // cables (row N4)
+    DevBuf<sfh_cable> d_cables;
+    DevBuf<double> d_node_pos, d_node_vel;
+    DevBuf<sfh_node_forces> d_node_out;
 
     // wave-field producer (row N3)
     DevBuf<float4> d_wg_s12, d_wg_s34, d_wg_tmp, d_wg_fft;
@@ -585,6 +591,7 @@ void sfh_destroy(sfh_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->slabs) cudaFree(s.base);
+    cudaFree(ctx->d_cables.p); cudaFree(ctx->d_node_pos.p); cudaFree(ctx->d_node_vel.p); cudaFree(ctx->d_node_out.p);
     cudaFree(ctx->d_wg_s12.p); cudaFree(ctx->d_wg_s34.p); cudaFree(ctx->d_wg_tmp.p); cudaFree(ctx->d_wg_fft.p);
     cudaFree(ctx->d_wg_bf_src.p); cudaFree(ctx->d_wg_bf_w.p);
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_wave_rgba.p); cudaFree(ctx->d_wave_ch0.p); cudaFree(ctx->d_wave_ch1.p);
@@ -892,6 +899,46 @@ int sfh_aero_step_device(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body
     rc = run_step(ctx, &fluid, d_states, n_bodies, d_out, plan);
     if (rc != SFH_OK) return rc;
     ctx->ev_valid = ctx->profiling;
+    return SFH_OK;
+}
+
+int sfh_cable_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_cable* cables, uint32_t n_cables, const double* node_pos,
+                   const double* node_vel, uint32_t n_nodes_total, sfh_node_forces* out)
+{
+    if (!ctx) return SFH_ERR_INVALID;
+    if (!ocean || (n_cables && !cables) || (n_nodes_total && (!node_pos || !node_vel || !out))) return fail(ctx, SFH_ERR_INVALID, "null argument");
+    if (ctx->step_in_flight) { int rc0 = sfh_sync(ctx); if (rc0 != SFH_OK) return rc0; }
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint32_t max_nodes = 0;
+    for (uint32_t i = 0; i < n_cables; ++i) {
+        if (cables[i].n_nodes < 2) return fail(ctx, SFH_ERR_INVALID, "cable %u: needs at least 2 nodes", i);
+        if ((uint64_t)cables[i].first_node + cables[i].n_nodes > n_nodes_total) return fail(ctx, SFH_ERR_INVALID, "cable %u: nodes out of range", i);
+        if (!(cables[i].radius > 0.0)) return fail(ctx, SFH_ERR_INVALID, "cable %u: radius must be positive", i);
+        if (cables[i].n_nodes > max_nodes) max_nodes = cables[i].n_nodes;
+    }
+    if (n_nodes_total == 0) return SFH_OK;
+    int rc;
+    bool general = false;
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); // buffers below may grow; this entry is synchronous anyway
+    if ((rc = stage_ocean(ctx, ocean, &general)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_cables, n_cables ? n_cables : 1)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_node_pos, (size_t)3 * n_nodes_total)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_node_vel, (size_t)3 * n_nodes_total)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_node_out, n_nodes_total)) != SFH_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_cables.p, cables, sizeof(sfh_cable) * n_cables, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_node_pos.p, node_pos, sizeof(double) * 3 * n_nodes_total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->d_node_vel.p, node_vel, sizeof(double) * 3 * n_nodes_total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->d_node_out.p, 0, sizeof(sfh_node_forces) * n_nodes_total, ctx->stream)); // nodes outside every cable
+    if (n_cables) {
+        CableParams cp;
+        cp.cables = ctx->d_cables.p; cp.n_cables = n_cables; cp.pos = ctx->d_node_pos.p; cp.vel = ctx->d_node_vel.p;
+        cp.ocean = ctx->d_ocean.p; cp.waves = ctx->waves; cp.out = ctx->d_node_out.p;
+        const dim3 grid((max_nodes + 127) / 128, n_cables);
+        k_cable_nodes<<<grid, 128, 0, ctx->stream>>>(cp);
+        CU(ctx, cudaGetLastError());
+    }
+    CU(ctx, cudaMemcpyAsync(out, ctx->d_node_out.p, sizeof(sfh_node_forces) * n_nodes_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SFH_OK;
 }
 

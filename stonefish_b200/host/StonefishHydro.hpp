@@ -264,6 +264,16 @@ struct SolidBody {
     Vector3 Fda, Tda;
 };
 
+//! The members CableEntity::ComputeHydrodynamicForces reads (CableEntity.cpp:239-372) and the NodalForces it fills
+//! (CableEntity.h:42-55). nodes / velocities = btSoftBody::m_nodes[i].m_x / m_v.
+struct CableBody {
+    Scalar radius = 0.01;
+    bool buoyancy = true;            // phy_.buoyancy
+    std::vector<Vector3> nodes, velocities;
+    struct NodalForces { Vector3 Fb, Fdq, Fdf; };
+    std::vector<NodalForces> nodalForces;   // output; ApplyHydrodynamicForces adds Fb + Fdf + Fdq to node i (:374-381)
+};
+
 //! One GPU worth of hydrodynamics: replaces the ThreadPool-driven loop of SimulationManager::SimulationTickCallback
 //! (SimulationManager.cpp:1619-1655). Not copyable; one per GPU.
 class HydroEngine {
@@ -345,6 +355,39 @@ public:
         }
         Check(sfh_aero_step(ctx, &atmosphere, states.data(), (uint32_t)states.size(), infos.data()), "sfh_aero_step");
         for (size_t i = 0; i < bodies.size(); ++i) { bodies[i]->Fda = Get(infos[i].Fdq); bodies[i]->Tda = Get(infos[i].Tdq); }
+    }
+
+    //! CableEntity::ComputeHydrodynamicForces for every cable of the batch (the CABLE branch of Ocean::ApplyFluidForces,
+    //! Ocean.cpp:257-266).
+    void ComputeCableForces(const HydrodynamicsSettings& settings, Ocean& ocn, const std::vector<CableBody*>& cables)
+    {
+        sfh_waves w;
+        if (ocn.TakeWavesDirty(w)) Check(sfh_waves_upload(ctx, &w), "sfh_waves_upload");
+        ocn.Fill(ocean);
+        std::vector<sfh_cable> cs(cables.size());
+        std::vector<double> pos, vel;
+        for (size_t i = 0; i < cables.size(); ++i) {
+            const CableBody& c = *cables[i];
+            if (c.nodes.size() != c.velocities.size()) throw std::runtime_error("cable: nodes and velocities differ in size");
+            cs[i].first_node = (uint32_t)(pos.size() / 3); cs[i].n_nodes = (uint32_t)c.nodes.size(); cs[i].reserved = 0;
+            cs[i].flags = (settings.dampingForces ? (uint32_t)SFH_F_DAMPING : 0u) | (settings.reallisticBuoyancy ? (uint32_t)SFH_F_BUOYANCY : 0u) |
+                          (c.buoyancy ? (uint32_t)SFH_F_BUOYANT : 0u);
+            cs[i].radius = c.radius;
+            for (size_t k = 0; k < c.nodes.size(); ++k) {
+                pos.insert(pos.end(), {c.nodes[k].x, c.nodes[k].y, c.nodes[k].z});
+                vel.insert(vel.end(), {c.velocities[k].x, c.velocities[k].y, c.velocities[k].z});
+            }
+        }
+        std::vector<sfh_node_forces> out(pos.size() / 3);
+        Check(sfh_cable_step(ctx, &ocean, cs.data(), (uint32_t)cs.size(), pos.data(), vel.data(), (uint32_t)out.size(), out.data()), "sfh_cable_step");
+        for (size_t i = 0; i < cables.size(); ++i) {
+            CableBody& c = *cables[i];
+            c.nodalForces.resize(c.nodes.size());
+            for (size_t k = 0; k < c.nodes.size(); ++k) {
+                const sfh_node_forces& f = out[cs[i].first_node + k];
+                c.nodalForces[k].Fb = Get(f.Fb); c.nodalForces[k].Fdq = Get(f.Fdq); c.nodalForces[k].Fdf = Get(f.Fdf);
+            }
+        }
     }
 
     //! Wave-field producer on the device (OpenGLOcean::InitializeSimulation / Simulate without OpenGL): InitWaves once,

@@ -3,7 +3,7 @@
 //   print "Hydrodynamics time: <avg> us" like Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:166.
 // The scenario is read from a small binary file written by tests/test_host_mirror_gpu.py (so the same inputs can be
 // pushed through the Python binding and the oracle), results go to a binary file. Needs a CUDA device at run time.
-//   usage: demo_fluid_dynamics scene.bin out.bin [steps [aero_out.bin [sea_state waves_out.bin]]]
+//   usage: demo_fluid_dynamics scene.bin out.bin [steps [aero_out.bin [sea_state waves_out.bin [cable_out.bin]]]]
 // With aero_out.bin the same bodies also go through HydroEngine::ComputeAerodynamicForces once: wind = the scene's velocity
 // fields, gas density 1.2, proxy type cycling AUTO/SPHERE/CYLINDER/ELLIPSOID with fdCd as the ellipsoid radii, T_CG2H = T_O.
 #include <chrono>
@@ -123,6 +123,22 @@ int main(int argc, char** argv)
                 const sfb::HydrodynamicsInfo& r = b.info;
                 const double d[8] = {r.Fb.x, r.Fb.y, r.Fb.z, r.Tb.x, r.Tb.y, r.Tb.z, r.Swet, r.Vsub};
                 wout.write(reinterpret_cast<const char*>(d), sizeof(d));
+            }
+        }
+        if (argc > 7) { // a 40-node cable piercing the (generated) sea surface, through HydroEngine::ComputeCableForces
+            sfb::CableBody cable;
+            cable.radius = 0.02;
+            for (int k = 0; k < 40; ++k) {
+                const double s = k / 39.0;
+                cable.nodes.push_back(sfb::Vector3(-2.0 + 4.0 * s, -1.0 + 2.0 * s, -0.5 + 2.0 * s));
+                cable.velocities.push_back(sfb::Vector3(0.1 * s, -0.2, 0.05 * k));
+            }
+            std::vector<sfb::CableBody*> cables{&cable};
+            engine.ComputeCableForces(settings, ocean, cables);
+            std::ofstream cout_(argv[7], std::ios::binary);
+            for (const auto& f : cable.nodalForces) {
+                const double d[9] = {f.Fb.x, f.Fb.y, f.Fb.z, f.Fdq.x, f.Fdq.y, f.Fdq.z, f.Fdf.x, f.Fdf.y, f.Fdf.z};
+                cout_.write(reinterpret_cast<const char*>(d), sizeof(d));
             }
         }
     } catch (const std::exception& e) {

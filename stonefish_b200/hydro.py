@@ -444,6 +444,22 @@ class HydroContext:
     def compute_aero_device(self, atm_struct, d_states_ptr: int, n: int, d_out_ptr: int):
         self._check(self.lib.sfh_aero_step_device(self.ctx, C.byref(atm_struct), d_states_ptr, n, d_out_ptr), "sfh_aero_step_device")
 
+    def compute_cables(self, ocean: Ocean, cables, node_pos: np.ndarray, node_vel: np.ndarray) -> np.ndarray:
+        """CableEntity::ComputeHydrodynamicForces for a batch of cables (sfh_cable_step). cables: iterable of
+        (first_node, n_nodes, radius, flags). Returns (n_nodes_total, 9): Fb, Fdq, Fdf per node."""
+        self._sync_waves(ocean)
+        pos = np.ascontiguousarray(node_pos, dtype=np.float64).reshape(-1, 3)
+        vel = np.ascontiguousarray(node_vel, dtype=np.float64).reshape(-1, 3)
+        assert pos.shape == vel.shape
+        cs = (_abi.sfh_cable * max(len(cables), 1))()
+        for i, (first, n, radius, flags) in enumerate(cables):
+            cs[i] = _abi.sfh_cable(int(first), int(n), int(flags), 0, float(radius))
+        out = np.zeros((pos.shape[0], 9), dtype=np.float64)
+        o = ocean.to_struct()
+        self._check(self.lib.sfh_cable_step(self.ctx, C.byref(o), cs, len(cables), pos.ctypes.data, vel.ctypes.data, pos.shape[0],
+                                            out.ctypes.data), "sfh_cable_step")
+        return out
+
     def compute_device(self, ocean_struct, d_states_ptr: int, n: int, d_out_ptr: int):
         """Device-resident step (sfh_step_device): asynchronous on the context's stream."""
         self._check(self.lib.sfh_step_device(self.ctx, C.byref(ocean_struct), d_states_ptr, n, d_out_ptr), "sfh_step_device")

@@ -146,6 +146,33 @@ for i in range(12):
     cd = arr(3)
     lib.btc_ellipsoid_cd((D * 3)(*params), cd)
     out["ellipsoid_cd"].append({"params": hx(params), "cd": hx(cd)})
+# --- CableEntity::ComputeHydrodynamicForces on a flat sea with a uniform current + a jet; node lines that reach every branch
+# of the submerged-volume case analysis (CableEntity.cpp:271-316)
+out["cables"] = []
+cab_ocean = _abi.sfh_ocean()
+cab_ocean.density, cab_ocean.gravity_z, cab_ocean.currents_enabled, cab_ocean.n_currents = 1025.0, 9.81, 1, 2
+cab_ocean.currents[0] = fields["uniform"]
+cab_ocean.currents[1] = fields["jet"]
+r = 0.05
+lines = {
+    "deep_inclined": [(0.1 * i, 0.05 * i, 2.0 + 0.07 * i) for i in range(6)],
+    "dry": [(0.1 * i, 0.0, -1.0 - 0.05 * i) for i in range(4)],
+    "piercing": [(0.2 * i, -0.1 * i, -0.5 + 0.3 * i) for i in range(7)],
+    "horizontal_awash": [(0.3 * i, 0.1 * i, 0.02) for i in range(5)],
+    "vertical": [(1.0, 2.0, -0.3 + 0.25 * i) for i in range(5)],
+    "both_caps_awash": [(0.5 * i, 0.0, -0.01 + 0.012 * i) for i in range(4)],
+    "second_cap_awash": [(0.0, 0.0, -0.2), (0.4, 0.1, 0.03), (0.8, 0.2, 0.031)],
+    "first_cap_awash": [(0.0, 0.0, -0.02), (0.3, 0.2, 0.3), (0.5, 0.2, 0.9)],
+    "in_the_jet": [(0.02 * i, -2.8 + 0.3 * i, 1.0 + 0.01 * i) for i in range(6)],
+}
+for name, nodes in lines.items():
+    for flags in (7, 1, 6):
+        pos = [c for nd in nodes for c in nd]
+        vel = take(3 * len(nodes), -1.5, 1.5)
+        res = arr(9 * len(nodes))
+        lib.btc_cable(C.byref(cab_ocean), C.c_uint32(len(nodes)), D(r), C.c_uint32(flags), (D * len(pos))(*pos), (D * len(vel))(*vel), res)
+        out["cables"].append({"name": name, "radius": r.hex(), "flags": flags, "pos": hx(pos), "vel": hx(vel), "out": hx(res)})
+out["cable_ocean"] = {"density": (1025.0).hex(), "gravity_z": (9.81).hex(), "fields": ["uniform", "jet"]}
 assert k < len(u)
 
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bt_golden.json")

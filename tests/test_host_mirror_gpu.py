@@ -116,9 +116,9 @@ def test_cpp_host_mirror_generated_waves(tmp_path, ctx):
     assert os.path.exists(DEMO), "build the host mirror demo first (make -C stonefish_b200/host)"
     sc = scenes.config1()
     scene = str(tmp_path / "scene.bin")
-    outs = [str(tmp_path / n) for n in ("out.bin", "aero.bin", "waves.bin")]
+    outs = [str(tmp_path / n) for n in ("out.bin", "aero.bin", "waves.bin", "cable.bin")]
     write_scene(scene, sc)
-    subprocess.check_output([DEMO, scene, outs[0], "2", outs[1], "1.0", outs[2]], text=True)  # sea state 1: decimetre waves
+    subprocess.check_output([DEMO, scene, outs[0], "2", outs[1], "1.0", outs[2], outs[3]], text=True)  # sea state 1: decimetre waves
     raw = np.fromfile(outs[2], dtype=np.float64).reshape(sc.n_bodies, 8)
     ctx.wavegen_init(wave_params(1.0))
     ctx.wavegen_simulate(1.5)
@@ -132,3 +132,9 @@ def test_cpp_host_mirror_generated_waves(tmp_path, ctx):
     assert np.array_equal(raw[crossing, 0:3], got["Fb"][crossing]) and np.array_equal(raw[crossing, 6], got["Swet"][crossing])
     flat = read_results(outs[0], sc.n_bodies)
     assert not np.array_equal(flat["Fb"][crossing], got["Fb"][crossing])  # the waves changed the answer
+    # sfb::HydroEngine::ComputeCableForces on the same generated sea: the demo's 40-node cable through the Python mirror
+    s = np.arange(40) / 39.0
+    pos = np.stack([-2.0 + 4.0 * s, -1.0 + 2.0 * s, -0.5 + 2.0 * s], axis=1)
+    vel = np.stack([0.1 * s, np.full(40, -0.2), 0.05 * np.arange(40)], axis=1)
+    cab = ctx.compute_cables(sc.ocean, [(0, 40, 0.02, 7)], pos, vel)
+    assert np.array_equal(np.fromfile(outs[3], dtype=np.float64).reshape(40, 9), cab) and np.abs(cab[:, 2]).max() > 0
