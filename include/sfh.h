@@ -157,6 +157,7 @@ int sfh_query_fluid_velocity(sfh_ctx* ctx, const sfh_ocean* ocean, const float* 
 /* On-device checks of the hand-written IEEE sequences the kernels use (stonefish_b200/csrc/sfh_packed.cuh):
  *   which 0: square root, exhaustive over [2^-101, FLT_MAX]      which 2: shared-reciprocal division, n random pairs
  *   which 1: division by 3, exhaustive over its domain            which 3: packed f32x2 operators vs scalar, n samples
+ *   which 4: the same division with unrelated magnitudes (coordinate / grid size), n random pairs
  * Writes the number of operands tested and of results that differ from the hardware's div.rn/sqrt.rn/add.rn/... */
 int sfh_selftest(sfh_ctx* ctx, uint32_t which, uint64_t n, uint64_t* tested_out, uint64_t* mismatches_out);
 

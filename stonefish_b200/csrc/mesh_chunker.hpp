@@ -6,10 +6,13 @@
 //          vertices they reference, sized and aligned so that ONE bulk async copy (cp.async.bulk, 16-byte
 //          granularity) brings a whole chunk into shared memory:
 //              +0                u32 n_verts, u32 n_faces, u32 next_bytes, u32 first_slot
-//              +16               float x[nv4]        nv4 = n_verts rounded up to a multiple of 4
-//              +16 + 4*nv4       float y[nv4]
-//              +16 + 8*nv4       float z[nv4]
-//              +16 + 12*nv4      u32   face[nf4]     local ids packed i0 | i1<<8 | i2<<16, nf4 = n_faces up to 4
+//              +16               float cx, cy, cz, r  bounding sphere of the chunk's vertices in the mesh frame (r rounded up)
+//              +32               float x[nv4]        nv4 = n_verts rounded up to a multiple of 4
+//              +32 + 4*nv4       float y[nv4]
+//              +32 + 8*nv4       float z[nv4]
+//              +32 + 12*nv4      u32   face[nf4]     local ids packed i0 | i1<<8 | i2<<16, nf4 = n_faces up to 4
+//          The sphere lets k_surface drop a chunk that lies entirely above the highest possible water surface after reading
+//          32 bytes of it: all its faces are class 0 and contribute nothing (SolidEntity.cpp:1353-1360).
 //          `next_bytes` is the size of the FOLLOWING chunk of the same mesh (0 for the last), so a block can
 //          issue the copy of chunk c+1 while it still works on chunk c without a dependent header read.
 //          chunk_off[c] (16-byte units, n_chunks+1 entries) gives random access for a block's first chunk.
@@ -21,6 +24,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -31,8 +35,8 @@
 #ifndef SFH_CH_VERTS
 #define SFH_CH_VERTS 256u
 #endif
-#define SFH_CH_HDR_BYTES 16u
-#define SFH_CH_MAX_BYTES (SFH_CH_HDR_BYTES + 12u * SFH_CH_VERTS + 4u * SFH_CH_FACES) /* 4112 */
+#define SFH_CH_HDR_BYTES 32u
+#define SFH_CH_MAX_BYTES (SFH_CH_HDR_BYTES + 12u * SFH_CH_VERTS + 4u * SFH_CH_FACES) /* 4128 */
 
 namespace sfh {
 
@@ -116,10 +120,30 @@ inline bool chunk_mesh(const void* pos, size_t stride, uint32_t n_verts, const u
         uint8_t* p = out.chunks.data() + base;
         const uint32_t hdr[4] = {nv, nf, 0u, chunk_id * SFH_CH_FACES};
         std::memcpy(p, hdr, sizeof(hdr));
-        std::memcpy(p + 16, cx.data(), 4 * nv);
-        std::memcpy(p + 16 + 4 * nv4, cy.data(), 4 * nv);
-        std::memcpy(p + 16 + 8 * nv4, cz.data(), 4 * nv);
-        std::memcpy(p + 16 + 12 * nv4, cf.data(), 4 * nf);
+        // bounding sphere: centre of the AABB, radius = largest distance in double, rounded up (NaN coordinates give a NaN
+        // sphere, which never passes the "entirely dry" test)
+        double lo3[3] = {1e300, 1e300, 1e300}, hi3[3] = {-1e300, -1e300, -1e300};
+        for (uint32_t v = 0; v < nv; ++v) {
+            const double q[3] = {cx[v], cy[v], cz[v]};
+            for (int k = 0; k < 3; ++k) { lo3[k] = std::min(lo3[k], q[k]); hi3[k] = std::max(hi3[k], q[k]); }
+        }
+        const float cen[3] = {(float)(0.5 * (lo3[0] + hi3[0])), (float)(0.5 * (lo3[1] + hi3[1])), (float)(0.5 * (lo3[2] + hi3[2]))};
+        double r2 = 0.0;
+        bool finite = true;
+        for (uint32_t v = 0; v < nv; ++v) {
+            const double dx = (double)cx[v] - cen[0], dy = (double)cy[v] - cen[1], dz = (double)cz[v] - cen[2];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (!(d2 <= 1e300)) finite = false;
+            r2 = std::max(r2, d2);
+        }
+        float rad = (float)(std::sqrt(r2) * (1.0 + 1e-6));
+        rad = std::nextafter(rad, 3.4e38f);
+        const float sphere[4] = {cen[0], cen[1], cen[2], finite ? rad : NAN};
+        std::memcpy(p + 16, sphere, sizeof(sphere));
+        std::memcpy(p + SFH_CH_HDR_BYTES, cx.data(), 4 * nv);
+        std::memcpy(p + SFH_CH_HDR_BYTES + 4 * nv4, cy.data(), 4 * nv);
+        std::memcpy(p + SFH_CH_HDR_BYTES + 8 * nv4, cz.data(), 4 * nv);
+        std::memcpy(p + SFH_CH_HDR_BYTES + 12 * nv4, cf.data(), 4 * nf);
         if (prev_hdr != (size_t)-1) std::memcpy(out.chunks.data() + prev_hdr + 8, &bytes, 4); // previous.next_bytes
         prev_hdr = base;
         out.n_chunk_verts += nv;

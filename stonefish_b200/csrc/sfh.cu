@@ -61,9 +61,9 @@ struct sfh_ctx {
     PinBuf h_mesh_table;
 
     // waves
-    DevBuf<float> d_wave_rgba, d_wave_ch0, d_wave_ch1;
+    DevBuf<float> d_wave_rgba, d_wave_ch0, d_wave_ch1, d_wave_hmax;
     PinBuf h_wave;
-    WavesDev waves{nullptr, nullptr, 0, 0.f, 0.f};
+    WavesDev waves{nullptr, nullptr, 0, 0.f, 0.f, nullptr};
     bool have_waves = false;
 
     // cables (row N4)
@@ -594,7 +594,7 @@ void sfh_destroy(sfh_ctx* ctx)
     cudaFree(ctx->d_cables.p); cudaFree(ctx->d_node_pos.p); cudaFree(ctx->d_node_vel.p); cudaFree(ctx->d_node_out.p);
     cudaFree(ctx->d_wg_s12.p); cudaFree(ctx->d_wg_s34.p); cudaFree(ctx->d_wg_tmp.p); cudaFree(ctx->d_wg_fft.p);
     cudaFree(ctx->d_wg_bf_src.p); cudaFree(ctx->d_wg_bf_w.p);
-    cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_wave_rgba.p); cudaFree(ctx->d_wave_ch0.p); cudaFree(ctx->d_wave_ch1.p);
+    cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_wave_rgba.p); cudaFree(ctx->d_wave_ch0.p); cudaFree(ctx->d_wave_ch1.p); cudaFree(ctx->d_wave_hmax.p);
     cudaFree(ctx->d_states.p); cudaFree(ctx->d_info.p); cudaFree(ctx->d_bodies.p); cudaFree(ctx->d_off_sub.p);
     cudaFree(ctx->d_off_surf.p); cudaFree(ctx->d_status.p); cudaFree(ctx->d_part_sub.p); cudaFree(ctx->d_part_surf.p);
     cudaFree(ctx->d_ocean.p); cudaFree(ctx->d_codes.p); cudaFree(ctx->d_code_base.p);
@@ -689,7 +689,10 @@ int sfh_waves_upload(sfh_ctx* ctx, const sfh_waves* w)
     CU(ctx, cudaMemcpyAsync(ctx->d_wave_rgba.p, src, have * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     k_waves_planar<<<(unsigned)((texels + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_wave_rgba.p, (uint32_t)have, (uint32_t)texels,
                                                                                ctx->d_wave_ch0.p, ctx->d_wave_ch1.p);
+    if ((rc = ensure_dev(ctx, ctx->d_wave_hmax, 1)) != SFH_OK) return rc;
+    k_wave_hmax<<<1, 1024, 0, ctx->stream>>>(ctx->d_wave_ch0.p, ctx->d_wave_ch1.p, (uint32_t)texels, ctx->d_wave_hmax.p);
     CU(ctx, cudaGetLastError());
+    ctx->waves.hmax = ctx->d_wave_hmax.p;
     ctx->waves.ch0 = ctx->d_wave_ch0.p;
     ctx->waves.ch1 = ctx->d_wave_ch1.p;
     ctx->waves.N = w->fft_size;
@@ -757,7 +760,10 @@ int sfh_wavegen_simulate(sfh_ctx* ctx, float t)
     k_waves_planar<<<(unsigned)((texels + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(ctx->d_wg_fft.p),
                                                                                (uint32_t)(texels * 4), (uint32_t)texels, ctx->d_wave_ch0.p,
                                                                                ctx->d_wave_ch1.p);
+    if ((rc = ensure_dev(ctx, ctx->d_wave_hmax, 1)) != SFH_OK) return rc;
+    k_wave_hmax<<<1, 1024, 0, ctx->stream>>>(ctx->d_wave_ch0.p, ctx->d_wave_ch1.p, (uint32_t)texels, ctx->d_wave_hmax.p);
     CU(ctx, cudaGetLastError());
+    ctx->waves.hmax = ctx->d_wave_hmax.p;
     ctx->waves.ch0 = ctx->d_wave_ch0.p;
     ctx->waves.ch1 = ctx->d_wave_ch1.p;
     ctx->waves.N = N;
@@ -980,7 +986,7 @@ int sfh_query_fluid_velocity(sfh_ctx* ctx, const sfh_ocean* ocean, const float* 
 int sfh_selftest(sfh_ctx* ctx, uint32_t which, uint64_t n, uint64_t* tested_out, uint64_t* mismatches_out)
 {
     if (!ctx) return SFH_ERR_INVALID;
-    if (which > 3 || !tested_out || !mismatches_out) return fail(ctx, SFH_ERR_INVALID, "bad selftest arguments");
+    if (which > 4 || !tested_out || !mismatches_out) return fail(ctx, SFH_ERR_INVALID, "bad selftest arguments");
     CU(ctx, cudaSetDevice(ctx->device));
     unsigned long long* d = nullptr;
     CU(ctx, cudaMalloc(&d, 3 * sizeof(unsigned long long)));

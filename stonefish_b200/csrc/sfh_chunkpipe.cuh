@@ -1,7 +1,7 @@
 // sfh_chunkpipe.cuh — double-buffered staging of mesh chunks in shared memory with bulk async copies
 // (cp.async.bulk = the 1-D TMA path, SASS UBLKCP) completing on mbarriers.
 //
-// One elected thread per block issues ONE copy per chunk (<= 4112 bytes, 16-byte granular — the chunk format of
+// One elected thread per stream issues ONE copy per chunk (<= 4128 bytes, 16-byte granular — the chunk format of
 // mesh_chunker.hpp is laid out for exactly this) one whole chunk ahead of its use, so no thread ever waits on a
 // global load inside the per-face loop and the copy costs no registers and no scoreboard slots.
 #pragma once
@@ -70,6 +70,7 @@ __device__ __forceinline__ void pipe_wait(const PipeAddr& a, int s, uint32_t par
 
 struct ChunkView { // where things are inside a staged chunk
     uint32_t nv, nf, next_bytes;
+    float4 sphere; // bounding sphere of the vertices, mesh frame
     const float *x, *y, *z;
     const uint32_t* faces;
 };
@@ -80,6 +81,7 @@ __device__ __forceinline__ ChunkView chunk_view(const uint8_t* buf)
     const uint32_t nv4 = (h.x + 3u) & ~3u;
     ChunkView v;
     v.nv = h.x; v.nf = h.y; v.next_bytes = h.z;
+    v.sphere = *reinterpret_cast<const float4*>(buf + 16);
     v.x = reinterpret_cast<const float*>(buf + SFH_CH_HDR_BYTES);
     v.y = v.x + nv4;
     v.z = v.y + nv4;

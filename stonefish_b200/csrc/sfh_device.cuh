@@ -60,6 +60,7 @@ struct WavesDev {
     const float* ch1; // channel 1 (grid 101 m)
     int32_t N;
     float gx, gy;     // gridSizes.x, gridSizes.y
+    const float* hmax; // device scalar: max|ch0| + max|ch1| >= |wave height| anywhere (bilinear = convex combination)
 };
 
 // Partial sums written by one thread block for one body.
@@ -108,6 +109,64 @@ __device__ __forceinline__ F3 xform(const float* R, const float* t, float x, flo
     r.y = fadd(fadd(fmul(R[3], x), fmul(R[4], y)), fadd(fmul(R[5], z), t[1]));
     r.z = fadd(fadd(fmul(R[6], x), fmul(R[7], y)), fadd(fmul(R[8], z), t[2]));
     return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scalar IEEE sequences (see sfh_packed.cuh for the two-lane twins and sfh_selftest for their validation): correctly
+// rounded results, identical to __fsqrt_rn / __fdiv_rn inside the stated domains, in fewer dispatched instructions.
+// ---------------------------------------------------------------------------------------------
+#define SFH_THIRD 0.3333333432674407958984375f /* RN(1/3) = 0x3eaaaaab */
+// sqrt: x in [2^-101, FLT_MAX]
+__device__ __forceinline__ float ieee_sqrt1(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    const float s = __fmul_rn(x, r), h = __fmul_rn(r, 0.5f);
+    const float e = __fmaf_rn(-s, s, x);
+    return __fmaf_rn(e, h, s);
+}
+
+// x / 3.f: x == 0 or 2^-100 <= |x| <= FLT_MAX
+__device__ __forceinline__ float ieee_div3_1(float x)
+{
+    const float q = __fmul_rn(x, SFH_THIRD);
+    const float rem = __fmaf_rn(-3.f, q, x);
+    return __fmaf_rn(rem, SFH_THIRD, q);
+}
+
+// a / b through a refined reciprocal r of b, shared by several numerators: b in [2^-20, 2^64] and a == 0 or |a| in
+// [2^-36, 2b] (selftest 2), or b in [2^-20, 2^40] and |a| in [2^-36, 2^64) (selftest 4)
+__device__ __forceinline__ float refined_rcp1(float b)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    const float e = __fmaf_rn(-b, r, 1.f);
+    return __fmaf_rn(r, e, r);
+}
+__device__ __forceinline__ float ieee_div_r1(float a, float b, float r)
+{
+    const float q = __fmul_rn(a, r);
+    const float rem = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, rem, q);
+}
+
+// ---- domain guards. key(x) = 2*|x|_bits - 1 (mod 2^32): 0xffffffff for +-0, monotone in |x| otherwise, so
+// "some operand is nonzero and smaller than a threshold" is one unsigned min and one compare.
+__device__ __forceinline__ uint32_t tiny_key(float x)
+{
+    const uint32_t b = __float_as_uint(x);
+    return b + b - 1u;
+}
+#define SFH_TINY_KEY 0x1affffffu /* 2*bits(2^-100) - 1 */
+
+#define SFH_NUM_KEY 0x5affffffu  /* 2*bits(2^-36) - 1 */
+#define SFH_KEY_SPAN 0x63ffffffu /* keys of |a| in [2^-36, 2^64) are SFH_NUM_KEY + [0, SFH_KEY_SPAN] */
+
+// x / 3.f and a / b with the fast forms inside their proven domains, the hardware division outside
+__device__ __forceinline__ float div3(float x) { return tiny_key(x) >= SFH_TINY_KEY ? ieee_div3_1(x) : __fdiv_rn(x, 3.f); }
+__device__ __forceinline__ float div_wide(float a, float b, float r, bool b_ok)
+{
+    return (b_ok && tiny_key(a) - SFH_NUM_KEY <= SFH_KEY_SPAN) ? ieee_div_r1(a, b, r) : __fdiv_rn(a, b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -181,11 +240,29 @@ __device__ __forceinline__ F3 fluid_velocity_general(const sfh_current* cur, uin
     return F3{(float)fv.x, (float)fv.y, (float)fv.z};
 }
 
-// OpenGLRealOcean::ComputeInterpolatedWaveData (OpenGLRealOcean.cpp:280-319) on a planar channel copy.
-__device__ __forceinline__ float wave_bilinear(const float* __restrict__ ch, int N, float x, float y)
+// Per-kernel constants of the wave lookup: the reference divides every coordinate by the grid size and recomputes
+// 0.5 / fftSize on every call (OpenGLRealOcean.cpp:283,325-326); same values, computed once.
+struct WaveConst {
+    float fN, half; // (float)N, 0.5f / N (IEEE)
+    float rgx, rgy; // refined reciprocals of gridSizes.x / .y for div_wide
+    bool gx_ok, gy_ok;
+};
+__device__ __forceinline__ WaveConst wave_const(const WavesDev& w)
 {
-    const float fN = (float)N;
-    const float half = fdiv(0.5f, fN);
+    WaveConst c;
+    c.fN = (float)w.N;
+    c.half = fdiv(0.5f, c.fN);
+    c.rgx = refined_rcp1(w.gx);
+    c.rgy = refined_rcp1(w.gy);
+    c.gx_ok = w.gx >= 0x1p-20f && w.gx <= 0x1p40f;
+    c.gy_ok = w.gy >= 0x1p-20f && w.gy <= 0x1p40f;
+    return c;
+}
+
+// OpenGLRealOcean::ComputeInterpolatedWaveData (OpenGLRealOcean.cpp:280-319) on a planar channel copy.
+__device__ __forceinline__ float wave_bilinear(const float* __restrict__ ch, int N, const WaveConst& c, float x, float y)
+{
+    const float fN = c.fN, half = c.half;
     float tmp;
     float i0f = modff(fsub(x, half), &tmp);
     float j0f = modff(fsub(y, half), &tmp);
@@ -216,19 +293,25 @@ __device__ __forceinline__ float wave_bilinear(const float* __restrict__ ch, int
 }
 
 // OpenGLRealOcean::ComputeWaveHeight (OpenGLRealOcean.cpp:321-331)
-__device__ __forceinline__ float wave_height(const WavesDev& w, float x, float y)
+__device__ __forceinline__ float wave_height(const WavesDev& w, const WaveConst& c, float x, float y)
 {
     float z = 0.f;
-    z = fsub(z, wave_bilinear(w.ch0, w.N, fdiv(x, w.gx), fdiv(y, w.gx)));
-    z = fsub(z, wave_bilinear(w.ch1, w.N, fdiv(x, w.gy), fdiv(y, w.gy)));
+    z = fsub(z, wave_bilinear(w.ch0, w.N, c, div_wide(x, w.gx, c.rgx, c.gx_ok), div_wide(y, w.gx, c.rgx, c.gx_ok)));
+    z = fsub(z, wave_bilinear(w.ch1, w.N, c, div_wide(x, w.gy, c.rgy, c.gy_ok), div_wide(y, w.gy, c.rgy, c.gy_ok)));
     return z;
 }
 
 // Ocean::GetDepth(glm::vec3) (Ocean.cpp:149-168)
 template <bool WAVES>
+__device__ __forceinline__ float get_depth(const WavesDev& w, const WaveConst& c, float x, float y, float z)
+{
+    if (WAVES) return fsub(z, wave_height(w, c, x, y));
+    return z;
+}
+template <bool WAVES>
 __device__ __forceinline__ float get_depth(const WavesDev& w, float x, float y, float z)
 {
-    if (WAVES) return fsub(z, wave_height(w, x, y));
+    if (WAVES) return fsub(z, wave_height(w, wave_const(w), x, y));
     return z;
 }
 

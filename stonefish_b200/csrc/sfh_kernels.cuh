@@ -94,7 +94,7 @@ __device__ __forceinline__ uint32_t damping_terms(const BodyRegs& B, const sfh_c
     F3 vt = vc - vn;
     if (vc_n < -1e-12f) {
         float vmag2 = length2(vc);
-        F3 q = ((vc * fsqrt(vmag2)) * (-vc_n)) * A;
+        F3 q = ((vc * ieee_sqrt1(vmag2)) * (-vc_n)) * A; // vc_n < -1e-12 puts |vc|^2 above 1e-24 > 2^-101
         F3 tq = cross(r, q);
         acc[0] = dadd(acc[0], (double)q.x);  acc[1] = dadd(acc[1], (double)q.y);  acc[2] = dadd(acc[2], (double)q.z);
         acc[3] = dadd(acc[3], (double)tq.x); acc[4] = dadd(acc[4], (double)tq.y); acc[5] = dadd(acc[5], (double)tq.z);
@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
     if (CUR) stage_currents(s_cur, P.ocean, n_cur);
     if (tid < 12) s_cnt[tid] = 0;
     const WavesDev wv = P.waves;
+    const float hmax = WAVES ? __ldg(wv.hmax) : 0.f;
+    const WaveConst wc = WAVES ? wave_const(wv) : WaveConst{};
 
     double acc[SFH_NACC_SURF];
 #pragma unroll
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
     BodyRegs B;
     F3 p0;
     bool buoy, damp;
+    float zrow; // >= |row z of T_C|
 
     auto flush = [&](uint32_t body) {
         spill_epack(epack, s_cnt);
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
         p0 = F3{B.p.x, B.p.y, 0.f}; // SolidEntity.cpp:1332-1334
         buoy = (s_body.flags & BF_BUOYANCY) != 0;
         damp = (s_body.flags & BF_DAMPING) != 0;
+        zrow = sqrtf(s_body.R[6] * s_body.R[6] + s_body.R[7] * s_body.R[7] + s_body.R[8] * s_body.R[8]) * 1.000001f;
     };
     fetch_regs();
 
@@ -227,18 +231,28 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
         it.parity ^= 1u << it.s;
         const ChunkView cv = chunk_view(s_pipe.buf[it.s]);
         const uint32_t nf = cv.nf, b = it.b, c = it.w - it.b_begin;
+        // Entirely above the highest possible water surface? Every vertex v of the chunk satisfies |v - centre| <= r in the mesh
+        // frame, so its world z is at most (T_C * centre).z + |row z of T_C| * r (Cauchy-Schwarz; any linear T_C) and its depth
+        // at most that + hmax (z points down, the surface is within +-hmax of z = 0); the last term covers the fp32 rounding
+        // of both transforms. Then every face is class 0 and adds nothing (SolidEntity.cpp:1353-1360).
+        const F3 cw = xform(s_body.R, s_body.t, cv.sphere.x, cv.sphere.y, cv.sphere.z);
+        const float reach = fabsf(s_body.t[2]) + fabsf(cv.sphere.x) + fabsf(cv.sphere.y) + fabsf(cv.sphere.z) + cv.sphere.w;
+        const bool dry = cw.z + zrow * cv.sphere.w + hmax + (4e-6f * reach + 1e-6f) < 0.f;
 
         __syncthreads(); // every thread is done with the previous chunk: s_v and the other staging buffer are free
         const uint8_t* nsrc = nullptr;
         uint32_t nbytes = 0;
         if (tid == 0) walk_issue_next(pa, it, P, cv.next_bytes, nsrc, nbytes);
+        if (dry) { // block-uniform
+            cpack += (tid < nf ? 1ull : 0ull) + (tid + SFH_BLOCK < nf ? 1ull : 0ull); // class 0, code 0 (the debug buffer is zero-filled)
+        } else {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const uint32_t i = tid + k * SFH_BLOCK;
             if (i < cv.nv) {
                 F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
                 // Ocean::GetDepth per vertex (SolidEntity.cpp:1349-1351): same bits for every incident face
-                s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(wv, pw.x, pw.y, pw.z));
+                s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z));
             }
         }
         __syncthreads();
@@ -260,7 +274,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
                 auto clip = [](F3 pa, F3 pu, float da, float du) { return pu + (pa - pu) * fdiv(du, fadd(fabsf(da), du)); };
                 // tetrahedron (p0, a, b, c) of the submerged volume (SolidEntity.cpp:1371-1377 and twins)
                 auto tetra = [&](F3 pa, F3 pb, F3 pc) {
-                    F3 cg = ((pa + pb) + pc) / 4.f;
+                    F3 cg = ((pa + pb) + pc) * 0.25f; // "/ 4.f": an exact scaling either way
                     float v6 = dot(pa, cross(pb, pc));
                     F3 m = cg * v6;
                     acc[20] = dadd(acc[20], (double)m.x); acc[21] = dadd(acc[21], (double)m.y); acc[22] = dadd(acc[22], (double)m.z);
@@ -285,10 +299,11 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
                     if (cls == 5) { tetra(p02, p04, p03); fv2 = p3 - p1; }
                     else          { tetra(p01, p03, p04); fv2 = p4 - p1; }
                     fv1 = p2 - p1; fv3 = p2 - p3; fv4 = p4 - p3;
-                    fc = (((p1 + p2) + p3) + p4) / 4.f;
+                    fc = (((p1 + p2) + p3) + p4) * 0.25f;
                 } else {
                     fv1 = p2 - p1; fv2 = p3 - p1;
-                    fc = ((p1 + p2) + p3) / 3.f;
+                    const F3 cs = (p1 + p2) + p3;
+                    fc = F3{div3(cs.x), div3(cs.y), div3(cs.z)};
                 }
                 F3 fn = cross(fv1, fv2);
                 float len = length2(fn);
@@ -296,11 +311,24 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
                     epack += 1u;
                     code |= SFH_FACE_DEGENERATE;
                 } else {
-                    len = fsqrt(len);
-                    F3 fn1 = fn / len;
-                    float A = is_quad ? fdiv(fadd(len, fsqrt(length2(cross(fv3, fv4)))), 2.f) : fdiv(len, 2.f);
+                    len = ieee_sqrt1(len); // len >= 1e-12
+                    // fn / len: |fn_i| <= len, len >= 1e-6 > 2^-20; components below 2^-36 (not zero) take the hardware division
+                    F3 fn1;
+                    if (min(min(tiny_key(fn.x), tiny_key(fn.y)), tiny_key(fn.z)) >= SFH_NUM_KEY) {
+                        const float r = refined_rcp1(len);
+                        fn1 = F3{ieee_div_r1(fn.x, len, r), ieee_div_r1(fn.y, len, r), ieee_div_r1(fn.z, len, r)};
+                    } else {
+                        fn1 = fn / len;
+                    }
+                    float A; // "/ 2.f": exact scaling
+                    if (is_quad) {
+                        const float l2 = length2(cross(fv3, fv4));
+                        A = fmul(fadd(len, l2 >= 0x1p-100f ? ieee_sqrt1(l2) : fsqrt(l2)), 0.5f);
+                    } else {
+                        A = fmul(len, 0.5f);
+                    }
                     if (WAVES && buoy) { // SolidEntity.cpp:1650-1658
-                        float depthc = get_depth<WAVES>(wv, fc.x, fc.y, fc.z);
+                        float depthc = get_depth<WAVES>(wv, wc, fc.x, fc.y, fc.z);
                         F3 Fbi = ((-fn1) * A) * depthc;
                         F3 Tbi = cross(fc - B.p, Fbi);
                         acc[12] = dadd(acc[12], (double)Fbi.x); acc[13] = dadd(acc[13], (double)Fbi.y); acc[14] = dadd(acc[14], (double)Fbi.z);
@@ -312,6 +340,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
             }
             if (DEBUG) P.codes[P.code_base[b] + s_body.orig_face[(size_t)c * SFH_CH_FACES + slot]] = (uint8_t)code;
         }
+        } // !dry
         if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); spill_cpack(cpack, s_cnt + 4); since_spill = 0; }
 
         if (++it.w >= it.w1) break;
@@ -685,6 +714,22 @@ __global__ void k_waves_planar(const float* __restrict__ rgba, uint32_t n_floats
     if (i >= n_texels) return;
     ch0[i] = (4 * i + 0 < n_floats_valid) ? rgba[4 * i + 0] : 0.f;
     ch1[i] = (4 * i + 1 < n_floats_valid) ? rgba[4 * i + 1] : 0.f;
+}
+
+// bound of the wave height: max|ch0| + max|ch1| over every texel the lookup can touch. One block.
+__global__ void __launch_bounds__(1024) k_wave_hmax(const float* __restrict__ ch0, const float* __restrict__ ch1, uint32_t n_texels, float* out)
+{
+    __shared__ float s_m[2][32];
+    float m0 = 0.f, m1 = 0.f;
+    for (uint32_t i = threadIdx.x; i < n_texels; i += blockDim.x) { m0 = fmaxf(m0, fabsf(ch0[i])); m1 = fmaxf(m1, fabsf(ch1[i])); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { m0 = fmaxf(m0, __shfl_down_sync(SFH_FULL, m0, off)); m1 = fmaxf(m1, __shfl_down_sync(SFH_FULL, m1, off)); }
+    if ((threadIdx.x & 31) == 0) { s_m[0][threadIdx.x >> 5] = m0; s_m[1][threadIdx.x >> 5] = m1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { m0 = fmaxf(m0, s_m[0][w]); m1 = fmaxf(m1, s_m[1][w]); }
+        *out = __fadd_ru(m0, m1);
+    }
 }
 
 } // namespace sfh

@@ -23,6 +23,8 @@ __device__ __forceinline__ bool same_bits(float a, float b)
 // which = 0: ieee_sqrt1 over EVERY float in [2^-101, FLT_MAX]                      (n ignored)
 // which = 1: ieee_div3_1 over EVERY float that is zero or has |x| >= 2^-100, finite  (n ignored)
 // which = 2: ieee_div_r1 on n pseudo-random (a, b): b in [2^-20, 2^64], a in {0} U +-[2^-36, 2b]
+// which = 4: ieee_div_r1 with UNRELATED magnitudes (coordinate / grid size in the wave lookup): b in [2^-20, 2^40],
+//            a in +-[2^-36, 2^64], n pseudo-random pairs
 // which = 3: packed operators vs scalar unfused operators on n pseudo-random operand pairs,
 //            including ieee_sqrt2 / ieee_div3_2 / ieee_div_r2 against their scalar twins
 __global__ void k_selftest(uint32_t which, uint64_t n, unsigned long long* mismatches, unsigned long long* tested)
@@ -67,6 +69,21 @@ __global__ void k_selftest(uint32_t which, uint64_t n, unsigned long long* misma
             const float want = __fdiv_rn(a, b);
             // the shared form may return +0 where IEEE gives -0 (documented; zero sign never reaches a result)
             if (!(same_bits(got, want) || (got == 0.f && want == 0.f))) { ++bad; first_bad = i; }
+            ++cnt;
+        }
+    } else if (which == 4) {
+        for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+            const uint64_t h = mix64(i ^ 0x1234567ull), g = mix64(h ^ 0x5851F42D4C957F2Dull);
+            uint32_t mb = (uint32_t)h & 0x7fffffu, ma = (uint32_t)(h >> 23) & 0x7fffffu;
+            const uint32_t pat = (uint32_t)(g >> 40) & 7u;
+            if (pat == 0) mb = 0x7fffffu; else if (pat == 1) mb = 0; else if (pat == 2) mb = 0x7ffffeu;
+            if (((g >> 43) & 7u) == 0) ma = 0x7fffffu; else if (((g >> 43) & 7u) == 1) ma = 0;
+            const int eb = -20 + (int)((g & 0xffff) % 61), ea = -36 + (int)(((g >> 22) & 0xffff) % 101);
+            const float b = __uint_as_float(((uint32_t)(eb + 127) << 23) | mb);
+            const float a = __uint_as_float(((uint32_t)(g >> 63) << 31) | ((uint32_t)(ea + 127) << 23) | ma);
+            const float got = ieee_div_r1(a, b, refined_rcp1(b));
+            const float want = __fdiv_rn(a, b);
+            if (!same_bits(got, want)) { ++bad; first_bad = i; }
             ++cnt;
         }
     } else {

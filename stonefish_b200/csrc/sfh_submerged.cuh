@@ -21,7 +21,6 @@ namespace sfh {
 // is proven for numerators that are zero or >= 2^-36 in magnitude (quotient zero or >= 2^-100, remainder exact).
 // ((a + b) + c) / 3.f uses ieee_div3_2, proven for sums that are zero or >= 2^-100.
 // Anything else — never seen on real meshes — is redone with the hardware division by the caller.
-#define SFH_NUM_KEY 0x5affffffu /* 2*bits(2^-36) - 1 */
 __device__ __forceinline__ uint32_t min_key(V3P a)
 {
     return min(min(min(tiny_key(lo(a.x)), tiny_key(lo(a.y))), tiny_key(lo(a.z))),

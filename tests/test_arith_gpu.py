@@ -37,3 +37,9 @@ def test_packed_operators_equal_scalar_unfused(ctx):
     tested, bad = _run(ctx, 3, 1 << 28)
     assert tested == 1 << 28
     assert bad == 0
+
+
+def test_shared_reciprocal_division_wide_quotients(ctx):
+    """ieee_div_r1 as the wave lookup uses it: world coordinate / grid size, magnitudes unrelated."""
+    tested, bad = _run(ctx, 4, 1 << 31)
+    assert tested == 1 << 31 and bad == 0

@@ -62,14 +62,17 @@ def test_chunks_reproduce_the_mesh(chk, mesh, keep):
             base = int(off[c]) * 16
             nv, nf, next_bytes, first_slot = (int(t) for t in np.frombuffer(data, np.uint32, 4, base))
             nv4, nf4 = (nv + 3) & ~3, (nf + 3) & ~3
-            size = 16 + 12 * nv4 + 4 * nf4
+            size = 32 + 12 * nv4 + 4 * nf4
             assert 1 <= nf <= 256 and 1 <= nv <= 256 and first_slot == c * 256
-            assert size == (int(off[c + 1]) - int(off[c])) * 16 and size % 16 == 0 and size <= 4112
+            assert size == (int(off[c + 1]) - int(off[c])) * 16 and size % 16 == 0 and size <= 4128
             assert next_bytes == ((int(off[c + 2]) - int(off[c + 1])) * 16 if c + 1 < n else 0)
-            x = np.frombuffer(data, np.float32, nv, base + 16)
-            y = np.frombuffer(data, np.float32, nv, base + 16 + 4 * nv4)
-            z = np.frombuffer(data, np.float32, nv, base + 16 + 8 * nv4)
-            f = np.frombuffer(data, np.uint32, nf, base + 16 + 12 * nv4)
+            x = np.frombuffer(data, np.float32, nv, base + 32)
+            y = np.frombuffer(data, np.float32, nv, base + 32 + 4 * nv4)
+            z = np.frombuffer(data, np.float32, nv, base + 32 + 8 * nv4)
+            f = np.frombuffer(data, np.uint32, nf, base + 32 + 12 * nv4)
+            sx, sy, sz, sr = (float(t) for t in np.frombuffer(data, np.float32, 4, base + 16))  # bounding sphere of the vertices
+            dist = np.sqrt((x.astype(np.float64) - sx) ** 2 + (y.astype(np.float64) - sy) ** 2 + (z.astype(np.float64) - sz) ** 2)
+            assert dist.max() <= sr <= dist.max() * 1.001 + 1e-6
             loc = np.stack([f & 255, (f >> 8) & 255, (f >> 16) & 255], axis=1)
             assert (loc < nv).all() and (f >> 24 == 0).all()
             faces = orig[c * 256: c * 256 + nf]
