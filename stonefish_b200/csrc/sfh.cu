@@ -310,14 +310,18 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
         if (g_surf > plan.chunks_ub) g_surf = plan.chunks_ub;
     }
 
+    // k_surface writes one partial record per (segment, body); k_scan_items sizes the segments so that there are at most
+    // SFH_SEG_PER_BLOCK per resident block (sfh_kernels.cuh)
+    const uint64_t n_seg_max = (g_surf ? g_surf : 1) * SFH_SEG_PER_BLOCK + 1;
+
     // buffers (growing them requires the stream to be idle: older kernels may still read the old ones)
-    const bool grow = n > ctx->d_bodies.cap || n + 1 > ctx->d_off_sub.cap || g_sub * SFH_SUB_WPB + n > ctx->d_part_sub.cap || g_surf + n > ctx->d_part_surf.cap;
+    const bool grow = n > ctx->d_bodies.cap || n + 1 > ctx->d_off_sub.cap || g_sub * SFH_SUB_WPB + n > ctx->d_part_sub.cap || n_seg_max + n > ctx->d_part_surf.cap;
     if (grow) CU(ctx, cudaStreamSynchronize(ctx->stream));
     if ((rc = ensure_dev(ctx, ctx->d_bodies, n)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_off_sub, n + 1)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_off_surf, n + 1)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_part_sub, g_sub * SFH_SUB_WPB + n)) != SFH_OK) return rc;
-    if ((rc = ensure_dev(ctx, ctx->d_part_surf, g_surf + n)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_part_surf, n_seg_max + n)) != SFH_OK) return rc;
     if (!ctx->d_status.p) {
         if ((rc = ensure_dev(ctx, ctx->d_status, 4)) != SFH_OK) return rc;
         CU(ctx, cudaMemsetAsync(ctx->d_status.p, 0, 4 * sizeof(uint32_t), ctx->stream));
@@ -331,13 +335,14 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;
     pp.off_sub = ctx->d_off_sub.p; pp.off_surf = ctx->d_off_surf.p; pp.status = ctx->d_status.p; pp.aero = plan.aero ? 1u : 0u;
     k_prologue<<<(n + 127) / 128, 128, 0, ctx->stream>>>(pp);
-    k_scan_items<<<1, 1024, 0, ctx->stream>>>(ctx->d_off_sub.p, ctx->d_off_surf.p, n);
+    k_scan_items<<<1, 1024, 0, ctx->stream>>>(ctx->d_off_sub.p, ctx->d_off_surf.p, n, ctx->d_status.p + 2, (uint32_t)g_surf);
     uint32_t launches = 2;
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 
     StepParams sp;
     sp.bodies = ctx->d_bodies.p; sp.n_bodies = n; sp.ocean = ctx->d_ocean.p; sp.waves = ctx->waves;
     sp.codes = plan.debug ? ctx->d_codes.p : nullptr; sp.code_base = plan.debug ? ctx->d_code_base.p : nullptr;
+    sp.seg_info = ctx->d_status.p + 2;
 
     ctx->ev_sub = ctx->ev_surf = false;
     if (plan.may_sub && g_sub > 0) {
@@ -372,7 +377,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     ep.states = d_states; ep.bodies = ctx->d_bodies.p; ep.n_bodies = n; ep.ocean = ctx->d_ocean.p;
     ep.off_sub = ctx->d_off_sub.p; ep.off_surf = ctx->d_off_surf.p;
     ep.part_sub = ctx->d_part_sub.p; ep.part_surf = ctx->d_part_surf.p;
-    ep.grid_sub = (uint32_t)(g_sub * SFH_SUB_WPB); ep.grid_surf = (uint32_t)g_surf; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
+    ep.grid_sub = (uint32_t)(g_sub * SFH_SUB_WPB); ep.seg_info = ctx->d_status.p + 2; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
     k_epilogue<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ep);
     ++launches;
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));

@@ -240,6 +240,66 @@ __device__ __forceinline__ F3 fluid_velocity_general(const sfh_current* cur, uin
     return F3{(float)fv.x, (float)fv.y, (float)fv.z};
 }
 
+// fp32 pre-test of a Jet / Pipe field against the bounding sphere of a CHUNK: most chunks of a scene lie far outside the
+// cone / the pipe, where the field is exactly zero (Jet.cpp:62-67, Pipe.cpp:66-71). The test evaluates the field geometry
+// at the sphere centre in fp32 with an error budget and only answers "certainly zero everywhere in the sphere"; fields that
+// may reach the chunk are evaluated in fp64 per face as before, so results are unchanged.
+struct CurGuard {
+    float a[3], n[3]; // centre / first point and axis, rounded to fp32
+    float r_hi, l_hi; // Jet: r; Pipe: max(r1, r2), and l — each rounded up
+    float a_abs;      // |a.x| + |a.y| + |a.z|
+    uint32_t type;
+};
+__device__ __forceinline__ CurGuard make_cur_guard(const sfh_current& c)
+{
+    CurGuard g;
+    for (int k = 0; k < 3; ++k) { g.a[k] = (float)c.a[k]; g.n[k] = (float)c.n[k]; }
+    const double r = c.type == SFH_CURRENT_PIPE ? fmax(c.r1, c.r2) : c.r1;
+    g.r_hi = __double2float_ru(r);
+    g.l_hi = __double2float_ru(c.l);
+    g.a_abs = fabsf(g.a[0]) + fabsf(g.a[1]) + fabsf(g.a[2]);
+    g.type = c.type;
+    return g;
+}
+// true: the field is certainly zero at every point within `rho` of p. With t = (q-a).n and d = |(q-a) x n| (|n| = 1), moving q
+// by at most rho moves t and d by at most rho; the fp32 evaluation at p is off by far less than E = 2e-5 (|p-a|_1 + |a|_1)
+// (operand rounding 6e-8 |a|, a dozen roundings at 6e-8 of |p-a|, |n| = 1 to 1e-7).
+__device__ __forceinline__ bool cur_certainly_zero(const CurGuard& g, F3 p, float rho)
+{
+    if (g.type == SFH_CURRENT_UNIFORM) return false;
+    const float x = p.x - g.a[0], y = p.y - g.a[1], z = p.z - g.a[2];
+    const float E = 2e-5f * (fabsf(x) + fabsf(y) + fabsf(z) + g.a_abs) + 1e-30f + rho;
+    const float t = x * g.n[0] + y * g.n[1] + z * g.n[2];
+    if (t < -E) return true; // behind the outlet / before the inlet
+    const float cx = y * g.n[2] - z * g.n[1], cy = z * g.n[0] - x * g.n[2], cz = x * g.n[1] - y * g.n[0];
+    const float d = sqrtf(cx * cx + cy * cy + cz * cz);
+    if (g.type == SFH_CURRENT_JET) return d - E > 0.2f * (t + E) + g.r_hi; // r_ = (t + 5 r) / 5 <= 0.2 (t + E) + r_hi
+    return t > g.l_hi + E || d - E > g.r_hi; // beyond the outlet, or outside the widest section
+}
+// Warp-collective: bit i set = Jet / Pipe field i may be non-zero somewhere in the sphere (centre p, radius rho); bits of
+// Uniform fields stay clear (their sum is position-independent and precomputed by k_prologue). n_cur <= 64.
+__device__ __forceinline__ uint64_t chunk_current_mask(const CurGuard* guard, uint32_t n_cur, F3 p, float rho)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t hi = min(lane + 32u, SFH_MAX_CURRENTS - 1u);
+    const bool lo_may = lane < n_cur && guard[lane].type != SFH_CURRENT_UNIFORM && !cur_certainly_zero(guard[lane], p, rho);
+    const bool hi_may = lane + 32u < n_cur && guard[hi].type != SFH_CURRENT_UNIFORM && !cur_certainly_zero(guard[hi], p, rho);
+    return (uint64_t)__ballot_sync(0xffffffffu, lo_may) | ((uint64_t)__ballot_sync(0xffffffffu, hi_may) << 32);
+}
+
+// Ocean::GetFluidVelocity(glm::vec3) with the chunk mask: Uniform fields and the Jet / Pipe fields that can reach the chunk,
+// in list order. Leaving out a field whose value is (+0, +0, +0) cannot change the sum: it starts at +0 and x + 0 = x.
+// Out of line on purpose: the fp64 field code (exp, pow, sqrt, divisions) would otherwise be scheduled into the per-face
+// loops and cost registers there even for the chunks no field reaches.
+__device__ __noinline__ F3 fluid_velocity_masked(const sfh_current* cur, uint64_t may, uint32_t n_cur, F3 fc)
+{
+    const D3 p = {(double)fc.x, (double)fc.y, (double)fc.z};
+    D3 fv = {0.0, 0.0, 0.0};
+    for (uint32_t i = 0; i < n_cur; ++i)
+        if (cur[i].enabled && (cur[i].type == SFH_CURRENT_UNIFORM || ((may >> i) & 1ull))) fv = fv + current_velocity(cur[i], p);
+    return F3{(float)fv.x, (float)fv.y, (float)fv.z};
+}
+
 // Per-kernel constants of the wave lookup: the reference divides every coordinate by the grid size and recomputes
 // 0.5 / fftSize on every call (OpenGLRealOcean.cpp:283,325-326); same values, computed once.
 struct WaveConst {

@@ -32,7 +32,14 @@ struct StepParams {
     void* partials;
     uint8_t* codes;            // debug: per-face codes, nullptr otherwise
     const uint64_t* code_base; // debug: first code index of each body
+    uint32_t* seg_info;        // k_surface: [0] next segment to hand out (zeroed by k_scan_items), [1] items per segment
 };
+
+// k_surface hands out its work list in SEGMENTS of seg_info[1] consecutive items through an atomic counter: crossing bodies
+// mix dry chunks (dropped after 32 bytes) with clipped and submerged ones, and a static split leaves SMs idle for a third
+// of the kernel. At most SFH_SEG_PER_BLOCK segments per resident block, at least SFH_SEG_MIN items per segment.
+#define SFH_SEG_PER_BLOCK 64u
+#define SFH_SEG_MIN 8u
 
 __device__ __forceinline__ uint32_t block_of_item(uint64_t w, uint64_t G, uint64_t W)
 {
@@ -82,11 +89,12 @@ struct BodyRegs { // hot per-body constants
 
 // Damping block shared by both integrators (SolidEntity.cpp:1661-1683, 1771-1790). acc[0..11] = Fdq Tdq Fdf Tdf.
 template <int CUR>
-__device__ __forceinline__ uint32_t damping_terms(const BodyRegs& B, const sfh_current* s_cur, uint32_t n_cur, F3 fc, F3 fn1,
-                                                  float A, double* acc, uint32_t& epack)
+__device__ __forceinline__ uint32_t damping_terms(const BodyRegs& B, const sfh_current* s_cur, uint64_t cur_may, uint32_t n_cur, F3 fc,
+                                                  F3 fn1, float A, double* acc, uint32_t& epack)
 {
     uint32_t code = 0;
-    F3 fluid = CUR ? fluid_velocity_general(s_cur, n_cur, fc) : B.cur;
+    // no Jet / Pipe field reaches this chunk: the sum of the enabled Uniform fields, narrowed once by k_prologue
+    F3 fluid = (CUR && cur_may) ? fluid_velocity_masked(s_cur, cur_may, n_cur, fc) : B.cur;
     F3 r = fc - B.p;
     F3 vc = fluid - (B.v + cross(B.omega, r));
     float vc_n = dot(vc, fn1);
@@ -120,11 +128,13 @@ __device__ __forceinline__ void load_body(BodyDev* sb, const BodyDev* __restrict
     for (uint32_t i = threadIdx.x; i < sizeof(BodyDev) / 4; i += SFH_BLOCK) d[i] = __ldg(s + i);
 }
 
-__device__ __forceinline__ void stage_currents(sfh_current* s_cur, const OceanDev* __restrict__ ocean, uint32_t n_cur)
+// current parameters and their fp32 pre-test records into shared memory (published by the caller's next block barrier)
+__device__ __forceinline__ void stage_currents(sfh_current* s_cur, CurGuard* s_guard, const OceanDev* __restrict__ ocean, uint32_t n_cur)
 {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(ocean->currents);
     uint32_t* d = reinterpret_cast<uint32_t*>(s_cur);
-    for (uint32_t i = threadIdx.x; i < n_cur * (uint32_t)(sizeof(sfh_current) / 4); i += SFH_BLOCK) d[i] = __ldg(s + i);
+    for (uint32_t i = threadIdx.x; i < n_cur * (uint32_t)(sizeof(sfh_current) / 4); i += blockDim.x) d[i] = __ldg(s + i);
+    for (uint32_t i = threadIdx.x; i < n_cur; i += blockDim.x) s_guard[i] = make_cur_guard(ocean->currents[i]);
 }
 
 // 3 x 10-bit event counters (degenerate | quadratic << 10 | skin << 20) -> shared u32 counters
@@ -166,20 +176,19 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
     __shared__ double s_red[SFH_BLOCK / 32][SFH_NACC_SURF];
     __shared__ uint32_t s_cnt[12]; // [0..2] degenerate quadratic skin, [4..11] classes
     __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
+    __shared__ CurGuard s_guard[CUR ? SFH_MAX_CURRENTS : 1];
 
     const uint32_t tid = threadIdx.x;
     // effective grid = min(launched blocks, work items): every participating block owns >= 1 item, so the
     // epilogue's [first block, last block] range of a body never contains a block that wrote no record
-    const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x, W);
-    if (blockIdx.x >= G) return;
+    __shared__ uint32_t s_seg;
+    const uint32_t W = P.item_off[P.n_bodies], SC = P.seg_info[1];
     ItemWalk it;
-    it.w = (uint32_t)((uint64_t)blockIdx.x * W / G);
-    it.w1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * W / G);
     it.s = 0;
     it.parity = 0;
 
     const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
-    if (CUR) stage_currents(s_cur, P.ocean, n_cur);
+    if (CUR) stage_currents(s_cur, s_guard, P.ocean, n_cur);
     if (tid < 12) s_cnt[tid] = 0;
     const WavesDev wv = P.waves;
     const float hmax = WAVES ? __ldg(wv.hmax) : 0.f;
@@ -191,22 +200,19 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
     uint32_t epack = 0, since_spill = 0;
     uint64_t cpack = 0;
 
-    it.b = body_of_item(P.item_off, P.n_bodies, it.w);
-    it.b_begin = P.item_off[it.b];
-    it.b_end = P.item_off[it.b + 1];
-    load_body(&s_body, P.bodies + it.b);
-    const PipeAddr pa = pipe_init(s_pipe); // includes the barrier that publishes s_body
-    if (tid == 0) walk_issue_first(pa, it, s_body);
+    const PipeAddr pa = pipe_init(s_pipe); // includes a block barrier (publishes s_cur / s_guard / s_cnt)
+    uint32_t seg = 0;
     BodyRegs B;
     F3 p0;
     bool buoy, damp;
-    float zrow; // >= |row z of T_C|
+    float zrow;  // >= |row z of T_C|
+    float rnorm; // >= the 2-norm of the linear part of T_C (Frobenius norm)
 
     auto flush = [&](uint32_t body) {
         spill_epack(epack, s_cnt);
         spill_cpack(cpack, s_cnt + 4);
         since_spill = 0;
-        PartialSurf* rec = reinterpret_cast<PartialSurf*>(P.partials) + (blockIdx.x + body);
+        PartialSurf* rec = reinterpret_cast<PartialSurf*>(P.partials) + (seg + body); // one record per (segment, body)
         __syncthreads();
         block_reduce_store<SFH_NACC_SURF>(acc, s_red, rec->a);
         if (tid < 3) (&rec->n_degenerate)[tid] = s_cnt[tid];
@@ -223,10 +229,28 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
         buoy = (s_body.flags & BF_BUOYANCY) != 0;
         damp = (s_body.flags & BF_DAMPING) != 0;
         zrow = sqrtf(s_body.R[6] * s_body.R[6] + s_body.R[7] * s_body.R[7] + s_body.R[8] * s_body.R[8]) * 1.000001f;
+        float fro = 0.f;
+        for (int k = 0; k < 9; ++k) fro += s_body.R[k] * s_body.R[k];
+        rnorm = sqrtf(fro) * 1.000001f;
     };
+
+    for (;;) { // segments
+    __syncthreads(); // the previous segment is flushed and s_seg has been read by everyone
+    if (tid == 0) s_seg = atomicAdd(&P.seg_info[0], 1u);
+    __syncthreads();
+    seg = s_seg;
+    if ((uint64_t)seg * SC >= W) break;
+    it.w = seg * SC;
+    it.w1 = min(it.w + SC, W);
+    it.b = body_of_item(P.item_off, P.n_bodies, it.w);
+    it.b_begin = P.item_off[it.b];
+    it.b_end = P.item_off[it.b + 1];
+    load_body(&s_body, P.bodies + it.b);
+    __syncthreads();
+    if (tid == 0) walk_issue_first(pa, it, s_body);
     fetch_regs();
 
-    for (;;) {
+    for (;;) { // chunks of the segment
         pipe_wait(pa, it.s, (it.parity >> it.s) & 1u);
         it.parity ^= 1u << it.s;
         const ChunkView cv = chunk_view(s_pipe.buf[it.s]);
@@ -238,6 +262,9 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
         const F3 cw = xform(s_body.R, s_body.t, cv.sphere.x, cv.sphere.y, cv.sphere.z);
         const float reach = fabsf(s_body.t[2]) + fabsf(cv.sphere.x) + fabsf(cv.sphere.y) + fabsf(cv.sphere.z) + cv.sphere.w;
         const bool dry = cw.z + zrow * cv.sphere.w + hmax + (4e-6f * reach + 1e-6f) < 0.f;
+        // which Jet / Pipe fields can reach this chunk at all (every face centroid lies inside the sphere)
+        const uint64_t cur_may =
+            CUR ? chunk_current_mask(s_guard, n_cur, cw, rnorm * cv.sphere.w + (4e-6f * (reach + fabsf(s_body.t[0]) + fabsf(s_body.t[1])) + 1e-6f)) : 0ull;
 
         __syncthreads(); // every thread is done with the previous chunk: s_v and the other staging buffer are free
         const uint8_t* nsrc = nullptr;
@@ -334,7 +361,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
                         acc[12] = dadd(acc[12], (double)Fbi.x); acc[13] = dadd(acc[13], (double)Fbi.y); acc[14] = dadd(acc[14], (double)Fbi.z);
                         acc[15] = dadd(acc[15], (double)Tbi.x); acc[16] = dadd(acc[16], (double)Tbi.y); acc[17] = dadd(acc[17], (double)Tbi.z);
                     }
-                    if (damp) code |= damping_terms<CUR>(B, s_cur, n_cur, fc, fn1, A, acc, epack);
+                    if (damp) code |= damping_terms<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, acc, epack);
                     acc[18] = dadd(acc[18], (double)A); // SolidEntity.cpp:1686
                 }
             }
@@ -356,7 +383,9 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
             fetch_regs();
         }
     }
+    it.s ^= 1; // the next segment's first copy goes to the other staging buffer
     flush(it.b);
+    } // segments
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -407,10 +436,11 @@ __global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
 
     // position-independent part of Ocean::GetFluidVelocity (Ocean.cpp:183-201)
     float cur[3] = {0.f, 0.f, 0.f};
-    if (oc->currents_enabled && !oc->cur_general) {
+    if (oc->currents_enabled) {
         D3 fv = {0.0, 0.0, 0.0};
         for (uint32_t k = 0; k < oc->n_currents; ++k)
-            if (oc->currents[k].enabled) fv = fv + D3{oc->currents[k].a[0], oc->currents[k].a[1], oc->currents[k].a[2]};
+            if (oc->currents[k].enabled && oc->currents[k].type == SFH_CURRENT_UNIFORM)
+                fv = fv + D3{oc->currents[k].a[0], oc->currents[k].a[1], oc->currents[k].a[2]};
         cur[0] = (float)fv.x; cur[1] = (float)fv.y; cur[2] = (float)fv.z;
     }
 
@@ -461,7 +491,8 @@ __global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
 }
 
 // In-place exclusive scan of the per-body chunk counts (n_bodies entries -> n_bodies + 1 offsets). One block.
-__global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies)
+__global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies, uint32_t* seg_info,
+                                                     uint32_t grid_surf)
 {
     __shared__ uint32_t s_warp[2][32];
     __shared__ uint32_t s_carry[2];
@@ -496,7 +527,14 @@ __global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t
         if (tid == 0) { s_carry[0] += s_warp[0][31]; s_carry[1] += s_warp[1][31]; }
         __syncthreads();
     }
-    if (tid == 0) { off_sub[n_bodies] = s_carry[0]; off_surf[n_bodies] = s_carry[1]; }
+    if (tid == 0) {
+        off_sub[n_bodies] = s_carry[0];
+        off_surf[n_bodies] = s_carry[1];
+        // k_surface's segment size: at most SFH_SEG_PER_BLOCK segments per resident block
+        const uint32_t cap = max(grid_surf, 1u) * SFH_SEG_PER_BLOCK;
+        seg_info[0] = 0;
+        seg_info[1] = max(SFH_SEG_MIN, (s_carry[1] + cap - 1) / cap);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -511,7 +549,8 @@ struct EpilogueParams {
     const uint32_t* off_surf;
     const PartialSub* part_sub;
     const PartialSurf* part_surf;
-    uint32_t grid_sub, grid_surf;
+    uint32_t grid_sub;
+    const uint32_t* seg_info; // [1] = items per k_surface segment
     uint32_t aero;
     sfh_info* out;
 };
@@ -600,8 +639,7 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
     } else if (kind == KIND_SURFACE) {
         const uint32_t o0 = P.off_surf[b], o1 = P.off_surf[b + 1];
         if (o1 > o0) {
-            const uint64_t W = P.off_surf[P.n_bodies], G = min((uint64_t)P.grid_surf, W);
-            const uint32_t k0 = block_of_item(o0, G, W), k1 = block_of_item(o1 - 1, G, W);
+            const uint32_t SC = P.seg_info[1], k0 = o0 / SC, k1 = (o1 - 1) / SC; // segments that overlap this body's items
             for (uint32_t k = k0 + lane; k <= k1; k += 32) {
                 const PartialSurf& r = P.part_surf[k + b];
 #pragma unroll

@@ -57,13 +57,13 @@ struct BodyP2 { // per-body constants broadcast to both lanes
 // Damping block for a pair of faces (SolidEntity.cpp:1771-1790 / 1661-1683). mA/mB: the face exists and is not
 // degenerate. Returns SFH_FACE_QUADRATIC / SFH_FACE_SKIN bits for A in bits 0..7 and for B in bits 8..15.
 template <int CUR>
-__device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_current* s_cur, uint32_t n_cur, V3P fc, V3P fn1, P2 A,
-                                                 bool mA, bool mB, double* acc, uint32_t& epack)
+__device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_current* s_cur, uint64_t cur_may, uint32_t n_cur, V3P fc,
+                                                 V3P fn1, P2 A, bool mA, bool mB, double* acc, uint32_t& epack)
 {
-    V3P fluid = B.cur;
-    if (CUR) {
-        const F3 fa = fluid_velocity_general(s_cur, n_cur, F3{lo(fc.x), lo(fc.y), lo(fc.z)});
-        const F3 fb = fluid_velocity_general(s_cur, n_cur, F3{hi(fc.x), hi(fc.y), hi(fc.z)});
+    V3P fluid = B.cur; // sum of the enabled Uniform fields; complete when no Jet / Pipe field reaches the chunk
+    if (CUR && cur_may) {
+        const F3 fa = fluid_velocity_masked(s_cur, cur_may, n_cur, F3{lo(fc.x), lo(fc.y), lo(fc.z)});
+        const F3 fb = fluid_velocity_masked(s_cur, cur_may, n_cur, F3{hi(fc.x), hi(fc.y), hi(fc.z)});
         fluid = V3P{pk(fa.x, fb.x), pk(fa.y, fb.y), pk(fa.z, fb.z)};
     }
     const V3P r = fc - B.p;
@@ -101,13 +101,13 @@ __device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_curr
 // tests dot(fn1, vn), not dot(vc, fn1), and scales by vn.length() — glm's COMPONENT COUNT, 3 — through
 // glm/gtx/scalar_multiplication.hpp (vec3 * int -> vec3 *= 3.f); both are kept. acc[0..5] = Fda Tda.
 template <int CUR>
-__device__ __forceinline__ uint32_t aero_pair(const BodyP2& B, const sfh_current* s_cur, uint32_t n_cur, V3P fc, V3P fn1, P2 A,
-                                              bool mA, bool mB, double* acc, uint32_t& epack)
+__device__ __forceinline__ uint32_t aero_pair(const BodyP2& B, const sfh_current* s_cur, uint64_t cur_may, uint32_t n_cur, V3P fc,
+                                              V3P fn1, P2 A, bool mA, bool mB, double* acc, uint32_t& epack)
 {
-    V3P fluid = B.cur;
-    if (CUR) {
-        const F3 fa = fluid_velocity_general(s_cur, n_cur, F3{lo(fc.x), lo(fc.y), lo(fc.z)});
-        const F3 fb = fluid_velocity_general(s_cur, n_cur, F3{hi(fc.x), hi(fc.y), hi(fc.z)});
+    V3P fluid = B.cur; // sum of the enabled Uniform fields; complete when no Jet / Pipe field reaches the chunk
+    if (CUR && cur_may) {
+        const F3 fa = fluid_velocity_masked(s_cur, cur_may, n_cur, F3{lo(fc.x), lo(fc.y), lo(fc.z)});
+        const F3 fb = fluid_velocity_masked(s_cur, cur_may, n_cur, F3{hi(fc.x), hi(fc.y), hi(fc.z)});
         fluid = V3P{pk(fa.x, fb.x), pk(fa.y, fb.y), pk(fa.z, fb.z)};
     }
     const V3P r = fc - B.p;
@@ -213,13 +213,12 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
 {
     __shared__ WarpStage s_stage[SFH_SUB_WPB];
     __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
+    __shared__ CurGuard s_guard[CUR ? SFH_MAX_CURRENTS : 1];
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
     if constexpr (CUR != 0) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.ocean->currents);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(s_cur);
-        for (uint32_t i = threadIdx.x; i < n_cur * (uint32_t)(sizeof(sfh_current) / 4); i += SFH_SUB_THREADS) dst[i] = __ldg(src + i);
+        stage_currents(s_cur, s_guard, P.ocean, n_cur);
         __syncthreads(); // the only block barrier of the kernel, before any warp can leave
     }
     const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x * SFH_SUB_WPB, W);
@@ -249,7 +248,13 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
     if (lane == 0) walk_issue_first(pa, it, s_body);
 
     BodyP2 B;
+    float rnorm = 0.f; // >= the 2-norm of the linear part of T_C (Frobenius norm)
     auto fetch_regs = [&]() {
+        if (CUR) {
+            float fro = 0.f;
+            for (int k = 0; k < 9; ++k) fro += s_body.R[k] * s_body.R[k];
+            rnorm = sqrtf(fro) * 1.000001f;
+        }
         B.p = V3P{pk1(s_body.p[0]), pk1(s_body.p[1]), pk1(s_body.p[2])};
         B.v = V3P{pk1(s_body.v[0]), pk1(s_body.v[1]), pk1(s_body.v[2])};
         B.omega = V3P{pk1(s_body.omega[0]), pk1(s_body.omega[1]), pk1(s_body.omega[2])};
@@ -297,6 +302,15 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
         }
         __syncwarp();
 
+        // which Jet / Pipe fields can reach this chunk at all (every face centroid lies inside the chunk's bounding sphere)
+        uint64_t cur_may = 0;
+        if (CUR) {
+            const F3 cw = xform(s_body.R, s_body.t, cv.sphere.x, cv.sphere.y, cv.sphere.z);
+            const float reach = fabsf(s_body.t[0]) + fabsf(s_body.t[1]) + fabsf(s_body.t[2]) + fabsf(cv.sphere.x) + fabsf(cv.sphere.y) +
+                                fabsf(cv.sphere.z) + cv.sphere.w;
+            cur_may = chunk_current_mask(s_guard, n_cur, cw, rnorm * cv.sphere.w + (4e-6f * reach + 1e-6f));
+        }
+
         const uint32_t nf = cv.nf;
 #pragma unroll 1
         for (uint32_t base = 0; base < nf; base += 64u) { // faces base+lane and base+lane+32 side by side
@@ -334,13 +348,13 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
                 if (fast) {
                     const V3P fn1 = normalize_fast(fn, len);
                     const V3P fc = {ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)};
-                    code = AERO ? aero_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack)
-                                : damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
+                    code = AERO ? aero_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack)
+                                : damping_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack);
                 } else { // operands outside the proven range: hardware divisions
                     V3P fn1, fc;
                     normalize_centroid_slow(fn, len, csum, fn1, fc);
-                    code = AERO ? aero_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack)
-                                : damping_pair<CUR>(B, s_cur, n_cur, fc, fn1, A, mA, mB, acc, epack);
+                    code = AERO ? aero_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack)
+                                : damping_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack);
                 }
             }
             if (DEBUG) {

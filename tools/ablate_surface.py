@@ -15,3 +15,7 @@ sc.ocean.DisableCurrents(); run("waves, no currents")
 sc.ocean.EnableCurrents(); sc.ocean.setWaves(None); run("flat, Jet+Pipe")
 sc.ocean.DisableCurrents(); run("flat, no currents")
 st2 = st.copy(); st2["flags"] = 1; run("flat, no currents (same)")
+# localized fields: the same Jet, the Pipe moved 100 m away -> every chunk is outside both (chunk-level pre-test)
+from stonefish_b200.hydro import Jet, Pipe
+sc.ocean.currents = [Jet((0.0, 0.0, 1.0), (0.0, 1.0, 0.0), 0.3, 5.0), Pipe((-20.0, 100.0, 2.0), (20.0, 100.0, 2.0), 3.0, 5.0, 2.0, 2.0)]
+sc.ocean.EnableCurrents(); run("flat, Jet + far Pipe")
