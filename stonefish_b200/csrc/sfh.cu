@@ -334,9 +334,15 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     pp.states = d_states; pp.meshes = ctx->d_meshes.p; pp.n_meshes = (uint32_t)ctx->meshes.size(); pp.n_bodies = n;
     pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;
     pp.off_sub = ctx->d_off_sub.p; pp.off_surf = ctx->d_off_surf.p; pp.status = ctx->d_status.p; pp.aero = plan.aero ? 1u : 0u;
-    k_prologue<<<(n + 127) / 128, 128, 0, ctx->stream>>>(pp);
-    k_scan_items<<<1, 1024, 0, ctx->stream>>>(ctx->d_off_sub.p, ctx->d_off_surf.p, n, ctx->d_status.p + 2, (uint32_t)g_surf);
-    uint32_t launches = 2;
+    uint32_t launches;
+    if (n <= 1024) {
+        k_prologue_scan<<<1, 1024, 0, ctx->stream>>>(pp, ctx->d_status.p + 2, (uint32_t)g_surf);
+        launches = 1;
+    } else {
+        k_prologue<<<(n + 127) / 128, 128, 0, ctx->stream>>>(pp);
+        k_scan_items<<<1, 1024, 0, ctx->stream>>>(ctx->d_off_sub.p, ctx->d_off_surf.p, n, ctx->d_status.p + 2, (uint32_t)g_surf);
+        launches = 2;
+    }
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 
     StepParams sp;

@@ -289,9 +289,7 @@ __device__ __forceinline__ uint64_t chunk_current_mask(const CurGuard* guard, ui
 
 // Ocean::GetFluidVelocity(glm::vec3) with the chunk mask: Uniform fields and the Jet / Pipe fields that can reach the chunk,
 // in list order. Leaving out a field whose value is (+0, +0, +0) cannot change the sum: it starts at +0 and x + 0 = x.
-// Out of line on purpose: the fp64 field code (exp, pow, sqrt, divisions) would otherwise be scheduled into the per-face
-// loops and cost registers there even for the chunks no field reaches.
-__device__ __noinline__ F3 fluid_velocity_masked(const sfh_current* cur, uint64_t may, uint32_t n_cur, F3 fc)
+__device__ __forceinline__ F3 fluid_velocity_masked(const sfh_current* cur, uint64_t may, uint32_t n_cur, F3 fc)
 {
     const D3 p = {(double)fc.x, (double)fc.y, (double)fc.z};
     D3 fv = {0.0, 0.0, 0.0};

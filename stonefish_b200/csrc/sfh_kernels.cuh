@@ -38,8 +38,8 @@ struct StepParams {
 // k_surface hands out its work list in SEGMENTS of seg_info[1] consecutive items through an atomic counter: crossing bodies
 // mix dry chunks (dropped after 32 bytes) with clipped and submerged ones, and a static split leaves SMs idle for a third
 // of the kernel. At most SFH_SEG_PER_BLOCK segments per resident block, at least SFH_SEG_MIN items per segment.
-#define SFH_SEG_PER_BLOCK 64u
-#define SFH_SEG_MIN 8u
+#define SFH_SEG_PER_BLOCK 16u
+#define SFH_SEG_MIN 1u
 
 __device__ __forceinline__ uint32_t block_of_item(uint64_t w, uint64_t G, uint64_t W)
 {
@@ -427,10 +427,8 @@ __device__ inline uint32_t check_body_fluid_position(bool waves, const WavesDev&
     return under == 0 ? SFH_POS_OUTSIDE : (under == 8 ? SFH_POS_INSIDE : SFH_POS_CROSSING);
 }
 
-__global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
+__device__ __forceinline__ void prologue_body(const PrologueParams& P, uint32_t i)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_bodies) return;
     const OceanDev* __restrict__ oc = P.ocean;
     const bool waves = oc->has_waves != 0;
 
@@ -490,9 +488,14 @@ __global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
     P.off_surf[i] = (kind == KIND_SURFACE) ? bd.n_chunks : 0u;
 }
 
+__global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_bodies) prologue_body(P, i);
+}
+
 // In-place exclusive scan of the per-body chunk counts (n_bodies entries -> n_bodies + 1 offsets). One block.
-__global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies, uint32_t* seg_info,
-                                                     uint32_t grid_surf)
+__device__ __forceinline__ void scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies, uint32_t* seg_info, uint32_t grid_surf)
 {
     __shared__ uint32_t s_warp[2][32];
     __shared__ uint32_t s_carry[2];
@@ -535,6 +538,18 @@ __global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t
         seg_info[0] = 0;
         seg_info[1] = max(SFH_SEG_MIN, (s_carry[1] + cap - 1) / cap);
     }
+}
+__global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies, uint32_t* seg_info,
+                                                     uint32_t grid_surf)
+{
+    scan_items(off_sub, off_surf, n_bodies, seg_info, grid_surf);
+}
+// Steps of at most 1024 bodies: prologue and scan in one launch (single-body steps are launch-latency bound)
+__global__ void __launch_bounds__(1024) k_prologue_scan(PrologueParams P, uint32_t* seg_info, uint32_t grid_surf)
+{
+    if (threadIdx.x < P.n_bodies) prologue_body(P, threadIdx.x);
+    __syncthreads();
+    scan_items(P.off_sub, P.off_surf, P.n_bodies, seg_info, grid_surf);
 }
 
 // ---------------------------------------------------------------------------------------------
