@@ -300,11 +300,16 @@ __global__ void __launch_bounds__(SFH_BLOCK, 4) k_surface(StepParams P)
                 // waterline point on the edge from the submerged vertex pu (du >= 0) to the dry vertex pa (da < 0)
                 auto clip = [](F3 pa, F3 pu, float da, float du) { return pu + (pa - pu) * fdiv(du, fadd(fabsf(da), du)); };
                 // tetrahedron (p0, a, b, c) of the submerged volume (SolidEntity.cpp:1371-1377 and twins)
+                // Vsub / CBsub only reach an output through the buoyancy block (SolidEntity.cpp:1690-1708), and CBsub only on a flat
+                // sea (:1703-1706): they are not accumulated where the reference computes them in vain.
                 auto tetra = [&](F3 pa, F3 pb, F3 pc) {
-                    F3 cg = ((pa + pb) + pc) * 0.25f; // "/ 4.f": an exact scaling either way
+                    if (!buoy) return;
                     float v6 = dot(pa, cross(pb, pc));
-                    F3 m = cg * v6;
-                    acc[20] = dadd(acc[20], (double)m.x); acc[21] = dadd(acc[21], (double)m.y); acc[22] = dadd(acc[22], (double)m.z);
+                    if (!WAVES) {
+                        F3 cg = ((pa + pb) + pc) * 0.25f; // "/ 4.f": an exact scaling either way
+                        F3 m = cg * v6;
+                        acc[20] = dadd(acc[20], (double)m.x); acc[21] = dadd(acc[21], (double)m.y); acc[22] = dadd(acc[22], (double)m.z);
+                    }
                     acc[19] = dadd(acc[19], (double)v6);
                 };
                 F3 p4 = p1, fv1, fv2, fv3, fv4;

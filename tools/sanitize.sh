@@ -1,6 +1,7 @@
 #!/bin/bash
-# compute-sanitizer memcheck + racecheck + synccheck of every kernel (prologue, scan, submerged, surface with waves and
-# Jet/Pipe currents, epilogue) through the C++ host mirror demo on a small mixed scene. Run on the GPU box:
+# compute-sanitizer memcheck + racecheck + synccheck of every kernel (prologue/scan, submerged and its aerodynamic variant,
+# surface flat and on a device-generated wave field with Jet/Pipe currents, epilogue, wave producer, cables) through the C++
+# host mirror demo on a small mixed scene. Run on the GPU box:
 #   bash tools/sanitize.sh > gpurun_out/sanitize.log
 set -e
 cd "$(dirname "$0")/.."
@@ -16,5 +17,5 @@ print("scene written:", sc.n_bodies, "bodies", sc.faces_per_step(), "faces")
 PY
 for tool in memcheck racecheck synccheck; do
   echo "== compute-sanitizer --tool $tool"
-  compute-sanitizer --tool $tool --error-exitcode 9 stonefish_b200/host/demo_fluid_dynamics /tmp/sanitize_scene.bin /tmp/sanitize_out.bin 2 2>&1 | tail -4
+  compute-sanitizer --tool $tool --error-exitcode 9 stonefish_b200/host/demo_fluid_dynamics /tmp/sanitize_scene.bin /tmp/sanitize_out.bin 2 /tmp/sanitize_aero.bin 1.0 /tmp/sanitize_waves.bin /tmp/sanitize_cable.bin 2>&1 | tail -4
 done
