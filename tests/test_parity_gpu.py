@@ -304,3 +304,47 @@ def test_ragged_and_chunk_boundary_meshes(ctx, oracle):
     err, where = max_rel_err(gi, ri)
     assert err <= REL_TOL, (err, where)
     assert gi["n_faces"].tolist() == [meshes_[i].n_faces for i in body_mesh]
+
+
+@pytest.mark.parametrize("waves", [False, True])
+def test_dry_chunk_skip_and_field_masks_are_exact(ctx, oracle, waves):
+    """k_surface drops chunks whose bounding sphere lies above the highest possible surface and skips Jet/Pipe fields that
+    cannot reach a chunk's sphere. Both are conservative tests, so codes and sums must stay what the oracle says — also for a
+    NON-RIGID T_C (scaled, sheared basis: the sphere bound uses row / Frobenius norms, not |R| = 1), for hulls standing
+    several wave heights out of the water (most chunks dropped) and for bodies straddling the edge of a jet cone and a pipe."""
+    from stonefish_b200 import meshes as M
+    from stonefish_b200.hydro import Jet, Ocean, Pipe, Uniform, make_transform, new_body_states, quat_to_basis
+
+    meshes_ = [M.box(0.6, 0.4, 6.0, 4), M.uv_ellipsoid(3.0, 0.5, 0.4, 120, 61), M.icosphere(0.5, 4)]
+    ocean = Ocean(1000.0, 9.81)
+    if waves:
+        ocean.setWaves(scenes.wave_field())
+    ocean.AddVelocityField(Uniform((0.2, -0.1, 0.0)))
+    ocean.AddVelocityField(Jet((0.0, -3.0, 0.5), (0.0, 1.0, 0.0), 0.3, 5.0))
+    ocean.AddVelocityField(Pipe((-6.0, 4.0, 1.0), (6.0, 4.0, 1.0), 0.8, 1.2, 2.0, 2.0))
+    ocean.AddVelocityField(Uniform((0.0, 0.05, 0.01)))
+    ocean.EnableCurrents()
+    poses = [  # (mesh, basis, origin)
+        (0, np.eye(3), (0.0, 0.0, -1.0)),                                   # a spar: 4 m of it dry
+        (0, quat_to_basis(scenes.euler_zyx_quat(0.3, 0.4, -0.2)), (2.0, 1.0, -0.5)),
+        (1, np.diag([1.5, 0.7, 2.0]) @ quat_to_basis(scenes.euler_zyx_quat(0.2, 0.1, 0.3)), (0.3, 0.0, 0.1)),   # scaled: crosses the jet cone
+        (1, np.array([[1.0, 0.3, 0.0], [0.0, 1.0, 0.2], [0.1, 0.0, 1.0]]), (0.0, 3.6, 0.2)),                    # sheared: grazes the pipe wall
+        (2, 3.0 * np.eye(3), (-3.0, -2.0, 0.8)),                                                                # uniformly scaled
+        (2, np.eye(3), (0.1, -1.0, 0.45)),                                                                      # inside the jet
+    ]
+    st = new_body_states(len(poses))
+    body_mesh = []
+    for k, (mi, basis, org) in enumerate(poses):
+        T = make_transform(np.asarray(basis, dtype=np.float64), org)
+        st["T_CG"][k], st["T_C"][k] = make_transform(None, org), T
+        st["mode"][k], st["flags"][k] = 2, 3
+        st["v"][k], st["omega"][k] = (0.4, -0.2, 0.1), (0.05, 0.1, -0.02)
+        body_mesh.append(mi)
+    sc = scenes.Scene("sphere_bounds", meshes_, np.array(body_mesh), ocean, st)
+    gi, gc, ri, rc = run_both(ctx, oracle, sc)
+    assert_counts_equal(gi, ri)
+    assert np.array_equal(gc & 15, rc & 15) and (gc != rc).sum() <= 1  # exp/pow: <= 1 drag flag in ~1e8 (DESIGN.md 5.4)
+    err, where = max_rel_err(gi, ri)
+    assert err <= REL_TOL, (err, where)
+    assert gi["class_count"][0][0] > 0.5 * meshes_[0].n_faces  # most of the spar is dry
+    assert (gi["class_count"][:, 1:7].sum(axis=1) > 0).all()   # every body really crosses the surface
