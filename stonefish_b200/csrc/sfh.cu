@@ -61,7 +61,8 @@ struct sfh_ctx {
     PinBuf h_mesh_table;
 
     // waves
-    DevBuf<float> d_wave_rgba, d_wave_ch0, d_wave_ch1, d_wave_hmax;
+    DevBuf<float> d_wave_rgba, d_wave_ch0, d_wave_ch1;
+    DevBuf<uint32_t> d_wave_hmax;
     PinBuf h_wave;
     WavesDev waves{nullptr, nullptr, 0, 0.f, 0.f, nullptr};
     bool have_waves = false;
@@ -698,10 +699,10 @@ int sfh_waves_upload(sfh_ctx* ctx, const sfh_waves* w)
         src = ctx->h_wave.p;
     }
     CU(ctx, cudaMemcpyAsync(ctx->d_wave_rgba.p, src, have * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ensure_dev(ctx, ctx->d_wave_hmax, 2)) != SFH_OK) return rc;
+    CU(ctx, cudaMemsetAsync(ctx->d_wave_hmax.p, 0, 2 * sizeof(uint32_t), ctx->stream));
     k_waves_planar<<<(unsigned)((texels + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_wave_rgba.p, (uint32_t)have, (uint32_t)texels,
-                                                                               ctx->d_wave_ch0.p, ctx->d_wave_ch1.p);
-    if ((rc = ensure_dev(ctx, ctx->d_wave_hmax, 1)) != SFH_OK) return rc;
-    k_wave_hmax<<<1, 1024, 0, ctx->stream>>>(ctx->d_wave_ch0.p, ctx->d_wave_ch1.p, (uint32_t)texels, ctx->d_wave_hmax.p);
+                                                                               ctx->d_wave_ch0.p, ctx->d_wave_ch1.p, ctx->d_wave_hmax.p);
     CU(ctx, cudaGetLastError());
     ctx->waves.hmax = ctx->d_wave_hmax.p;
     ctx->waves.ch0 = ctx->d_wave_ch0.p;
@@ -768,11 +769,11 @@ int sfh_wavegen_simulate(sfh_ctx* ctx, float t)
     k_wave_rows<<<grid, N, smem, ctx->stream>>>(G, t);
     k_wave_cols<<<grid, N, smem, ctx->stream>>>(G);
     // the per-face kernels read planar copies of channels 0 and 1 of layer 0 (+ one row and one texel of layer 1)
+    if ((rc = ensure_dev(ctx, ctx->d_wave_hmax, 2)) != SFH_OK) return rc;
+    CU(ctx, cudaMemsetAsync(ctx->d_wave_hmax.p, 0, 2 * sizeof(uint32_t), ctx->stream));
     k_waves_planar<<<(unsigned)((texels + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(ctx->d_wg_fft.p),
                                                                                (uint32_t)(texels * 4), (uint32_t)texels, ctx->d_wave_ch0.p,
-                                                                               ctx->d_wave_ch1.p);
-    if ((rc = ensure_dev(ctx, ctx->d_wave_hmax, 1)) != SFH_OK) return rc;
-    k_wave_hmax<<<1, 1024, 0, ctx->stream>>>(ctx->d_wave_ch0.p, ctx->d_wave_ch1.p, (uint32_t)texels, ctx->d_wave_hmax.p);
+                                                                               ctx->d_wave_ch1.p, ctx->d_wave_hmax.p);
     CU(ctx, cudaGetLastError());
     ctx->waves.hmax = ctx->d_wave_hmax.p;
     ctx->waves.ch0 = ctx->d_wave_ch0.p;

@@ -60,7 +60,7 @@ struct WavesDev {
     const float* ch1; // channel 1 (grid 101 m)
     int32_t N;
     float gx, gy;     // gridSizes.x, gridSizes.y
-    const float* hmax; // device scalar: max|ch0| + max|ch1| >= |wave height| anywhere (bilinear = convex combination)
+    const uint32_t* hmax; // device: float bits of max|ch0|, max|ch1|; their sum bounds |wave height| anywhere
 };
 
 // Partial sums written by one thread block for one body.

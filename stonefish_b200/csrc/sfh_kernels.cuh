@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
     if (CUR) stage_currents(s_cur, s_guard, P.ocean, n_cur);
     if (tid < 12) s_cnt[tid] = 0;
     const WavesDev wv = P.waves;
-    const float hmax = WAVES ? __ldg(wv.hmax) : 0.f;
+    const float hmax = WAVES ? __fadd_ru(__uint_as_float(__ldg(wv.hmax)), __uint_as_float(__ldg(wv.hmax + 1))) : 0.f;
     const WaveConst wc = WAVES ? wave_const(wv) : WaveConst{};
 
     double acc[SFH_NACC_SURF];
@@ -769,28 +769,22 @@ __global__ void k_query_velocity(const float* __restrict__ xyz, uint32_t n, cons
 }
 
 // wave field de-interleave: RGBA32F layer 0 (+ spill-over row) -> planar channel 0 / 1
-__global__ void k_waves_planar(const float* __restrict__ rgba, uint32_t n_floats_valid, uint32_t n_texels, float* ch0, float* ch1)
+// Also leaves max|ch0| and max|ch1| in hmax[0..1] (float bits; the caller zeroes them first): their sum bounds the wave
+// height anywhere, because the bilinear lookup is a convex combination of texels.
+__global__ void k_waves_planar(const float* __restrict__ rgba, uint32_t n_floats_valid, uint32_t n_texels, float* ch0, float* ch1,
+                               uint32_t* hmax)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_texels) return;
-    ch0[i] = (4 * i + 0 < n_floats_valid) ? rgba[4 * i + 0] : 0.f;
-    ch1[i] = (4 * i + 1 < n_floats_valid) ? rgba[4 * i + 1] : 0.f;
-}
-
-// bound of the wave height: max|ch0| + max|ch1| over every texel the lookup can touch. One block.
-__global__ void __launch_bounds__(1024) k_wave_hmax(const float* __restrict__ ch0, const float* __restrict__ ch1, uint32_t n_texels, float* out)
-{
-    __shared__ float s_m[2][32];
-    float m0 = 0.f, m1 = 0.f;
-    for (uint32_t i = threadIdx.x; i < n_texels; i += blockDim.x) { m0 = fmaxf(m0, fabsf(ch0[i])); m1 = fmaxf(m1, fabsf(ch1[i])); }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) { m0 = fmaxf(m0, __shfl_down_sync(SFH_FULL, m0, off)); m1 = fmaxf(m1, __shfl_down_sync(SFH_FULL, m1, off)); }
-    if ((threadIdx.x & 31) == 0) { s_m[0][threadIdx.x >> 5] = m0; s_m[1][threadIdx.x >> 5] = m1; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 32; ++w) { m0 = fmaxf(m0, s_m[0][w]); m1 = fmaxf(m1, s_m[1][w]); }
-        *out = __fadd_ru(m0, m1);
+    float a = 0.f, b = 0.f;
+    if (i < n_texels) {
+        a = (4 * i + 0 < n_floats_valid) ? rgba[4 * i + 0] : 0.f;
+        b = (4 * i + 1 < n_floats_valid) ? rgba[4 * i + 1] : 0.f;
+        ch0[i] = a;
+        ch1[i] = b;
     }
+    // |x| as an unsigned integer orders like |x| (NaN sorts above infinity: a NaN texel disables the dry-chunk test)
+    const uint32_t ma = __reduce_max_sync(SFH_FULL, __float_as_uint(a) & 0x7fffffffu), mb = __reduce_max_sync(SFH_FULL, __float_as_uint(b) & 0x7fffffffu);
+    if ((threadIdx.x & 31) == 0) { atomicMax(hmax, ma); atomicMax(hmax + 1, mb); }
 }
 
 } // namespace sfh
