@@ -117,6 +117,9 @@ struct sfh_ctx {
         cudaGraphExec_t exec;
     };
     std::vector<GraphEntry> graphs;
+    // zero-copy results of small steps: the host spins on a sequence number instead of synchronising the stream
+    uint32_t zc_seq = 0;
+    bool zc_pending = false;
     GraphKey last_key{};
     bool last_key_valid = false;
     uint64_t graph_launches = 0;
@@ -171,6 +174,7 @@ int ensure_pin(sfh_ctx* ctx, PinBuf& b, size_t bytes)
     if (b.p) CU(ctx, cudaFreeHost(b.p));
     b.p = nullptr; b.cap = 0;
     CU(ctx, cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
+    std::memset(b.p, 0, cap); // flags and sequence numbers polled by the host start from a known value
     b.cap = cap;
     return SFH_OK;
 }
@@ -210,6 +214,7 @@ int occupancy(sfh_ctx* ctx, K kernel, int* cache, int threads = SFH_BLOCK)
 }
 
 #define SFH_GRAPH_MAX_BODIES 1024u
+#define SFH_ZEROCOPY_MAX_BODIES 64u /* results of steps this small are written straight into pinned host memory */
 
 // Write the ocean record into the pinned staging buffer (no CUDA call after the first) and report whether some
 // enabled current needs the per-face fp64 evaluation.
@@ -269,6 +274,7 @@ struct StepPlan {
     bool host_states = true;     // states/out are host pointers
     bool debug = false;
     bool aero = false;           // sfh_aero_step: the "ocean" is the atmosphere and every body runs the aero face loop
+    bool zero_copy_out = false;  // d_out is pinned HOST memory; the epilogue publishes status + sequence number to h_status
     bool may_sub = true, may_surf = true; // host knows no body can reach the kernel -> skip the launch
     uint64_t chunks_ub = 0;      // upper bound of work items (host variant), 0 = unknown
     uint64_t faces = 0;
@@ -323,9 +329,9 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     if ((rc = ensure_dev(ctx, ctx->d_off_surf, n + 1)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_part_sub, g_sub * SFH_SUB_WPB + n)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_part_surf, n_seg_max + n)) != SFH_OK) return rc;
-    if (!ctx->d_status.p) {
-        if ((rc = ensure_dev(ctx, ctx->d_status, 4)) != SFH_OK) return rc;
-        CU(ctx, cudaMemsetAsync(ctx->d_status.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+    if (!ctx->d_status.p) { // [0] error flags, [1] epilogue blocks finished, [2..3] k_surface segments, [4] zero-copy sequence number
+        if ((rc = ensure_dev(ctx, ctx->d_status, 8)) != SFH_OK) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->d_status.p, 0, 8 * sizeof(uint32_t), ctx->stream));
     }
 
     const bool prof = ctx->profiling;
@@ -385,6 +391,12 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     ep.off_sub = ctx->d_off_sub.p; ep.off_surf = ctx->d_off_surf.p;
     ep.part_sub = ctx->d_part_sub.p; ep.part_surf = ctx->d_part_surf.p;
     ep.grid_sub = (uint32_t)(g_sub * SFH_SUB_WPB); ep.seg_info = ctx->d_status.p + 2; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
+    ep.zc_host = nullptr; ep.zc_dev = ctx->d_status.p;
+    if (plan.zero_copy_out) {
+        void* dp = nullptr;
+        CU(ctx, cudaHostGetDevicePointer(&dp, ctx->h_status.p, 0));
+        ep.zc_host = static_cast<uint32_t*>(dp);
+    }
     k_epilogue<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ep);
     ++launches;
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -455,7 +467,18 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
         sfh_ctx::GraphKey key;
         std::memset(&key, 0, sizeof(key));
         key.n = n; key.n_currents = ocean->n_currents; key.n_meshes = (uint32_t)ctx->meshes.size();
-        key.flags = (general ? 1u : 0u) | (ocean->has_waves ? 2u : 0u) | (plan.may_sub ? 4u : 0u) | (plan.may_surf ? 8u : 0u) | (aero ? 16u : 0u);
+        // Few bodies: the epilogue writes the records straight into the pinned result buffer and then a sequence number the host
+        // spins on — no device-to-host copy nodes and no stream synchronisation on the critical path of a small step.
+        const bool zc = n <= SFH_ZEROCOPY_MAX_BODIES;
+        plan.zero_copy_out = zc;
+        sfh_info* out_target = ctx->d_info.p;
+        if (zc) {
+            void* dp = nullptr;
+            CU(ctx, cudaHostGetDevicePointer(&dp, ctx->h_info.p, 0));
+            out_target = static_cast<sfh_info*>(dp);
+        }
+        key.flags = (general ? 1u : 0u) | (ocean->has_waves ? 2u : 0u) | (plan.may_sub ? 4u : 0u) | (plan.may_surf ? 8u : 0u) | (aero ? 16u : 0u) |
+                    (zc ? 32u : 0u);
         key.chunks_ub = plan.chunks_ub;
         key.d_states = ctx->d_states.p; key.d_info = ctx->d_info.p; key.h_states = ctx->h_states.p; key.h_info = ctx->h_info.p;
         key.h_ocean = ctx->h_ocean.p; key.d_ocean = ctx->d_ocean.p; key.d_meshes = ctx->d_meshes.p; key.d_bodies = ctx->d_bodies.p;
@@ -476,8 +499,8 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
         } else {
             if (capture) CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             cudaError_t e = cudaMemcpyAsync(ctx->d_states.p, ctx->h_states.p, sbytes, cudaMemcpyHostToDevice, ctx->stream);
-            rc = (e == cudaSuccess) ? run_step(ctx, ocean, ctx->d_states.p, n, ctx->d_info.p, plan) : fail(ctx, SFH_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
-            if (rc == SFH_OK) {
+            rc = (e == cudaSuccess) ? run_step(ctx, ocean, ctx->d_states.p, n, out_target, plan) : fail(ctx, SFH_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
+            if (rc == SFH_OK && !zc) {
                 e = cudaMemcpyAsync(ctx->h_info.p, ctx->d_info.p, obytes, cudaMemcpyDeviceToHost, ctx->stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream);
                 if (e != cudaSuccess) rc = fail(ctx, SFH_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
@@ -503,6 +526,7 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
         ctx->pending_codes = nullptr;
         ctx->step_in_flight = true;
         ctx->ev_valid = false;
+        if (zc) { ++ctx->zc_seq; ctx->zc_pending = true; }
         return SFH_OK;
     }
 
@@ -818,7 +842,13 @@ int sfh_sync(sfh_ctx* ctx)
 {
     if (!ctx) return SFH_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    bool published = false;
+    if (ctx->zc_pending) { // a zero-copy step: its epilogue writes the sequence number last (after a system-wide fence)
+        ctx->zc_pending = false;
+        const volatile uint32_t* seq = static_cast<const volatile uint32_t*>(ctx->h_status.p) + 1;
+        for (uint32_t spin = 0; spin < (1u << 22) && !published; ++spin) published = *seq == ctx->zc_seq;
+    }
+    if (!published) CU(ctx, cudaStreamSynchronize(ctx->stream)); // also the path that reports a failed kernel
     if (ctx->step_in_flight) {
         ctx->step_in_flight = false;
         if (ctx->pending_out) std::memcpy(ctx->pending_out, ctx->h_info.p, ctx->pending_out_bytes);
@@ -826,7 +856,8 @@ int sfh_sync(sfh_ctx* ctx)
         ctx->pending_out = nullptr;
         ctx->pending_codes = nullptr;
         if (ctx->h_status.p && *static_cast<uint32_t*>(ctx->h_status.p) != 0) {
-            cudaMemsetAsync(ctx->d_status.p, 0, 4 * sizeof(uint32_t), ctx->stream);
+            cudaMemsetAsync(ctx->d_status.p, 0, sizeof(uint32_t), ctx->stream); // the error flags only
+            *static_cast<uint32_t*>(ctx->h_status.p) = 0;
             return fail(ctx, SFH_ERR_INVALID, "a body referenced an unknown mesh id");
         }
     }

@@ -576,6 +576,10 @@ struct EpilogueParams {
     const uint32_t* seg_info; // [1] = items per k_surface segment
     uint32_t aero;
     sfh_info* out;
+    // zero-copy steps (few bodies: `states` and `out` are pinned HOST memory, no copy nodes): the last block to finish
+    // publishes the status word and a sequence number to the host, which spins on it instead of synchronising the stream
+    uint32_t* zc_host;  // pinned: [0] status, [1] sequence number; nullptr = not a zero-copy step
+    uint32_t* zc_dev;   // device: [0] status flags (k_prologue), [1] blocks finished, [4] sequence counter
 };
 
 // btMatrix3x3::inverse (cofactors / determinant) as three rows, and btVector3::safeNormalize of M^-1 * X
@@ -632,11 +636,29 @@ __device__ inline void correct_aero(double* Fda, double* Tda, const double* Cd, 
     for (int k = 0; k < 3; ++k) { Fda[k] = dmul(Fda[k], cor); Tda[k] = dmul(Tda[k], cor); }
 }
 
+__device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t b, uint32_t lane);
+
 __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= P.n_bodies) return;
+    if (b < P.n_bodies) epilogue_body(P, b, lane);
+    if (P.zc_host) {
+        __threadfence_system(); // this thread's record (if it wrote one) is visible to the host before the flag can be
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&P.zc_dev[1], 1u) + 1u == gridDim.x) {
+            P.zc_dev[1] = 0;
+            const uint32_t seq = P.zc_dev[4] + 1u;
+            P.zc_dev[4] = seq;
+            P.zc_host[0] = P.zc_dev[0];
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(P.zc_host + 1) = seq;
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t b, uint32_t lane)
+{
     const BodyDev& bd = P.bodies[b];
     const uint32_t kind = bd.kind & 255u, pos = bd.kind >> 8;
 
