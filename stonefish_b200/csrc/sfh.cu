@@ -843,12 +843,16 @@ int sfh_sync(sfh_ctx* ctx)
     if (!ctx) return SFH_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     bool published = false;
-    if (ctx->zc_pending) { // a zero-copy step: its epilogue writes the sequence number last (after a system-wide fence)
+    const bool polled = ctx->zc_pending;
+    const volatile uint32_t* seq = ctx->h_status.p ? static_cast<const volatile uint32_t*>(ctx->h_status.p) + 1 : nullptr;
+    if (polled) { // a zero-copy step: its epilogue writes the sequence number last (after a system-wide fence)
         ctx->zc_pending = false;
-        const volatile uint32_t* seq = static_cast<const volatile uint32_t*>(ctx->h_status.p) + 1;
         for (uint32_t spin = 0; spin < (1u << 22) && !published; ++spin) published = *seq == ctx->zc_seq;
     }
-    if (!published) CU(ctx, cudaStreamSynchronize(ctx->stream)); // also the path that reports a failed kernel
+    if (!published) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); // also the path that reports a failed kernel
+        if (polled) ctx->zc_seq = *seq;               // stay in step with the device's counter whatever happened
+    }
     if (ctx->step_in_flight) {
         ctx->step_in_flight = false;
         if (ctx->pending_out) std::memcpy(ctx->pending_out, ctx->h_info.p, ctx->pending_out_bytes);

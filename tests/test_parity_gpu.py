@@ -348,3 +348,29 @@ def test_dry_chunk_skip_and_field_masks_are_exact(ctx, oracle, waves):
     assert err <= REL_TOL, (err, where)
     assert gi["class_count"][0][0] > 0.5 * meshes_[0].n_faces  # most of the spar is dry
     assert (gi["class_count"][:, 1:7].sum(axis=1) > 0).all()   # every body really crosses the surface
+
+
+def test_zero_copy_small_steps_interleaved_with_large_ones(ctx, oracle):
+    """Steps of <= 64 bodies return their results through pinned host memory and a polled sequence number; larger ones through
+    copies and a stream synchronisation. Alternating them, with changing inputs, every result must equal the debug entry's
+    (which uses neither graphs nor zero-copy) bit for bit, and a failing step must not desynchronise the ones after it."""
+    from stonefish_b200.hydro import SfhError
+
+    small, large = scenes.mixed_small(5, True, "uniform"), scenes.config4(96, 50, 21)
+    assert small.n_bodies <= 64 < large.n_bodies
+    st_s, st_l = small.bind(ctx), large.bind(ctx)
+    for it in range(12):
+        st_s["v"] = st_s["v"] * 0.9 + 0.01 * it
+        got = ctx.compute(small.ocean, st_s)
+        want, _ = ctx.compute_debug(small.ocean, st_s, small.faces_per_step())
+        assert got.tobytes() == want.tobytes(), it
+        if it % 3 == 0:
+            st_l["omega"] *= 1.1
+            got = ctx.compute(large.ocean, st_l)
+            want, _ = ctx.compute_debug(large.ocean, st_l, large.faces_per_step())
+            assert got.tobytes() == want.tobytes(), it
+        if it == 5:
+            bad = st_s.copy()
+            bad["mesh_id"][0] = 10**6
+            with pytest.raises(SfhError):
+                ctx.compute(small.ocean, bad)
