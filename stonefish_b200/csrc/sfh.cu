@@ -91,6 +91,12 @@ struct sfh_ctx {
     DevBuf<uint8_t> d_codes;
     DevBuf<uint64_t> d_code_base;
     PinBuf h_ocean, h_states, h_info, h_status, h_codes, h_code_base;
+    // ocean staging of the asynchronous (non-graph) paths: a ring of pinned slots guarded by events, so that a queued copy is
+    // never overwritten, and the bytes staged last, so that an unchanged ocean costs no copy at all
+    PinBuf h_ocean_ring;
+    cudaEvent_t ocean_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int ocean_slot = 0;
+    std::vector<uint8_t> ocean_last;
 
     // pending host-side completion of the last async step
     sfh_info* pending_out = nullptr;
@@ -218,14 +224,10 @@ int occupancy(sfh_ctx* ctx, K kernel, int* cache, int threads = SFH_BLOCK)
 
 // Write the ocean record into the pinned staging buffer (no CUDA call after the first) and report whether some
 // enabled current needs the per-face fp64 evaluation.
-int fill_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
+int fill_ocean_into(sfh_ctx* ctx, const sfh_ocean* o, OceanDev* h, bool* cur_general)
 {
     if (o->n_currents > SFH_MAX_CURRENTS) return fail(ctx, SFH_ERR_INVALID, "n_currents %u > %u", o->n_currents, SFH_MAX_CURRENTS);
     if (o->has_waves && !ctx->have_waves) return fail(ctx, SFH_ERR_STATE, "ocean.has_waves set but sfh_waves_upload was never called");
-    int rc;
-    if ((rc = ensure_pin(ctx, ctx->h_ocean, sizeof(OceanDev))) != SFH_OK) return rc;
-    if ((rc = ensure_dev(ctx, ctx->d_ocean, 1)) != SFH_OK) return rc;
-    OceanDev* h = static_cast<OceanDev*>(ctx->h_ocean.p);
     h->density = o->density;
     h->gravity_z = o->gravity_z;
     h->has_waves = o->has_waves ? 1u : 0u;
@@ -241,14 +243,43 @@ int fill_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
     *cur_general = general;
     return SFH_OK;
 }
-
-// fill_ocean + the (stream-ordered) copy to the device
-int stage_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
+// the graph path's fixed staging buffer (a replayed copy node reads it; steps on that path are synchronised one by one)
+int fill_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general)
 {
-    int rc = fill_ocean(ctx, o, cur_general);
-    if (rc != SFH_OK) return rc;
-    const size_t bytes = offsetof(OceanDev, currents) + sizeof(sfh_current) * (o->n_currents ? o->n_currents : 1);
-    CU(ctx, cudaMemcpyAsync(ctx->d_ocean.p, ctx->h_ocean.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc;
+    if ((rc = ensure_pin(ctx, ctx->h_ocean, sizeof(OceanDev))) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_ocean, 1)) != SFH_OK) return rc;
+    ctx->ocean_last.clear(); // the device copy is about to change behind stage_ocean's back
+    return fill_ocean_into(ctx, o, static_cast<OceanDev*>(ctx->h_ocean.p), cur_general);
+}
+
+// Ocean record to the device, stream-ordered. `fixed`: through the graph path's staging buffer, always copied (the call is
+// being captured or precedes a capture). Otherwise: nothing if the bytes equal what the device already holds, else through
+// the next slot of a pinned ring whose previous copy has completed.
+int stage_ocean(sfh_ctx* ctx, const sfh_ocean* o, bool* cur_general, bool fixed = false)
+{
+    int rc;
+    const size_t bytes = offsetof(OceanDev, currents) + sizeof(sfh_current) * (o->n_currents && o->n_currents <= SFH_MAX_CURRENTS ? o->n_currents : 1);
+    if (fixed) {
+        if ((rc = fill_ocean(ctx, o, cur_general)) != SFH_OK) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->d_ocean.p, ctx->h_ocean.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return SFH_OK;
+    }
+    OceanDev tmp;
+    std::memset(&tmp, 0, bytes);
+    if ((rc = fill_ocean_into(ctx, o, &tmp, cur_general)) != SFH_OK) return rc;
+    if (ctx->ocean_last.size() == bytes && std::memcmp(ctx->ocean_last.data(), &tmp, bytes) == 0) return SFH_OK;
+    const size_t stride = (sizeof(OceanDev) + 255) & ~(size_t)255;
+    if ((rc = ensure_pin(ctx, ctx->h_ocean_ring, 4 * stride)) != SFH_OK) return rc;
+    if ((rc = ensure_dev(ctx, ctx->d_ocean, 1)) != SFH_OK) return rc;
+    const int slot = ctx->ocean_slot = (ctx->ocean_slot + 1) & 3;
+    if (!ctx->ocean_ev[slot]) CU(ctx, cudaEventCreateWithFlags(&ctx->ocean_ev[slot], cudaEventDisableTiming));
+    else CU(ctx, cudaEventSynchronize(ctx->ocean_ev[slot]));
+    uint8_t* h = static_cast<uint8_t*>(ctx->h_ocean_ring.p) + (size_t)slot * stride;
+    std::memcpy(h, &tmp, bytes);
+    CU(ctx, cudaMemcpyAsync(ctx->d_ocean.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ocean_ev[slot], ctx->stream));
+    ctx->ocean_last.assign(reinterpret_cast<const uint8_t*>(&tmp), reinterpret_cast<const uint8_t*>(&tmp) + bytes);
     return SFH_OK;
 }
 
@@ -274,6 +305,7 @@ struct StepPlan {
     bool host_states = true;     // states/out are host pointers
     bool debug = false;
     bool aero = false;           // sfh_aero_step: the "ocean" is the atmosphere and every body runs the aero face loop
+    bool graph_path = false;     // the call is (or may next time be) captured: fixed staging buffers, every copy issued
     bool zero_copy_out = false;  // d_out is pinned HOST memory; the epilogue publishes status + sequence number to h_status
     bool may_sub = true, may_surf = true; // host knows no body can reach the kernel -> skip the launch
     uint64_t chunks_ub = 0;      // upper bound of work items (host variant), 0 = unknown
@@ -289,7 +321,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
 {
     int rc;
     bool general = false;
-    if ((rc = stage_ocean(ctx, ocean, &general)) != SFH_OK) return rc;
+    if ((rc = stage_ocean(ctx, ocean, &general, plan.graph_path)) != SFH_OK) return rc;
     if ((rc = sync_mesh_table(ctx)) != SFH_OK) return rc;
     const bool waves = ocean->has_waves != 0;
 
@@ -471,6 +503,7 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
         // spins on — no device-to-host copy nodes and no stream synchronisation on the critical path of a small step.
         const bool zc = n <= SFH_ZEROCOPY_MAX_BODIES;
         plan.zero_copy_out = zc;
+        plan.graph_path = true;
         sfh_info* out_target = ctx->d_info.p;
         if (zc) {
             void* dp = nullptr;
@@ -634,7 +667,9 @@ void sfh_destroy(sfh_ctx* ctx)
     cudaFree(ctx->d_states.p); cudaFree(ctx->d_info.p); cudaFree(ctx->d_bodies.p); cudaFree(ctx->d_off_sub.p);
     cudaFree(ctx->d_off_surf.p); cudaFree(ctx->d_status.p); cudaFree(ctx->d_part_sub.p); cudaFree(ctx->d_part_surf.p);
     cudaFree(ctx->d_ocean.p); cudaFree(ctx->d_codes.p); cudaFree(ctx->d_code_base.p);
-    for (PinBuf* b : {&ctx->h_mesh_table, &ctx->h_wave, &ctx->h_ocean, &ctx->h_states, &ctx->h_info, &ctx->h_status, &ctx->h_codes, &ctx->h_code_base})
+    for (cudaEvent_t e : ctx->ocean_ev)
+        if (e) cudaEventDestroy(e);
+    for (PinBuf* b : {&ctx->h_ocean_ring, &ctx->h_mesh_table, &ctx->h_wave, &ctx->h_ocean, &ctx->h_states, &ctx->h_info, &ctx->h_status, &ctx->h_codes, &ctx->h_code_base})
         if (b->p) cudaFreeHost(b->p);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);

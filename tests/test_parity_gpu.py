@@ -374,3 +374,34 @@ def test_zero_copy_small_steps_interleaved_with_large_ones(ctx, oracle):
             bad["mesh_id"][0] = 10**6
             with pytest.raises(SfhError):
                 ctx.compute(small.ocean, bad)
+
+
+def test_queued_device_steps_each_see_their_own_ocean(ctx):
+    """sfh_step_device is asynchronous: several steps with DIFFERENT ocean parameters queued back to back must not share a
+    staging buffer (each reads the ocean it was called with), and an unchanged ocean must still give the same answer when its
+    copy is skipped."""
+    import torch
+
+    from stonefish_b200 import BODY_STATE_DTYPE, INFO_DTYPE
+
+    sc = scenes.config4(32, 50, 21)
+    st = sc.bind(ctx)
+    n = st.shape[0]
+    dev = torch.device("cuda", 0)
+    d_states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(dev)
+    speeds = [0.1, 0.7, 0.7, -0.4, 1.3, 0.0, 0.1, 0.1]
+    outs = [torch.zeros(n * INFO_DTYPE.itemsize, dtype=torch.uint8, device=dev) for _ in speeds]
+    want = []
+    for s in speeds:  # the synchronous answers first
+        sc.ocean.currents[0].setVelocity((s, -0.2, 0.05))
+        want.append(ctx.compute(sc.ocean, st).copy())
+    torch.cuda.synchronize(dev)
+    for s, o in zip(speeds, outs):  # then the same sequence queued without any synchronisation in between
+        sc.ocean.currents[0].setVelocity((s, -0.2, 0.05))
+        ctx.compute_device(sc.ocean.to_struct(), d_states.data_ptr(), n, o.data_ptr())
+    ctx.sync()
+    torch.cuda.synchronize(dev)
+    for k, (o, w) in enumerate(zip(outs, want)):
+        got = np.frombuffer(o.cpu().numpy().tobytes(), dtype=INFO_DTYPE)
+        assert got.tobytes() == w.tobytes(), k
+    assert want[0].tobytes() != want[1].tobytes()
