@@ -325,21 +325,23 @@ __device__ __forceinline__ WaveConst wave_const(const WavesDev& w)
 __device__ __forceinline__ float wave_bilinear(const float* __restrict__ ch, int N, const WaveConst& c, float x, float y)
 {
     const float fN = c.fN, half = c.half;
-    float tmp;
-    float i0f = modff(fsub(x, half), &tmp);
-    float j0f = modff(fsub(y, half), &tmp);
+    // modf(v).fractional = v - trunc(v), exact for finite v. (std::modf returns -0 where this gives +0 — for negative whole
+    // numbers — but a zero weight or index offset is the same number with either sign; nothing below looks at the sign.)
+    auto frac = [](float v) { return fsub(v, truncf(v)); };
+    float i0f = frac(fsub(x, half));
+    float j0f = frac(fsub(y, half));
     if (i0f < 0.f) i0f = fsub(1.f, fabsf(i0f));
     if (j0f < 0.f) j0f = fsub(1.f, fabsf(j0f));
     int i0 = (int)truncf(fmul(i0f, fN));
     int j0 = (int)truncf(fmul(j0f, fN));
-    float i1f = modff(fadd(x, half), &tmp);
-    float j1f = modff(fadd(y, half), &tmp);
+    float i1f = frac(fadd(x, half));
+    float j1f = frac(fadd(y, half));
     if (i1f < 0.f) i1f = fsub(1.f, fabsf(i1f));
     if (j1f < 0.f) j1f = fsub(1.f, fabsf(j1f));
     int i1 = (int)truncf(fmul(i1f, fN));
     int j1 = (int)truncf(fmul(j1f, fN));
-    float alpha = modff(fmul(i0f, fN), &tmp);
-    float beta = modff(fmul(j0f, fN), &tmp);
+    float alpha = frac(fmul(i0f, fN));
+    float beta = frac(fmul(j0f, fN));
     // Indices stay within [0, N*N+N] for finite inputs (i,j in [0,N]); clamp only guards NaN/Inf coordinates,
     // where the reference's (int) cast is undefined behaviour.
     const int lim = N * N + N;
