@@ -276,16 +276,91 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
         if (dry) { // block-uniform
             cpack += (tid < nf ? 1ull : 0ull) + (tid + SFH_BLOCK < nf ? 1ull : 0ull); // class 0, code 0 (the debug buffer is zero-filled)
         } else {
+        bool under = true; // every vertex of the chunk is under water: !(depth < 0), the reference's own test (:1353)
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const uint32_t i = tid + k * SFH_BLOCK;
             if (i < cv.nv) {
                 F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
                 // Ocean::GetDepth per vertex (SolidEntity.cpp:1349-1351): same bits for every incident face
-                s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z));
+                const float depth = get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z);
+                s_v[i] = make_float4(pw.x, pw.y, pw.z, depth);
+                under = under && !(depth < 0.f);
             }
         }
-        __syncthreads();
+        // The pair path pays on a flat sea only: with waves its two centroid lookups (and, with Jet/Pipe, two field evaluations)
+        // per thread cost more in registers and instruction fetch than the pairing saves (0.54 -> 0.63 ms on cfg 5).
+        const bool all_wet = __syncthreads_and(under) != 0 && !WAVES;
+
+        if (all_wet) {
+            // Every face of the chunk is class 7 (no clipping): the triangle branch of the reference (:1605-1687) for faces tid
+            // and tid + 128 side by side, in the pair arithmetic of k_submerged (same per-face terms bit for bit).
+            const bool vA = tid < nf, vB = tid + SFH_BLOCK < nf;
+            const uint32_t fA = vA ? cv.faces[tid] : 0u, fB = vB ? cv.faces[tid + SFH_BLOCK] : 0u;
+            const float4 a1 = s_v[__byte_perm(fA, 0, 0x4440)], a2 = s_v[__byte_perm(fA, 0, 0x4441)], a3 = s_v[__byte_perm(fA, 0, 0x4442)];
+            const float4 b1 = s_v[__byte_perm(fB, 0, 0x4440)], b2 = s_v[__byte_perm(fB, 0, 0x4441)], b3 = s_v[__byte_perm(fB, 0, 0x4442)];
+            const V3P q1 = {pk(a1.x, b1.x), pk(a1.y, b1.y), pk(a1.z, b1.z)};
+            const V3P q2 = {pk(a2.x, b2.x), pk(a2.y, b2.y), pk(a2.z, b2.z)};
+            const V3P q3 = {pk(a3.x, b3.x), pk(a3.y, b3.y), pk(a3.z, b3.z)};
+            cpack += ((vA ? 1ull : 0ull) + (vB ? 1ull : 0ull)) << 56; // class 7
+            if (buoy) { // tetrahedron (p0, p1, p2, p3) of the submerged volume (SolidEntity.cpp:1612-1618)
+                const V3P o0 = {pk1(p0.x), pk1(p0.y), pk1(p0.z)};
+                const V3P t1 = q1 - o0, t2 = q2 - o0, t3 = q3 - o0;
+                const P2 v6 = dot(t1, cross(t2, t3));
+                if (!WAVES) {
+                    const V3P m = (((t1 + t2) + t3) * pk1(0.25f)) * v6;
+                    if (vA) { acc[20] = dadd(acc[20], (double)lo(m.x)); acc[21] = dadd(acc[21], (double)lo(m.y)); acc[22] = dadd(acc[22], (double)lo(m.z)); }
+                    if (vB) { acc[20] = dadd(acc[20], (double)hi(m.x)); acc[21] = dadd(acc[21], (double)hi(m.y)); acc[22] = dadd(acc[22], (double)hi(m.z)); }
+                }
+                if (vA) acc[19] = dadd(acc[19], (double)lo(v6));
+                if (vB) acc[19] = dadd(acc[19], (double)hi(v6));
+            }
+            const V3P fn = cross(q2 - q1, q3 - q1);
+            const P2 len2 = dot(fn, fn);
+            const bool dA = lo(len2) < 1e-12f, dB = hi(len2) < 1e-12f;
+            const bool mA = vA && !dA, mB = vB && !dB;
+            epack += (vA && dA ? 1u : 0u) + (vB && dB ? 1u : 0u);
+            uint32_t code = 0;
+            if (__any_sync(SFH_FULL, mA | mB)) {
+                const P2 len = ieee_sqrt2(len2); // lanes with len2 < 1e-12 compute garbage that is masked out
+                const P2 A = len * pk1(0.5f);
+                const V3P csum = (q1 + q2) + q3;
+                V3P fn1, fc;
+                if ((min_key(fn) >= SFH_NUM_KEY) & (min_key(csum) >= SFH_TINY_KEY)) {
+                    fn1 = normalize_fast(fn, len);
+                    fc = V3P{ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)};
+                } else {
+                    normalize_centroid_slow(fn, len, csum, fn1, fc);
+                }
+                const V3P pp = {pk1(B.p.x), pk1(B.p.y), pk1(B.p.z)};
+                if (WAVES && buoy) { // pressure buoyancy at the centroid (SolidEntity.cpp:1650-1658)
+                    const float dcA = get_depth<WAVES>(wv, wc, lo(fc.x), lo(fc.y), lo(fc.z));
+                    const float dcB = get_depth<WAVES>(wv, wc, hi(fc.x), hi(fc.y), hi(fc.z));
+                    const P2 nA = neg(A);
+                    const V3P Fbi = (fn1 * nA) * pk(dcA, dcB); // ((-fn1) * A) * depthc: negating A instead of fn1 flips the same sign bits
+                    const V3P Tbi = cross(fc - pp, Fbi);
+                    if (mA) { acc[12] = dadd(acc[12], (double)lo(Fbi.x)); acc[13] = dadd(acc[13], (double)lo(Fbi.y)); acc[14] = dadd(acc[14], (double)lo(Fbi.z));
+                              acc[15] = dadd(acc[15], (double)lo(Tbi.x)); acc[16] = dadd(acc[16], (double)lo(Tbi.y)); acc[17] = dadd(acc[17], (double)lo(Tbi.z)); }
+                    if (mB) { acc[12] = dadd(acc[12], (double)hi(Fbi.x)); acc[13] = dadd(acc[13], (double)hi(Fbi.y)); acc[14] = dadd(acc[14], (double)hi(Fbi.z));
+                              acc[15] = dadd(acc[15], (double)hi(Tbi.x)); acc[16] = dadd(acc[16], (double)hi(Tbi.y)); acc[17] = dadd(acc[17], (double)hi(Tbi.z)); }
+                }
+                if (damp) {
+                    BodyP2 BP;
+                    BP.p = pp;
+                    BP.v = V3P{pk1(B.v.x), pk1(B.v.y), pk1(B.v.z)};
+                    BP.omega = V3P{pk1(B.omega.x), pk1(B.omega.y), pk1(B.omega.z)};
+                    BP.cur = V3P{pk1(B.cur.x), pk1(B.cur.y), pk1(B.cur.z)};
+                    code = damping_pair<CUR>(BP, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack);
+                }
+                if (mA) acc[18] = dadd(acc[18], (double)lo(A)); // Swet (SolidEntity.cpp:1686)
+                if (mB) acc[18] = dadd(acc[18], (double)hi(A));
+            }
+            if (DEBUG) {
+                const uint32_t* of = s_body.orig_face + (size_t)c * SFH_CH_FACES;
+                if (vA) P.codes[P.code_base[b] + of[tid]] = (uint8_t)(7u | (dA ? SFH_FACE_DEGENERATE : 0u) | (code & 255u));
+                if (vB) P.codes[P.code_base[b] + of[tid + SFH_BLOCK]] = (uint8_t)(7u | (dB ? SFH_FACE_DEGENERATE : 0u) | (code >> 8));
+            }
+        } else {
 
 #pragma unroll 1 // interleaving the two faces costs more in instruction fetch than it gains in ILP (0.72 -> 0.87 ms)
         for (int k = 0; k < 2; ++k) {
@@ -375,6 +450,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
             }
             if (DEBUG) P.codes[P.code_base[b] + s_body.orig_face[(size_t)c * SFH_CH_FACES + slot]] = (uint8_t)code;
         }
+        } // !all_wet
         } // !dry
         if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); spill_cpack(cpack, s_cnt + 4); since_spill = 0; }
 
