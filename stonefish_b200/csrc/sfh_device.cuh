@@ -342,11 +342,10 @@ __device__ __forceinline__ float wave_bilinear(const float* __restrict__ ch, int
     int j1 = (int)truncf(fmul(j1f, fN));
     float alpha = frac(fmul(i0f, fN));
     float beta = frac(fmul(j0f, fN));
-    // Indices stay within [0, N*N+N] for finite inputs (i,j in [0,N]); clamp only guards NaN/Inf coordinates,
-    // where the reference's (int) cast is undefined behaviour.
-    const int lim = N * N + N;
-    int k00 = j0 * N + i0, k01 = j0 * N + i1, k10 = j1 * N + i0, k11 = j1 * N + i1;
-    k00 = min(max(k00, 0), lim); k01 = min(max(k01, 0), lim); k10 = min(max(k10, 0), lim); k11 = min(max(k11, 0), lim);
+    // i0f..j1f lie in [0, 1] for finite coordinates, so i, j lie in [0, N] and the indices in [0, N*N+N]: the planes hold that
+    // many texels (+1). A NaN/Inf coordinate makes the fractions NaN, and cvt.rzi.s32.f32 turns NaN into 0 (the reference's
+    // (int) cast of a NaN is undefined behaviour): still in range, no clamp needed.
+    const int k00 = j0 * N + i0, k01 = j0 * N + i1, k10 = j1 * N + i0, k11 = j1 * N + i1;
     const float t0 = __ldg(ch + k00), t1 = __ldg(ch + k01), t2 = __ldg(ch + k10), t3 = __ldg(ch + k11);
     const float oma = fsub(1.f, alpha), omb = fsub(1.f, beta);
     float h = fmul(fmul(oma, omb), t0);

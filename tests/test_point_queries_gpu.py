@@ -110,3 +110,19 @@ def test_fluid_velocity_jet_pipe(ctx, oracle):
     diff[both_nan] = 0
     assert np.abs(diff).max() <= 1
     assert (diff != 0).sum() <= 3
+
+
+def test_non_finite_coordinates_stay_in_bounds(ctx):
+    """NaN / Inf / huge coordinates: the reference's (int) cast is undefined there; here the lookup must simply stay inside
+    the wave planes (cvt.rzi turns NaN into index 0) and return something without faulting."""
+    from stonefish_b200 import scenes
+    from stonefish_b200.hydro import Ocean
+
+    ocean = Ocean()
+    ocean.setWaves(scenes.wave_field())
+    pts = np.array([[np.nan, 0, 0], [0, np.nan, 1], [np.inf, 1, 0], [1, -np.inf, 0], [3e38, -3e38, 0], [1e30, 1e-30, 2], [0, 0, np.nan]], dtype=np.float32)
+    d = ctx.GetDepth(ocean, pts)
+    assert d.shape == (7,)
+    assert np.isfinite(d[4]) and np.isfinite(d[5])
+    # the context is still healthy
+    assert np.isfinite(ctx.GetDepth(ocean, np.zeros((1, 3), np.float32)))[0]
