@@ -265,6 +265,9 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
         const F3 cw = xform(s_body.R, s_body.t, cv.sphere.x, cv.sphere.y, cv.sphere.z);
         const float reach = fabsf(s_body.t[2]) + fabsf(cv.sphere.x) + fabsf(cv.sphere.y) + fabsf(cv.sphere.z) + cv.sphere.w;
         const bool dry = cw.z + zrow * cv.sphere.w + hmax + (4e-6f * reach + 1e-6f) < 0.f;
+        // ... or entirely below the lowest possible surface: every vertex is under water whatever the waves do, every face is
+        // class 7, and the per-vertex wave lookups (used for nothing but the classification then) can be skipped
+        const bool deep = WAVES && cw.z - zrow * cv.sphere.w - hmax - (4e-6f * reach + 1e-6f) > 0.f;
         // which Jet / Pipe fields can reach this chunk at all (every face centroid lies inside the sphere)
         const uint64_t cur_may =
             CUR ? chunk_current_mask(s_guard, n_cur, cw, rnorm * cv.sphere.w + (4e-6f * (reach + fabsf(s_body.t[0]) + fabsf(s_body.t[1])) + 1e-6f)) : 0ull;
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
             if (i < cv.nv) {
                 F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
                 // Ocean::GetDepth per vertex (SolidEntity.cpp:1349-1351): same bits for every incident face
-                const float depth = get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z);
+                const float depth = deep ? 1.f : get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z); // only its sign matters for class 7
                 s_v[i] = make_float4(pw.x, pw.y, pw.z, depth);
                 under = under && !(depth < 0.f);
             }
