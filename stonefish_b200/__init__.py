@@ -6,9 +6,11 @@ and meshes.py hold the synthetic BASELINE inputs. Importing the package does not
 `HydroContext` does, and fails loudly without one — there is no CPU fallback.
 """
 from . import _abi
-from .hydro import (BODY_STATE_DTYPE, INFO_DTYPE, BodyFluidPosition, HydroContext, HydrodynamicsSettings, Jet, Mesh, Ocean, Pipe,
-                    SfhError, Uniform, VelocityField, make_transform, new_body_states, quat_to_basis, transform_mul)
+from .hydro import (BODY_STATE_DTYPE, INFO_DTYPE, Atmosphere, BodyFluidPosition, GeometryApproxType, HydroContext,
+                    HydrodynamicsSettings, Jet, Mesh, Ocean, Pipe, SfhError, Uniform, VelocityField, aero_proxy, compound_part_states,
+                    make_transform, new_body_states, quat_to_basis, sum_compound, sum_compound_aero, transform_mul, wave_params)
 
-__all__ = ["_abi", "BODY_STATE_DTYPE", "INFO_DTYPE", "BodyFluidPosition", "HydroContext", "HydrodynamicsSettings", "Jet", "Mesh",
-           "Ocean", "Pipe", "SfhError", "Uniform", "VelocityField", "make_transform", "new_body_states", "quat_to_basis",
-           "transform_mul"]
+__all__ = ["_abi", "BODY_STATE_DTYPE", "INFO_DTYPE", "Atmosphere", "BodyFluidPosition", "GeometryApproxType", "HydroContext",
+           "HydrodynamicsSettings", "Jet", "Mesh", "Ocean", "Pipe", "SfhError", "Uniform", "VelocityField", "aero_proxy",
+           "compound_part_states", "make_transform", "new_body_states", "quat_to_basis", "sum_compound", "sum_compound_aero",
+           "transform_mul", "wave_params"]
