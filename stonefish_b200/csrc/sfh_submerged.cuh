@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
         }
 
         const uint32_t nf = cv.nf;
-#pragma unroll 1
+#pragma unroll 1 // unrolling by 2 (112 registers) changes nothing: 0.446 vs 0.444 ms
         for (uint32_t base = 0; base < nf; base += 64u) { // faces base+lane and base+lane+32 side by side
             const uint32_t iA = base + lane, iB = iA + 32u;
             const bool vA = iA < nf, vB = iB < nf;
