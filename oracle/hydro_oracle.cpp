@@ -1,7 +1,8 @@
 /*
  * hydro_oracle.cpp — CPU restatement of Stonefish's per-triangle hydrodynamic force integration.
  *
- * TEST INFRASTRUCTURE ONLY (see hydro_oracle.h). PARITY UNPINNED at the glm boundary.
+ * TEST INFRASTRUCTURE ONLY (see hydro_oracle.h). Parity: pinned bit for bit against the reference's own definitions compiled from
+ * its source text (oracle/ref_harness.cpp, tests/test_oracle_refsource.py); only the GLM primitives under them are a stand-in.
  *
  * Every function cites the reference lines it follows (paths relative to the Stonefish v1.6.0 tree).
  * Arithmetic rules:

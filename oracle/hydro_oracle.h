@@ -6,14 +6,19 @@
  * `cpu_baseline` / `--impl reference` leg of bench.py. Nothing in the product path
  * (stonefish_b200/, include/sfh.h) links, imports or calls it.
  *
- * PARITY UNPINNED at the glm boundary: the reference cannot be compiled here (glm, SDL2, Freetype and
- * GL headers are absent, no network) and its repository holds no golden vectors or enabled known-answer
- * tests for this path (the only numeric checks are commented out,
- * Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:168-249). The fp32 chain follows GLM 0.9.9
- * scalar semantics as listed in SURVEY.md Appendix A.1; the fp64 pieces (currents, correction, transforms)
- * are additionally validated against the reference's own vendored Bullet LinearMath headers
- * (oracle/_ref, built by oracle/Makefile when /root/reference is present; vectors committed under
- * tests/golden/).
+ * PARITY: PINNED against the reference's own source text, with one stated residue. The reference's build cannot run here (GLM,
+ * SDL2, Freetype and GL headers are absent, no network) and its repository holds no golden vectors or enabled known-answer tests
+ * for this path (the only numeric checks are commented out, Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:168-249). But
+ * the DEFINITIONS of the path compile on their own: oracle/ref_extract.py pulls them out of the reference's files where they lie
+ * (SolidEntity's integrators, dispatcher and corrections, Compound, CableEntity, Ocean, the wave lookup, Uniform/Jet/Pipe,
+ * Atmosphere, glMatrixFromTransform — 31 definitions), oracle/ref_harness.cpp compiles that text with the reference's flags
+ * against the reference's vendored Bullet and oracle/ref_shim/shim.hpp into oracle/_ref/librefsrc.so, and this oracle, in the
+ * reference's own accumulation mode, reproduces its outputs BIT FOR BIT (tests/golden/ref_golden.json written from it;
+ * tests/test_oracle_refsource.py). THE RESIDUE: GLM itself is not in the image, so shim.hpp stands in for the dozen GLM
+ * primitives those definitions use (vec3/vec4/mat4 operators, dot, cross, length2, sqrt, mat4*vec4, gtx/scalar_multiplication),
+ * following GLM 0.9.9's scalar code path as listed in SURVEY.md Appendix A.1 — that layer is UNPINNED. The fp64 pieces are
+ * additionally validated against Bullet directly (oracle/bt_check.cpp -> oracle/_ref/libbtcheck.so, tests/golden/bt_golden.json).
+ * The wave-field PRODUCER (wave_oracle.cpp) restates shader code whose arithmetic is implementation-defined: parity unpinned there.
  */
 #ifndef HYDRO_ORACLE_H
 #define HYDRO_ORACLE_H

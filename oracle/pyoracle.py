@@ -1,7 +1,7 @@
 """ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE ONLY.
 
 Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by
-the product package. PARITY UNPINNED at the glm boundary (see oracle/hydro_oracle.h).
+the product package. Pinned against the reference's own source text except for the GLM primitives (see oracle/hydro_oracle.h).
 """
 from __future__ import annotations
 
@@ -30,7 +30,7 @@ def build(force: bool = False):
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/3rdparty/LinearMath"):
-        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", HERE, "ref", "refsrc"], stdout=subprocess.DEVNULL)
 
 
 _lib = None

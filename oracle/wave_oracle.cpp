@@ -4,12 +4,15 @@
  * (:857-927), the h(k,t) pass (Library/shaders/oceanInit.frag) and the 2 x 8 FFT passes (oceanFFTX.frag / oceanFFTY.frag)
  * as OpenGLOcean::Simulate sequences them (:455-534).
  *
- * TEST INFRASTRUCTURE ONLY (see hydro_oracle.h). PARITY UNPINNED, and here necessarily so: the reference evaluates the
- * two shader stages on whatever GPU runs OpenGL, where sin/cos precision and a*b+c contraction are implementation-defined
- * (GLSL 3.30 §4.5), and it stores spectrum and butterfly table in GL_RGBA16F textures (OpenGLOcean.cpp:84-85,419-422) whose
- * float->half rounding is also the driver's. This file fixes those choices to: round-to-nearest-even halves, libm
- * sinf/cosf, no contraction. Host-side C++ follows the reference expression by expression, with the float overloads of
- * <cmath> functions for float arguments (the translation unit sees SDL's <math.h>, i.e. libstdc++'s global overloads).
+ * TEST INFRASTRUCTURE ONLY (see hydro_oracle.h). PARITY, two halves:
+ *   - host half (spectrum, LCG phases, butterfly table): PINNED bit for bit against the reference's own definitions compiled from
+ *     its source text (oracle/ref_harness.cpp: OpenGLOcean::GenerateWavesSpectrum / spectrum / GetSpectrumSample /
+ *     ComputeButterflyLookupTable, lrandom / frandom; tests/test_oracle_refsource.py::test_wave_producer_host_tables). Unqualified
+ *     sqrt/pow/log/cos... on float arguments resolve to the float overloads there as here (Bullet's btScalar.h includes <math.h>).
+ *   - shader half (oceanInit.frag, oceanFFTX/Y.frag): UNPINNED, and necessarily so: the reference evaluates it on whatever GPU
+ *     runs OpenGL, where sin/cos precision and a*b+c contraction are implementation-defined (GLSL 3.30 §4.5), and it stores
+ *     spectrum and butterfly table in GL_RGBA16F textures (OpenGLOcean.cpp:84-85,419-422) whose float->half rounding is also the
+ *     driver's. This file fixes those choices to: round-to-nearest-even halves, libm sinf/cosf, no contraction.
  */
 #include <cmath>
 #include <cstdint>
