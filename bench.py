@@ -146,28 +146,43 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle legs
-def cpu_oracle_rate(workload: str, scene, host_meshes, budget_s: float, threads: int):
-    """Reference algorithm (oracle port, REF_F32_SEQ) on the first len(host_meshes) bodies, scheduled like the
-    reference: one task per body on `threads` pool threads; single-body workloads are therefore single-threaded
-    in the reference's schedule. Returns (faces/s, sample description, faces per pass, seconds per pass)."""
+def cpu_stepper(meshes, body_mesh, ocean, states):
+    """The CPU arm: (step(n_threads) -> (infos, seconds), kind). "reference" = the reference's OWN definitions of the path compiled
+    from its source text (oracle/_ref/librefsrc.so, built where the reference checkout is mounted and shipped with the repo
+    snapshot; real Bullet, a stand-in for the GLM primitives — oracle/ref_harness.cpp); "port" = the oracle's restatement, bit-identical
+    to it (tests/test_oracle_refsource.py), used when that library is absent."""
     from oracle import pyoracle as po
+    from oracle import pyrefsrc as rs
 
+    if rs.available():
+        sc = rs.RefScene(meshes, body_mesh, ocean, states)
+        return (lambda threads: sc.step(threads)), "reference"
+    osc = po.OracleScene(meshes, body_mesh, ocean, states)
+    return (lambda threads: osc.step(po.ORC_REF_F32_SEQ, n_threads=threads)), "port"
+
+
+def cpu_oracle_rate(workload: str, scene, host_meshes, budget_s: float, threads: int):
+    """The reference's CPU path on the first len(host_meshes) bodies, scheduled like the reference: one task per body on `threads`
+    pool threads; single-body workloads are therefore single-threaded in the reference's schedule.
+    Returns (faces/s, sample description, faces per pass, seconds per pass, kind)."""
     n = len(host_meshes)
-    osc = po.OracleScene(host_meshes, np.arange(n), scene.ocean, scene.states[:n])
+    step, kind = cpu_stepper(host_meshes, np.arange(n), scene.ocean, scene.states[:n])
     faces = sum(m.n_faces for m in host_meshes)
     secs, passes = 0.0, 0
     t_end = time.perf_counter() + budget_s
     while passes < 1 or (time.perf_counter() < t_end and passes < 1000):
-        _, s = osc.step(po.ORC_REF_F32_SEQ, n_threads=threads)
+        _, s = step(threads)
         secs += s
         passes += 1
-    desc = f"{n} bodies ({faces} faces) of the workload x {passes} passes, one task per body on {threads} threads, fp32 sequential sums"
-    return faces * passes / secs, desc, faces, secs / passes
+    what = "the reference's own code (oracle/_ref/librefsrc.so)" if kind == "reference" else "oracle port"
+    desc = f"{n} bodies ({faces} faces) of the workload x {passes} passes, one task per body on {threads} threads, fp32 sequential sums, {what}"
+    return faces * passes / secs, desc, faces, secs / passes, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path = the oracle port (the reference does not
-    compile here: glm/SDL2/GL absent), all host threads, same config/metric/unit; a step = one pass over a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path — its definitions compiled from its source text
+    (oracle/_ref/librefsrc.so; the full reference build needs glm/SDL2/GL, absent here), else the bit-identical oracle port —
+    on all host threads, same config/metric/unit; a step = one pass over a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -181,22 +196,23 @@ def run_reference(args):
     scene = factory(sample_bodies, 0)
     base = scene.meshes[0]
     meshes = [M.jitter(base, jitter_seed(args.workload, i)) for i in range(sample_bodies)] if unique else [base] * sample_bodies
-    osc = po.OracleScene(meshes, np.arange(sample_bodies), scene.ocean, scene.states)
+    step, kind = cpu_stepper(meshes, np.arange(sample_bodies), scene.ocean, scene.states)
     faces = sum(m.n_faces for m in meshes)
     use_threads = threads if sample_bodies > 1 else 1
     for _ in range(args.warmup):
-        osc.step(po.ORC_REF_F32_SEQ, n_threads=use_threads)
+        step(use_threads)
     t = 0.0
     for _ in range(args.steps):
-        _, s = osc.step(po.ORC_REF_F32_SEQ, n_threads=use_threads)
+        _, s = step(use_threads)
         t += s
     value = faces * args.steps / t
-    sample = f"{sample_bodies} bodies ({faces} faces) per step, one task per body on {use_threads} threads (reference schedule), fp32 sequential sums"
+    what = "the reference's own code compiled from its source text (oracle/_ref/librefsrc.so)" if kind == "reference" else "oracle port of the reference"
+    sample = f"{sample_bodies} bodies ({faces} faces) per step, one task per body on {use_threads} threads (reference schedule), fp32 sequential sums, {what}"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "bodies_per_step": sample_bodies, "faces_per_step": faces},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": use_threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": use_threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -355,8 +371,8 @@ def run_ours(args):
             po.build()
             threads = os.cpu_count() or 1
             use = threads if keep > 1 else 1
-            rate, sample, _, _ = cpu_oracle_rate(args.workload, scene, host_meshes, args.cpu_seconds, use)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": use, "kind": "port", "sample": sample}
+            rate, sample, _, _, kind = cpu_oracle_rate(args.workload, scene, host_meshes, args.cpu_seconds, use)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": use, "kind": kind, "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local_rank])

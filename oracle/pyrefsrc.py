@@ -47,6 +47,8 @@ def lib():
         L.refx_velocity_d.argtypes = [P(refx_fluid), P(C.c_double), P(C.c_double)]
         L.refx_body.restype = None
         L.refx_body.argtypes = [P(orc_mesh), P(refx_fluid), C.c_void_p, C.c_void_p]
+        L.refx_step.restype = C.c_double
+        L.refx_step.argtypes = [P(P(orc_mesh)), P(refx_fluid), C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.refx_aero.restype = None
         L.refx_aero.argtypes = [P(orc_mesh), P(refx_fluid), C.c_void_p, C.c_int, C.c_int, P(C.c_double), P(C.c_double), P(C.c_double)]
         L.refx_compound.restype = None
@@ -159,3 +161,23 @@ def wave_tables(params, spectrum: bool = True):
     bf = np.zeros(n * params.passes * 4, np.float32)
     lib().refx_wave_tables(C.byref(params), s12.ctypes.data if spectrum else None, s34.ctypes.data if spectrum else None, bf.ctypes.data)
     return s12, s34, bf
+
+
+class RefScene:
+    """A whole scene on the reference's own compiled code, stepped like the reference schedules it (one task per body on a pool,
+    refx_step). Same role and interface as pyoracle.OracleScene.step: the CPU arm of bench.py."""
+
+    def __init__(self, meshes, body_mesh, ocean, states: np.ndarray):
+        self.meshes = meshes
+        self.mstructs = [mesh_struct(m) for m in meshes]
+        self.fluid = ocean_fluid(ocean)
+        self.states = np.ascontiguousarray(states)
+        arr = (C.POINTER(orc_mesh) * len(body_mesh))()
+        for i, mi in enumerate(body_mesh):
+            arr[i] = C.pointer(self.mstructs[int(mi)])
+        self.mesh_ptrs = arr
+
+    def step(self, n_threads: int = 1):
+        out = np.zeros(self.states.shape[0], dtype=INFO_DTYPE)
+        secs = lib().refx_step(self.mesh_ptrs, C.byref(self.fluid), self.states.ctypes.data, self.states.shape[0], n_threads, out.ctypes.data)
+        return out, secs

@@ -19,6 +19,10 @@
  */
 #include "ref_shim/shim.hpp"
 
+#include <atomic>
+#include <chrono>
+#include <thread>
+
 #include "../include/sfh_types.h"
 #include "hydro_oracle.h"
 
@@ -160,13 +164,10 @@ void refx_field_axis(const refx_field* d, double n_out[3], double* l_out)
  *   SFH_F_DISPATCH (mode must be SFH_POS_AUTO): SolidEntity::ComputeHydrodynamicForces, outputs that it leaves untouched are
  *       reported through wrote_buoyancy / wrote_damping = 0 (the members start as NaN so "untouched" is observable);
  *   otherwise the static integrator selected by mode. position: 0 OUTSIDE, 1 INSIDE, 2 CROSSING as in sfh_types.h. */
-void refx_body(const orc_mesh* mesh_in, const refx_fluid* f, const sfh_body_state* st, sfh_info* out)
+static void run_body(World& w, const sf::Mesh* mesh, const sfh_body_state* st, sfh_info* out)
 {
-    World w(f);
-    sf::Mesh mesh;
-    if (mesh_in) fill_mesh(mesh, mesh_in);
     sf::SolidEntity s;
-    fill_solid(s, st, mesh_in ? &mesh : nullptr);
+    fill_solid(s, st, mesh);
     const double nan = std::nan("");
     s.Fb = s.Tb = s.Fdq = s.Tdq = s.Fdf = s.Tdf = sf::Vector3(nan, nan, nan);
     s.Swet = s.Vsub = nan;
@@ -201,6 +202,47 @@ void refx_body(const orc_mesh* mesh_in, const refx_fluid* f, const sfh_body_stat
     if (out->wrote_damping) { put(out->Fdq, s.Fdq); put(out->Tdq, s.Tdq); put(out->Fdf, s.Fdf); put(out->Tdf, s.Tdf); }
     out->Swet = std::isnan(s.Swet) ? 0.0 : s.Swet;
     out->Vsub = std::isnan(s.Vsub) ? 0.0 : s.Vsub;
+}
+
+void refx_body(const orc_mesh* mesh_in, const refx_fluid* f, const sfh_body_state* st, sfh_info* out)
+{
+    World w(f);
+    sf::Mesh mesh;
+    if (mesh_in) fill_mesh(mesh, mesh_in);
+    run_body(w, mesh_in ? &mesh : nullptr, st, out);
+}
+
+/* Whole step scheduled like the reference: one task per body on a pool of n_threads (SimulationManager.cpp:1641-1651,
+ * utils/ThreadPool.hpp). Meshes are converted before the clock starts (the reference holds them resident). Returns the wall
+ * seconds between the first task and the join. This is the CPU arm of bench.py (`--impl reference`, cpu_baseline.kind
+ * "reference"): the reference's own code on the host cores. */
+double refx_step(const orc_mesh* const* meshes, const refx_fluid* f, const sfh_body_state* states, uint32_t n, int n_threads, sfh_info* out)
+{
+    World w(f);
+    std::vector<const orc_mesh*> uniq;
+    std::vector<std::unique_ptr<sf::Mesh>> built;
+    std::vector<const sf::Mesh*> of_body(n, nullptr);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (!meshes[i]) continue;
+        size_t k = 0;
+        while (k < uniq.size() && uniq[k] != meshes[i]) ++k;
+        if (k == uniq.size()) {
+            uniq.push_back(meshes[i]);
+            built.emplace_back(new sf::Mesh());
+            fill_mesh(*built.back(), meshes[i]);
+        }
+        of_body[i] = built[k].get();
+    }
+    if (n_threads < 1) n_threads = 1;
+    std::atomic<uint32_t> next(0);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t)
+        pool.emplace_back([&]() {
+            for (uint32_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) run_body(w, of_body[i], &states[i], &out[i]);
+        });
+    for (auto& th : pool) th.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 /* SolidEntity::ComputeAerodynamicForces: the static integrator, or (dispatch != 0) the member = static + CorrectAerodynamicForces
