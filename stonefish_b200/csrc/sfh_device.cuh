@@ -189,6 +189,58 @@ __device__ __forceinline__ D3 dcross(D3 a, D3 v)
 }
 __device__ __forceinline__ double dnorm(D3 a) { return __dsqrt_rn(ddot(a, a)); }
 
+// a[0..5] += (double){x0..x5}: the fp32 per-face terms enter the fp64 sums exactly
+__device__ __forceinline__ void acc6(double* a, float x0, float x1, float x2, float x3, float x4, float x5)
+{
+    a[0] = dadd(a[0], (double)x0); a[1] = dadd(a[1], (double)x1); a[2] = dadd(a[2], (double)x2);
+    a[3] = dadd(a[3], (double)x3); a[4] = dadd(a[4], (double)x4); a[5] = dadd(a[5], (double)x5);
+}
+
+// The same under a per-lane condition. SFH_ACC_VARIANT 1: the conversions run unconditionally — pinned with asm volatile so they
+// are not sunk back into the conditional block — which lets ptxas predicate the DADDs (no BSSY/BRA/BSYNC per block) and spread the
+// XU-pipe F2Fs over the surrounding fp32 work: k_submerged 0.4454 -> 0.4300 ms per 51.2 M faces. 0: a divergent
+// block per condition.
+#ifndef SFH_ACC_VARIANT
+#define SFH_ACC_VARIANT 1
+#endif
+__device__ __forceinline__ double cvt_pinned(float x)
+{
+    double d;
+    asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(x));
+    return d;
+}
+__device__ __forceinline__ void acc6_if(bool p, double* a, float x0, float x1, float x2, float x3, float x4, float x5)
+{
+#if SFH_ACC_VARIANT == 1
+    const double d0 = cvt_pinned(x0), d1 = cvt_pinned(x1), d2 = cvt_pinned(x2), d3 = cvt_pinned(x3), d4 = cvt_pinned(x4), d5 = cvt_pinned(x5);
+    if (p) {
+        a[0] = dadd(a[0], d0); a[1] = dadd(a[1], d1); a[2] = dadd(a[2], d2);
+        a[3] = dadd(a[3], d3); a[4] = dadd(a[4], d4); a[5] = dadd(a[5], d5);
+    }
+#else
+    if (p) acc6(a, x0, x1, x2, x3, x4, x5);
+#endif
+}
+
+__device__ __forceinline__ void acc3_if(bool p, double* a, float x0, float x1, float x2)
+{
+#if SFH_ACC_VARIANT == 1
+    const double d0 = cvt_pinned(x0), d1 = cvt_pinned(x1), d2 = cvt_pinned(x2);
+    if (p) { a[0] = dadd(a[0], d0); a[1] = dadd(a[1], d1); a[2] = dadd(a[2], d2); }
+#else
+    if (p) { a[0] = dadd(a[0], (double)x0); a[1] = dadd(a[1], (double)x1); a[2] = dadd(a[2], (double)x2); }
+#endif
+}
+__device__ __forceinline__ void acc1_if(bool p, double& a, float x)
+{
+#if SFH_ACC_VARIANT == 1
+    const double d = cvt_pinned(x);
+    if (p) a = dadd(a, d);
+#else
+    if (p) a = dadd(a, (double)x);
+#endif
+}
+
 // Uniform/Jet/Pipe::GetVelocityAtPoint (Uniform.cpp:54-57, Jet.cpp:54-75, Pipe.cpp:57-78).
 // exp/pow are CUDA's (<= 1-2 ulp) where the reference calls glibc's: see DESIGN.md "fp64 transcendentals".
 __device__ __forceinline__ D3 current_velocity(const sfh_current& c, D3 p)

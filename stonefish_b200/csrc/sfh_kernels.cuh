@@ -312,11 +312,11 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
                 const P2 v6 = dot(t1, cross(t2, t3));
                 if (!WAVES) {
                     const V3P m = (((t1 + t2) + t3) * pk1(0.25f)) * v6;
-                    if (vA) { acc[20] = dadd(acc[20], (double)lo(m.x)); acc[21] = dadd(acc[21], (double)lo(m.y)); acc[22] = dadd(acc[22], (double)lo(m.z)); }
-                    if (vB) { acc[20] = dadd(acc[20], (double)hi(m.x)); acc[21] = dadd(acc[21], (double)hi(m.y)); acc[22] = dadd(acc[22], (double)hi(m.z)); }
+                    acc3_if(vA, acc + 20, lo(m.x), lo(m.y), lo(m.z));
+                    acc3_if(vB, acc + 20, hi(m.x), hi(m.y), hi(m.z));
                 }
-                if (vA) acc[19] = dadd(acc[19], (double)lo(v6));
-                if (vB) acc[19] = dadd(acc[19], (double)hi(v6));
+                acc1_if(vA, acc[19], lo(v6));
+                acc1_if(vB, acc[19], hi(v6));
             }
             const V3P fn = cross(q2 - q1, q3 - q1);
             const P2 len2 = dot(fn, fn);
@@ -342,10 +342,8 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
                     const P2 nA = neg(A);
                     const V3P Fbi = (fn1 * nA) * pk(dcA, dcB); // ((-fn1) * A) * depthc: negating A instead of fn1 flips the same sign bits
                     const V3P Tbi = cross(fc - pp, Fbi);
-                    if (mA) { acc[12] = dadd(acc[12], (double)lo(Fbi.x)); acc[13] = dadd(acc[13], (double)lo(Fbi.y)); acc[14] = dadd(acc[14], (double)lo(Fbi.z));
-                              acc[15] = dadd(acc[15], (double)lo(Tbi.x)); acc[16] = dadd(acc[16], (double)lo(Tbi.y)); acc[17] = dadd(acc[17], (double)lo(Tbi.z)); }
-                    if (mB) { acc[12] = dadd(acc[12], (double)hi(Fbi.x)); acc[13] = dadd(acc[13], (double)hi(Fbi.y)); acc[14] = dadd(acc[14], (double)hi(Fbi.z));
-                              acc[15] = dadd(acc[15], (double)hi(Tbi.x)); acc[16] = dadd(acc[16], (double)hi(Tbi.y)); acc[17] = dadd(acc[17], (double)hi(Tbi.z)); }
+                    acc6_if(mA, acc + 12, lo(Fbi.x), lo(Fbi.y), lo(Fbi.z), lo(Tbi.x), lo(Tbi.y), lo(Tbi.z));
+                    acc6_if(mB, acc + 12, hi(Fbi.x), hi(Fbi.y), hi(Fbi.z), hi(Tbi.x), hi(Tbi.y), hi(Tbi.z));
                 }
                 if (damp) {
                     BodyP2 BP;
@@ -355,8 +353,8 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
                     BP.cur = V3P{pk1(B.cur.x), pk1(B.cur.y), pk1(B.cur.z)};
                     code = damping_pair<CUR>(BP, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack);
                 }
-                if (mA) acc[18] = dadd(acc[18], (double)lo(A)); // Swet (SolidEntity.cpp:1686)
-                if (mB) acc[18] = dadd(acc[18], (double)hi(A));
+                acc1_if(mA, acc[18], lo(A)); // Swet (SolidEntity.cpp:1686)
+                acc1_if(mB, acc[18], hi(A));
             }
             if (DEBUG) {
                 const uint32_t* of = s_body.orig_face + (size_t)c * SFH_CH_FACES;

@@ -42,13 +42,6 @@ __device__ __forceinline__ void normalize_centroid_slow(V3P fn, P2 len, V3P s, V
     fc.z = pk(__fdiv_rn(lo(s.z), 3.f), __fdiv_rn(hi(s.z), 3.f));
 }
 
-// a[0..5] += (double){x0..x5}: the fp32 per-face terms enter the fp64 sums exactly
-__device__ __forceinline__ void acc6(double* a, float x0, float x1, float x2, float x3, float x4, float x5)
-{
-    a[0] = dadd(a[0], (double)x0); a[1] = dadd(a[1], (double)x1); a[2] = dadd(a[2], (double)x2);
-    a[3] = dadd(a[3], (double)x3); a[4] = dadd(a[4], (double)x4); a[5] = dadd(a[5], (double)x5);
-}
-
 struct BodyP2 { // per-body constants broadcast to both lanes
     V3P p, v, omega, cur;
     float R[9], t[3]; // T_C, for the per-chunk vertex transform
@@ -74,13 +67,13 @@ __device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_curr
     uint32_t code = 0;
 
     const bool qA = mA && lo(vc_n) < -1e-12f, qB = mB && hi(vc_n) < -1e-12f;
-    if (__any_sync(SFH_FULL, qA | qB)) {
+    { // no warp vote around the block: straight-line code schedules better than the skipped work costs (0.418 -> 0.413 ms)
         // vc_n < -1e-12 implies |vc|^2 > 1e-24 > 2^-101: inside ieee_sqrt2's range for every lane that is used
         const P2 vmag2 = dot(vc, vc);
         const V3P q = ((vc * ieee_sqrt2(vmag2)) * neg(vc_n)) * A;
         const V3P tq = cross(r, q);
-        if (qA) acc6(acc, lo(q.x), lo(q.y), lo(q.z), lo(tq.x), lo(tq.y), lo(tq.z));
-        if (qB) acc6(acc, hi(q.x), hi(q.y), hi(q.z), hi(tq.x), hi(tq.y), hi(tq.z));
+        acc6_if(qA, acc, lo(q.x), lo(q.y), lo(q.z), lo(tq.x), lo(tq.y), lo(tq.z));
+        acc6_if(qB, acc, hi(q.x), hi(q.y), hi(q.z), hi(tq.x), hi(tq.y), hi(tq.z));
         epack += (qA ? 1u << 10 : 0u) + (qB ? 1u << 10 : 0u);
         code |= (qA ? (uint32_t)SFH_FACE_QUADRATIC : 0u) | (qB ? (uint32_t)SFH_FACE_QUADRATIC << 8 : 0u);
     }
@@ -89,8 +82,8 @@ __device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_curr
     { // nearly every face has tangential flow: no warp vote
         const V3P s = vt * A;
         const V3P ts = cross(r, s);
-        if (sA) acc6(acc + 6, lo(s.x), lo(s.y), lo(s.z), lo(ts.x), lo(ts.y), lo(ts.z));
-        if (sB) acc6(acc + 6, hi(s.x), hi(s.y), hi(s.z), hi(ts.x), hi(ts.y), hi(ts.z));
+        acc6_if(sA, acc + 6, lo(s.x), lo(s.y), lo(s.z), lo(ts.x), lo(ts.y), lo(ts.z));
+        acc6_if(sB, acc + 6, hi(s.x), hi(s.y), hi(s.z), hi(ts.x), hi(ts.y), hi(ts.z));
         epack += (sA ? 1u << 20 : 0u) + (sB ? 1u << 20 : 0u);
         code |= (sA ? (uint32_t)SFH_FACE_SKIN : 0u) | (sB ? (uint32_t)SFH_FACE_SKIN << 8 : 0u);
     }
@@ -116,11 +109,11 @@ __device__ __forceinline__ uint32_t aero_pair(const BodyP2& B, const sfh_current
     const P2 t = dot(fn1, vn);
     uint32_t code = 0;
     const bool qA = mA && lo(t) < -1e-12f, qB = mB && hi(t) < -1e-12f;
-    if (__any_sync(SFH_FULL, qA | qB)) {
+    { // straight-line, as in damping_pair
         const V3P q = (vn * pk1(3.f)) * A;
         const V3P tq = cross(r, q);
-        if (qA) acc6(acc, lo(q.x), lo(q.y), lo(q.z), lo(tq.x), lo(tq.y), lo(tq.z));
-        if (qB) acc6(acc, hi(q.x), hi(q.y), hi(q.z), hi(tq.x), hi(tq.y), hi(tq.z));
+        acc6_if(qA, acc, lo(q.x), lo(q.y), lo(q.z), lo(tq.x), lo(tq.y), lo(tq.z));
+        acc6_if(qB, acc, hi(q.x), hi(q.y), hi(q.z), hi(tq.x), hi(tq.y), hi(tq.z));
         epack += (qA ? 1u << 10 : 0u) + (qB ? 1u << 10 : 0u);
         code |= (qA ? (uint32_t)SFH_FACE_QUADRATIC : 0u) | (qB ? (uint32_t)SFH_FACE_QUADRATIC << 8 : 0u);
     }
@@ -178,6 +171,10 @@ __device__ __forceinline__ void walk_issue_next(const PipeAddr& pipe, ItemWalk& 
 #define SFH_SUB_MIN_BLOCKS 8
 #endif
 #define SFH_SUB_THREADS (32u * SFH_SUB_WPB)
+#ifndef SFH_SUB_UNROLL
+#define SFH_SUB_UNROLL 1 /* face pairs per lane interleaved in the face loop */
+#endif
+constexpr int kSubUnroll = SFH_SUB_UNROLL;
 
 struct WarpStage { // shared memory private to one warp
     ChunkPipe pipe;
@@ -312,7 +309,7 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
         }
 
         const uint32_t nf = cv.nf;
-#pragma unroll 1 // unrolling by 2 (112 registers) changes nothing: 0.446 vs 0.444 ms
+#pragma unroll kSubUnroll // unrolling by 2 (112 registers) changes nothing: 0.446 vs 0.444 ms
         for (uint32_t base = 0; base < nf; base += 64u) { // faces base+lane and base+lane+32 side by side
             const uint32_t iA = base + lane, iB = iA + 32u;
             const bool vA = iA < nf, vB = iB < nf;
@@ -343,19 +340,15 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
                 const float m_fn = fminf(fminf(fminf(lo(sx), lo(sy)), lo(sz)), fminf(fminf(hi(sx), hi(sy)), hi(sz)));
                 const float m_cs = fminf(fminf(fminf(fabsf(lo(csum.x)), fabsf(lo(csum.y))), fabsf(lo(csum.z))),
                                          fminf(fminf(fabsf(hi(csum.x)), fabsf(hi(csum.y))), fabsf(hi(csum.z))));
-                bool fast = (m_fn >= 0x1p-72f) & (m_cs >= 0x1p-100f);
-                if (!fast) fast = (min_key(fn) >= SFH_NUM_KEY) & (min_key(csum) >= SFH_TINY_KEY);
-                if (fast) {
-                    const V3P fn1 = normalize_fast(fn, len);
-                    const V3P fc = {ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)};
-                    code = AERO ? aero_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack)
-                                : damping_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack);
-                } else { // operands outside the proven range: hardware divisions
-                    V3P fn1, fc;
+                const bool cheap_ok = (m_fn >= 0x1p-72f) & (m_cs >= 0x1p-100f);
+                // One straight-line block: the proven forms run for every pair; the rare pair that fails the cheap test takes the
+                // exact integer test and, outside the proven range, redoes the six quotients with the hardware division.
+                V3P fn1 = normalize_fast(fn, len);
+                V3P fc = {ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)};
+                if (!cheap_ok && !((min_key(fn) >= SFH_NUM_KEY) & (min_key(csum) >= SFH_TINY_KEY)))
                     normalize_centroid_slow(fn, len, csum, fn1, fc);
-                    code = AERO ? aero_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack)
-                                : damping_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack);
-                }
+                code = AERO ? aero_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack)
+                            : damping_pair<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack);
             }
             if (DEBUG) {
                 const uint32_t* of = s_body.orig_face + (size_t)(it.w - it.b_begin) * SFH_CH_FACES;
