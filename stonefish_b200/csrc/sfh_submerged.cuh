@@ -289,12 +289,21 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
         uint32_t nbytes = 0;
         if (lane == 0) walk_issue_next(pa, it, P, cv.next_bytes, nsrc, nbytes);
 
-#pragma unroll
-        for (int k = 0; k < (int)(SFH_CH_VERTS / 32u); ++k) { // each vertex transformed once per chunk (SolidEntity.cpp:1755-1757)
-            const uint32_t i = lane + 32u * k;
-            if (i < cv.nv) {
+        { // each vertex transformed once per chunk (SolidEntity.cpp:1755-1757). Slots 0..191 in one straight-line block without a
+          // per-lane test: T_C is read from shared memory once, every address is a constant offset, nothing diverges. Slots past
+          // the chunk's last vertex read other bytes of the staging buffer (x/y/z[i], i < 256, always lie inside it) and fill
+          // vertex slots no face refers to. The groups above 192 (one chunk in five on a Morton-ordered hull) under
+          // warp-uniform tests.
+            auto xf = [&](uint32_t k) {
+                const uint32_t i = lane + 32u * k;
                 const F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
                 s_v[i] = make_float4(pw.x, pw.y, pw.z, 0.f);
+            };
+#pragma unroll
+            for (uint32_t k = 0; k < 6u; ++k) xf(k);
+            if (cv.nv > 192u) {
+                xf(6u);
+                if (cv.nv > 224u) xf(7u);
             }
         }
         __syncwarp();
