@@ -1,11 +1,18 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (one kernel) into the numbers DESIGN.md / profiles/ quote: duration, DRAM traffic, pipe
 utilisation, issue efficiency, stall reasons, dynamic instruction mix and the hottest SASS lines.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [faces_per_launch]"""
-import collections, csv, io, re, subprocess, sys
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [faces_per_launch] [--traffic-json profiles/ncu_traffic_rNN.json]
+(--traffic-json also writes the per-face DRAM traffic and the pipe utilisations bench.py quotes as roofline.traffic / .secondary)"""
+import collections, csv, io, json, re, subprocess, sys
 
-rep = sys.argv[1]
-faces = float(sys.argv[2]) if len(sys.argv) > 2 else None
+argv = list(sys.argv)
+traffic_json = None
+if "--traffic-json" in argv:
+    i = argv.index("--traffic-json")
+    traffic_json = argv[i + 1]
+    del argv[i:i + 2]
+rep = argv[1]
+faces = float(argv[2]) if len(argv) > 2 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -27,6 +34,23 @@ if faces:
     rd = float(g("dram__bytes_read.sum")[0].replace(",", "")); u = g("dram__bytes_read.sum")[1]
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
     print(f"  DRAM bytes read per face: {rd * mult / faces:.2f}")
+if traffic_json and faces:
+    def num(k):
+        v, u = g(k)
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1, "ms": 1e3, "ns": 1e-3, "%": 0.01}.get(u, 1)
+    rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
+    json.dump({"kernel": g("Kernel Name")[0],
+               "command": "ncu --set full --clock-control none --import-source on -k regex:k_submerged -s 3 -c 1 python bench.py --bodies 1024 --steps 3 --warmup 1 --no-cpu",
+               "faces_per_launch": int(faces), "dram_bytes_read": rd, "dram_bytes_write": wr,
+               "dram_bytes_per_face": round((rd + wr) / faces, 5), "duration_us": num("gpu__time_duration.sum"),
+               "report": "profiles/ncu_k_submerged_r01.txt",
+               "secondary": {"issue_slot_utilisation": round(num("smsp__issue_active.avg.pct_of_peak_sustained_active"), 3),
+                             "fma_pipe": round(num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"), 3),
+                             "xu_pipe": round(num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"), 3),
+                             "alu_pipe": round(num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), 3),
+                             "fp64_pipe": round(num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"), 3),
+                             "dram_throughput_pct_of_peak": round(num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), 3)}},
+              open(traffic_json, "w"), indent=1)
 print("stall reasons (warps stalled per issue-active cycle):")
 st = {h.split("issue_stalled_")[1].split("_per_issue")[0]: float(v) for h, (v, u) in m.items() if "issue_stalled_" in h and h.endswith("per_issue_active.ratio")}
 for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:9]:
