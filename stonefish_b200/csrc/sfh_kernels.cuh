@@ -19,9 +19,13 @@
 
 namespace sfh {
 
-#define SFH_BLOCK 128
+#ifndef SFH_BLOCK
+#define SFH_BLOCK 128 /* threads of a k_surface block: 128 or 64 */
+#endif
+#define SFH_SURF_FPT (256 / SFH_BLOCK) /* faces (and vertices) of a chunk per k_surface thread */
 #define SFH_FULL 0xffffffffu
-#define SFH_SPILL_EVERY 100u /* chunks between counter spills: 2 faces/thread/chunk keeps 8/10-bit fields < 255 */
+#define SFH_SPILL_EVERY 100u /* chunks between counter spills: 8 faces/lane/chunk keeps k_submerged's 10-bit fields < 1023 */
+#define SFH_SURF_SPILL_EVERY (250u / SFH_SURF_FPT) /* ... and SFH_SURF_FPT faces/thread/chunk k_surface's 8-bit fields < 255 */
 
 struct StepParams {
     const BodyDev* bodies;
@@ -168,7 +172,7 @@ namespace sfh {
 // acc: [0..11] Fdq Tdq Fdf Tdf | [12..14] Fb | [15..17] Tb | [18] Swet | [19] Vsub | [20..22] CBsub
 // ---------------------------------------------------------------------------------------------
 #ifndef SFH_SURF_MIN_BLOCKS
-#define SFH_SURF_MIN_BLOCKS 4
+#define SFH_SURF_MIN_BLOCKS (4 * 128 / SFH_BLOCK)
 #endif
 template <bool WAVES, int CUR, bool DEBUG>
 __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(StepParams P)
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
         bool under = !dry; // every vertex of the chunk is under water: !(depth < 0), the reference's own test (:1353)
         if (!dry) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < SFH_SURF_FPT; ++k) {
             const uint32_t i = tid + k * SFH_BLOCK;
             if (i < cv.nv) {
                 F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
@@ -299,14 +303,18 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
         const bool all_wet = __syncthreads_and(under) != 0 && !WAVES; // the chunk's one block barrier (dry chunks included)
         if (tid == 0) walk_issue_next(pa, it, P, cv.next_bytes, nsrc, nbytes);
         if (dry) { // block-uniform
-            cpack += (tid < nf ? 1ull : 0ull) + (tid + SFH_BLOCK < nf ? 1ull : 0ull); // class 0, code 0 (the debug buffer is zero-filled)
+#pragma unroll
+            for (int k = 0; k < SFH_SURF_FPT; ++k) cpack += tid + k * SFH_BLOCK < nf ? 1ull : 0ull; // class 0, code 0 (the debug buffer is zero-filled)
         } else {
 
         if (all_wet) {
             // Every face of the chunk is class 7 (no clipping): the triangle branch of the reference (:1605-1687) for faces tid
             // and tid + 128 side by side, in the pair arithmetic of k_submerged (same per-face terms bit for bit).
-            const bool vA = tid < nf, vB = tid + SFH_BLOCK < nf;
-            const uint32_t fA = vA ? cv.faces[tid] : 0u, fB = vB ? cv.faces[tid + SFH_BLOCK] : 0u;
+#pragma unroll 1
+            for (uint32_t tA = tid; tA < SFH_CH_FACES; tA += 2u * SFH_BLOCK) {
+            const uint32_t tB = tA + SFH_BLOCK;
+            const bool vA = tA < nf, vB = tB < nf;
+            const uint32_t fA = vA ? cv.faces[tA] : 0u, fB = vB ? cv.faces[tB] : 0u;
             const float4 a1 = s_v[__byte_perm(fA, 0, 0x4440)], a2 = s_v[__byte_perm(fA, 0, 0x4441)], a3 = s_v[__byte_perm(fA, 0, 0x4442)];
             const float4 b1 = s_v[__byte_perm(fB, 0, 0x4440)], b2 = s_v[__byte_perm(fB, 0, 0x4441)], b3 = s_v[__byte_perm(fB, 0, 0x4442)];
             const V3P q1 = {pk(a1.x, b1.x), pk(a1.y, b1.y), pk(a1.z, b1.z)};
@@ -365,13 +373,14 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
             }
             if (DEBUG) {
                 const uint32_t* of = s_body.orig_face + (size_t)c * SFH_CH_FACES;
-                if (vA) P.codes[P.code_base[b] + of[tid]] = (uint8_t)(7u | (dA ? SFH_FACE_DEGENERATE : 0u) | (code & 255u));
-                if (vB) P.codes[P.code_base[b] + of[tid + SFH_BLOCK]] = (uint8_t)(7u | (dB ? SFH_FACE_DEGENERATE : 0u) | (code >> 8));
+                if (vA) P.codes[P.code_base[b] + of[tA]] = (uint8_t)(7u | (dA ? SFH_FACE_DEGENERATE : 0u) | (code & 255u));
+                if (vB) P.codes[P.code_base[b] + of[tB]] = (uint8_t)(7u | (dB ? SFH_FACE_DEGENERATE : 0u) | (code >> 8));
             }
+            } // pairs
         } else {
 
 #pragma unroll 1 // interleaving the two faces costs more in instruction fetch than it gains in ILP (0.72 -> 0.87 ms)
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < SFH_SURF_FPT; ++k) {
             const uint32_t slot = tid + k * SFH_BLOCK;
             if (slot >= nf) continue;
             const uint32_t fp = cv.faces[slot];
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(Step
         }
         } // !all_wet
         } // !dry
-        if (++since_spill == SFH_SPILL_EVERY) { spill_epack(epack, s_cnt); spill_cpack(cpack, s_cnt + 4); since_spill = 0; }
+        if (++since_spill == SFH_SURF_SPILL_EVERY) { spill_epack(epack, s_cnt); spill_cpack(cpack, s_cnt + 4); since_spill = 0; }
 
         if (++it.w >= it.w1) break;
         it.s ^= 1;
