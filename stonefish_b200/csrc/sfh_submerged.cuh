@@ -8,7 +8,9 @@
 //   2. has the NEXT chunk (of this or of the next body) already in flight as one bulk async copy (sfh_chunkpipe.cuh),
 //   3. evaluates faces base+lane and base+lane+32 side by side (P2 = one value per face), 4 such pairs per lane per
 //      chunk, with the IEEE divisions and square roots written out (sfh_packed.cuh),
-//   4. adds the fp32 per-face terms into per-lane fp64 accumulators.
+//   4. adds the fp32 per-face terms into per-lane fp64 accumulators under predicates (acc6_if).
+// Steps 1 and 3-4 are straight-line code: no warp vote, no divergent block, one rare branch (operands outside the proven
+// range of the written-out divisions) — ptxas schedules one large block per face pair, which is worth 9 %.
 // Accumulators are reduced per (warp, body) and written as one partial record (see sfh_kernels.cuh).
 #pragma once
 
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
         }
 
         const uint32_t nf = cv.nf;
-#pragma unroll kSubUnroll // unrolling by 2 (112 registers) changes nothing: 0.446 vs 0.444 ms
+#pragma unroll kSubUnroll // 1; unrolling by 2 (127 registers) changes nothing: 0.3994 vs 0.3995 ms
         for (uint32_t base = 0; base < nf; base += 64u) { // faces base+lane and base+lane+32 side by side
             const uint32_t iA = base + lane, iB = iA + 32u;
             const bool vA = iA < nf, vB = iB < nf;
