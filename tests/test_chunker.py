@@ -38,19 +38,7 @@ def _decode(lib, h):
     return n, data, off, orig
 
 
-@pytest.mark.parametrize("keep", [0, 1])
-@pytest.mark.parametrize("mesh", ["ellipsoid", "icosphere_strided", "degenerate_box", "soup"])
-def test_chunks_reproduce_the_mesh(chk, mesh, keep):
-    if mesh == "ellipsoid":
-        m = meshes.uv_ellipsoid(2.5, 0.3, 0.3, 100, 51)
-    elif mesh == "icosphere_strided":
-        m = meshes.icosphere(0.6, 3, stride_floats=11)
-    elif mesh == "degenerate_box":
-        b = meshes.box(1.0, 0.5, 0.2, 2)
-        m = Mesh(b.positions.copy(), np.concatenate([b.faces, [[0, 0, 1], [2, 2, 2]]]).astype(np.uint32))
-    else:  # unshared vertices in random order: worst case for locality, 3 fresh vertices per face
-        r = meshes.splitmix_uniform(9, 900 * 3).reshape(-1, 3).astype(np.float32)
-        m = Mesh(r, np.arange(900, dtype=np.uint32).reshape(-1, 3))
+def _check_roundtrip(chk, m, keep, finite=True):
     h = chk.chk_build(m.vertex_data.ctypes.data, m.stride_bytes, m.n_verts, m.faces.ctypes.data, m.n_faces, keep)
     assert h
     try:
@@ -71,8 +59,10 @@ def test_chunks_reproduce_the_mesh(chk, mesh, keep):
             z = np.frombuffer(data, np.float32, nv, base + 32 + 8 * nv4)
             f = np.frombuffer(data, np.uint32, nf, base + 32 + 12 * nv4)
             sx, sy, sz, sr = (float(t) for t in np.frombuffer(data, np.float32, 4, base + 16))  # bounding sphere of the vertices
-            dist = np.sqrt((x.astype(np.float64) - sx) ** 2 + (y.astype(np.float64) - sy) ** 2 + (z.astype(np.float64) - sz) ** 2)
-            assert dist.max() <= sr <= dist.max() * 1.001 + 1e-6
+            with np.errstate(invalid="ignore"):
+                dist = np.sqrt((x.astype(np.float64) - sx) ** 2 + (y.astype(np.float64) - sy) ** 2 + (z.astype(np.float64) - sz) ** 2)
+            if finite:
+                assert dist.max() <= sr <= dist.max() * 1.001 + 1e-6
             loc = np.stack([f & 255, (f >> 8) & 255, (f >> 16) & 255], axis=1)
             assert (loc < nv).all() and (f >> 24 == 0).all()
             faces = orig[c * 256: c * 256 + nf]
@@ -90,6 +80,22 @@ def test_chunks_reproduce_the_mesh(chk, mesh, keep):
         chk.chk_free(h)
 
 
+@pytest.mark.parametrize("keep", [0, 1])
+@pytest.mark.parametrize("mesh", ["ellipsoid", "icosphere_strided", "degenerate_box", "soup"])
+def test_chunks_reproduce_the_mesh(chk, mesh, keep):
+    if mesh == "ellipsoid":
+        m = meshes.uv_ellipsoid(2.5, 0.3, 0.3, 100, 51)
+    elif mesh == "icosphere_strided":
+        m = meshes.icosphere(0.6, 3, stride_floats=11)
+    elif mesh == "degenerate_box":
+        b = meshes.box(1.0, 0.5, 0.2, 2)
+        m = Mesh(b.positions.copy(), np.concatenate([b.faces, [[0, 0, 1], [2, 2, 2]]]).astype(np.uint32))
+    else:  # unshared vertices in random order: worst case for locality, 3 fresh vertices per face
+        r = meshes.splitmix_uniform(9, 900 * 3).reshape(-1, 3).astype(np.float32)
+        m = Mesh(r, np.arange(900, dtype=np.uint32).reshape(-1, 3))
+    _check_roundtrip(chk, m, keep)
+
+
 def test_morton_order_improves_vertex_sharing(chk):
     m = meshes.uv_ellipsoid(1.2, 0.15, 0.15, 250, 101)
     hs = [chk.chk_build(m.vertex_data.ctypes.data, m.stride_bytes, m.n_verts, m.faces.ctypes.data, m.n_faces, k) for k in (0, 1)]
@@ -104,3 +110,32 @@ def test_bad_index_is_rejected(chk):
     v = np.zeros((3, 3), np.float32)
     f = np.array([[0, 1, 3]], np.uint32)
     assert not chk.chk_build(v.ctypes.data, 12, 3, f.ctypes.data, 1, 0)
+
+
+def test_random_meshes_roundtrip(chk):
+    """Property test over ragged random meshes: any vertex count, any face count (also not a multiple of anything), faces that
+    repeat a vertex, vertices nobody uses, clustered and scattered index patterns, strided vertex records and non-finite
+    coordinates: every face once, bits preserved, limits kept, in both orders."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(1, 700), st.integers(1, 1500), st.integers(0, 2 ** 31), st.sampled_from([3, 6, 11]), st.integers(0, 3), st.integers(0, 1))
+    def run(n_verts, n_faces, seed, stride_floats, pattern, keep):
+        rng = np.random.default_rng(seed)
+        pos = (rng.standard_normal((n_verts, 3)) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+        finite = True
+        if pattern == 3 and n_verts > 2:  # NaN / Inf coordinates travel bit for bit (the kernels let them propagate like the reference)
+            pos[rng.integers(0, n_verts)] = [np.nan, np.inf, -np.inf]
+            finite = False
+        if pattern == 0:    # scattered: almost no sharing
+            faces = rng.integers(0, n_verts, (n_faces, 3))
+        elif pattern == 1:  # clustered: consecutive faces share vertices
+            base = rng.integers(0, n_verts, n_faces)
+            faces = (base[:, None] + rng.integers(0, 4, (n_faces, 3))) % n_verts
+        else:               # strip-like, with repeated vertices inside a face now and then
+            k = np.arange(n_faces)
+            faces = np.stack([k % n_verts, (k + 1) % n_verts, (k + 1 + (k % 7 != 0)) % n_verts], axis=1)
+        m = Mesh(pos, faces.astype(np.uint32), vertex_stride_floats=stride_floats)
+        _check_roundtrip(chk, m, keep, finite)
+
+    run()
