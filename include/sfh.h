@@ -118,7 +118,9 @@ int sfh_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states,
 int sfh_step_debug(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states, uint32_t n_bodies,
                    sfh_info* out, uint8_t* face_codes, size_t face_codes_bytes);
 /* Device-resident variant: d_states / d_out are DEVICE pointers (state already in HBM, results stay in HBM).
- * Only the ocean parameters (a few KB) are copied. Asynchronous on the context's stream. */
+ * Only the ocean parameters (a few KB) are copied. Asynchronous on the context's stream. The states cannot be validated on the
+ * host: a body that names an unknown or released mesh id yields zero forces and makes the NEXT sfh_sync return SFH_ERR_INVALID
+ * (sfh_sync after a device-resident step waits for the stream and fetches the step's status word). */
 int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies,
                     sfh_info* d_out);
 

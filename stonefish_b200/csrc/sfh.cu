@@ -51,6 +51,7 @@ struct sfh_ctx {
     bool own_stream = true;
     int num_sms = 0;
     std::string err;
+    std::mutex err_mutex;  // uploads may fail concurrently
     std::mutex mesh_mutex;
 
     // static geometry
@@ -104,6 +105,7 @@ struct sfh_ctx {
     uint8_t* pending_codes = nullptr;
     size_t pending_codes_bytes = 0;
     bool step_in_flight = false;
+    bool device_step_pending = false; // sfh_step_device / sfh_aero_step_device since the last sfh_sync: its status word is still on the device
 
     // occupancy cache: blocks per SM for [kernel variant]
     int occ_sub[2] = {0, 0};
@@ -147,7 +149,7 @@ int fail(sfh_ctx* ctx, int code, const char* fmt, ...)
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf; else g_create_error = buf;
+    if (ctx) { std::lock_guard<std::mutex> lock(ctx->err_mutex); ctx->err = buf; } else g_create_error = buf;
     return code;
 }
 
@@ -159,10 +161,21 @@ int fail(sfh_ctx* ctx, int code, const char* fmt, ...)
                         cudaGetErrorString(e__), __FILE__, __LINE__);                                         \
     } while (0)
 
+// Captured graphs bake in the addresses of every per-step buffer (states, results, work lists, partial records, status words,
+// the ocean record, the wave planes): whenever one of them is reallocated every cached graph is dropped, whatever its key says
+// (a key that lists "the pointers that matter" is one forgotten pointer away from replaying freed memory).
+void invalidate_graphs(sfh_ctx* ctx)
+{
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec); // deferred by the runtime until in-flight launches have finished
+    ctx->graphs.clear();
+    ctx->last_key_valid = false;
+}
+
 template <typename T>
 int ensure_dev(sfh_ctx* ctx, DevBuf<T>& b, size_t n)
 {
     if (n <= b.cap) return SFH_OK;
+    invalidate_graphs(ctx);
     size_t cap = b.cap ? b.cap : 1;
     while (cap < n) cap *= 2;
     if (b.p) CU(ctx, cudaFree(b.p)); // stream-ordered users finished: callers sync before growing (see prepare)
@@ -175,6 +188,7 @@ int ensure_dev(sfh_ctx* ctx, DevBuf<T>& b, size_t n)
 int ensure_pin(sfh_ctx* ctx, PinBuf& b, size_t bytes)
 {
     if (bytes <= b.cap) return SFH_OK;
+    invalidate_graphs(ctx);
     size_t cap = b.cap ? b.cap : 256;
     while (cap < bytes) cap *= 2;
     if (b.p) CU(ctx, cudaFreeHost(b.p));
@@ -295,7 +309,8 @@ int sync_mesh_table(sfh_ctx* ctx)
     if ((rc = ensure_pin(ctx, ctx->h_mesh_table, n * sizeof(MeshDev))) != SFH_OK) return rc;
     MeshDev* h = static_cast<MeshDev*>(ctx->h_mesh_table.p);
     CU(ctx, cudaStreamSynchronize(ctx->stream)); // previous async copy from this staging buffer is done
-    for (size_t i = 0; i < ctx->meshes.size(); ++i) h[i] = ctx->meshes[i].live ? ctx->meshes[i].dev : MeshDev{nullptr, nullptr, nullptr, 0, 0};
+    // a released id keeps its slot with n_faces = SFH_MESH_TOMBSTONE: k_prologue flags bodies that still refer to it
+    for (size_t i = 0; i < ctx->meshes.size(); ++i) h[i] = ctx->meshes[i].live ? ctx->meshes[i].dev : MeshDev{nullptr, nullptr, nullptr, 0, SFH_MESH_TOMBSTONE};
     CU(ctx, cudaMemcpyAsync(ctx->d_meshes.p, h, ctx->meshes.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
     ctx->mesh_table_dirty = false;
     return SFH_OK;
@@ -705,6 +720,10 @@ int sfh_mesh_upload(sfh_ctx* ctx, const void* pos, size_t stride_bytes, uint32_t
         CU(ctx, cudaMemcpy(d_chunks, cm.chunks.data(), cm.chunks.size(), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemcpy(d_off, cm.chunk_off.data(), cm.chunk_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemcpy(d_orig, cm.orig_face.data(), cm.orig_face.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        // A pageable cudaMemcpy may return once the data is staged, with the DMA still in flight on the legacy stream, and the
+        // context's non-blocking stream is not ordered after it: wait for the legacy stream, so that a step enqueued right after
+        // the upload reads the whole mesh.
+        CU(ctx, cudaStreamSynchronize(cudaStreamLegacy));
         hm.dev.chunks = d_chunks;
         hm.dev.chunk_off = reinterpret_cast<const uint32_t*>(d_off);
         hm.dev.orig_face = reinterpret_cast<const uint32_t*>(d_orig);
@@ -897,7 +916,18 @@ int sfh_sync(sfh_ctx* ctx)
         if (ctx->h_status.p && *static_cast<uint32_t*>(ctx->h_status.p) != 0) {
             cudaMemsetAsync(ctx->d_status.p, 0, sizeof(uint32_t), ctx->stream); // the error flags only
             *static_cast<uint32_t*>(ctx->h_status.p) = 0;
-            return fail(ctx, SFH_ERR_INVALID, "a body referenced an unknown mesh id");
+            ctx->device_step_pending = false;
+            return fail(ctx, SFH_ERR_INVALID, "a body referenced an unknown or released mesh id");
+        }
+    }
+    if (ctx->device_step_pending) { // device-resident steps cannot be validated on the host: fetch the status word they left behind
+        ctx->device_step_pending = false;
+        uint32_t st = 0;
+        CU(ctx, cudaMemcpyAsync(&st, ctx->d_status.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (st != 0) {
+            CU(ctx, cudaMemsetAsync(ctx->d_status.p, 0, sizeof(uint32_t), ctx->stream));
+            return fail(ctx, SFH_ERR_INVALID, "a body of a device-resident step referenced an unknown or released mesh id");
         }
     }
     return SFH_OK;
@@ -969,6 +999,7 @@ int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* 
     int rc = run_step(ctx, ocean, d_states, n_bodies, d_out, plan);
     if (rc != SFH_OK) return rc;
     ctx->ev_valid = ctx->profiling;
+    ctx->device_step_pending = true;
     return SFH_OK;
 }
 
@@ -987,6 +1018,7 @@ int sfh_aero_step_device(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body
     rc = run_step(ctx, &fluid, d_states, n_bodies, d_out, plan);
     if (rc != SFH_OK) return rc;
     ctx->ev_valid = ctx->profiling;
+    ctx->device_step_pending = true;
     return SFH_OK;
 }
 

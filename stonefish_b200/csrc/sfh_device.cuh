@@ -25,6 +25,8 @@ struct MeshDev {
     uint32_t n_faces;
 };
 
+#define SFH_MESH_TOMBSTONE 0xffffffffu /* MeshDev::n_faces of a released mesh id */
+
 enum { KIND_NONE = 0, KIND_SUBMERGED = 1, KIND_SURFACE = 2 };
 enum { BF_DAMPING = 1u, BF_BUOYANCY = 2u };
 
@@ -344,7 +346,9 @@ __device__ __forceinline__ uint64_t chunk_current_mask(const CurGuard* guard, ui
 }
 
 // Ocean::GetFluidVelocity(glm::vec3) with the chunk mask: Uniform fields and the Jet / Pipe fields that can reach the chunk,
-// in list order. Leaving out a field whose value is (+0, +0, +0) cannot change the sum: it starts at +0 and x + 0 = x.
+// in list order. Leaving out a field whose value is (+0, +0, +0) cannot change the sum, signed zeros included: the sum starts at
+// +0 (Ocean.cpp:185) and under round-to-nearest a running sum that started at +0 is never -0 (+0 + -0 = +0, and an exact
+// cancellation gives +0), so the skipped `x + (+0)` is always the identity — a Uniform field with a -0 component included.
 __device__ __forceinline__ F3 fluid_velocity_masked(const sfh_current* cur, uint64_t may, uint32_t n_cur, F3 fc)
 {
     const D3 p = {(double)fc.x, (double)fc.y, (double)fc.z};

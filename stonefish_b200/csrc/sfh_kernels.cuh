@@ -563,8 +563,12 @@ __device__ __forceinline__ void prologue_body(const PrologueParams& P, uint32_t 
         kind = KIND_SURFACE;
     }
     MeshDev m = {nullptr, nullptr, nullptr, 0, 0};
-    if (st.mesh_id < P.n_meshes) m = P.meshes[st.mesh_id];
-    else if (kind != KIND_NONE) atomicOr(P.status, 1u);
+    bool known = st.mesh_id < P.n_meshes;
+    if (known) {
+        m = P.meshes[st.mesh_id];
+        if (m.n_faces == SFH_MESH_TOMBSTONE) { known = false; m.n_faces = 0; } // released by sfh_mesh_release
+    }
+    if (!known && kind != KIND_NONE) atomicOr(P.status, 1u);
     // glMatrixFromTransform / glVectorFromVector (OpenGLDataStructs.cpp:148-171)
     for (int k = 0; k < 9; ++k) bd.R[k] = (float)st.T_C[k];
     for (int k = 0; k < 3; ++k) {

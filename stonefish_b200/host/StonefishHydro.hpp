@@ -502,7 +502,9 @@ inline void SumCompoundParts(const std::vector<CompoundPart>& parts, const Hydro
         add(out.Fb, Fbp); add(out.Tb, Tbp);
         out.Vsub += Vsubp;
         if (p.isExternal) {
-            add(out.Fdq, r.Fdq); add(out.Tdq, r.Tdq); add(out.Fdf, r.Fdf); add(out.Tdf, r.Tdf);
+            // with dampingForces off the reference adds its zero-initialised temporaries (Compound.cpp:395-417): nothing changes.
+            // r.Fdq.. would be stale here (Scatter leaves them untouched when the part's damping was not assigned).
+            if (r.dampingAssigned) { add(out.Fdq, r.Fdq); add(out.Tdq, r.Tdq); add(out.Fdf, r.Fdf); add(out.Tdf, r.Tdf); }
             out.Swet += r.Swet;
         }
     }
