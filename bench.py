@@ -357,7 +357,7 @@ def measure(rig: Rig, args, workload: str, n: int, first: int, keep_host: int, s
 
         # ---- roofline: the per-face kernels alone, timed by events inside libsfh around those launches
         ctx.set_profiling(True)
-        k_ms, pro_ms, epi_ms, launches, dominant = [], [], [], 0, "k_submerged"
+        k_ms, pro_ms, epi_ms, launches, dominant, split = [], [], [], 0, "k_submerged", []
         for _ in range(min(args.steps, 200)):
             step_device()
             t = ctx.timings()
@@ -365,6 +365,9 @@ def measure(rig: Rig, args, workload: str, n: int, first: int, keep_host: int, s
             pro_ms.append(t.prologue_ms); epi_ms.append(t.epilogue_ms)
             launches = t.launches
             dominant = "k_submerged" if t.submerged_ms >= t.surface_ms else "surface path (k_classify + k_surface_wet + k_surface_clip)"
+            split.append((t.classify_ms, t.wet_ms, t.clip_ms))
+            chunks = {"surface": int(t.chunks_surface), "wet": int(t.chunks_wet), "clip": int(t.chunks_clip),
+                      "dry": int(t.chunks_surface - t.chunks_wet - t.chunks_clip)}
         ctx.set_profiling(False)
         rig.barrier()
 
@@ -382,7 +385,8 @@ def measure(rig: Rig, args, workload: str, n: int, first: int, keep_host: int, s
     infos = h_infos.copy()  # results of the last e2e step: the DEBUG=0 kernels on the full-size workload
     res = {"workload": workload, "n": n, "first": first, "faces": faces, "verts": verts, "algo_bytes": algo_bytes, "dev_ms": dev_ms,
            "e2e_ms": e2e_ms, "kern_ms": kern_ms, "pro_ms": float(np.mean(pro_ms)), "epi_ms": float(np.mean(epi_ms)),
-           "launches": int(launches), "dominant": dominant, "setup_s": t_setup, "infos": infos, "scene": scene,
+           "launches": int(launches), "dominant": dominant, "setup_s": t_setup,
+           "surface_split": None if dominant == "k_submerged" else dict(zip(("classify_ms", "wet_ms", "clip_ms"), (float(x) for x in np.mean(split, axis=0))), chunks=chunks), "infos": infos, "scene": scene,
            "host_meshes": host_meshes, "h2d": int(n * BODY_STATE_DTYPE.itemsize), "d2h": int(n * INFO_DTYPE.itemsize + 4)}
     ctx.close()
     del d_states, d_infos
@@ -414,7 +418,7 @@ def roofline_obj(m: dict, peak: float, peak_src: str) -> dict:
     return {"bound": "hbm", "kernel": m["dominant"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(m["algo_bytes"]),
             "kernel_ms": m["kern_ms"], "prologue_ms": m["pro_ms"], "epilogue_ms": m["epi_ms"],
-            "bytes_per_face": ALGO_BYTES_PER_FACE_NOTE, "secondary": secondary}
+            "bytes_per_face": ALGO_BYTES_PER_FACE_NOTE, "secondary": secondary, "surface_split": m["surface_split"]}
 
 
 def workload_record(m: dict, world: int, steps: int, peak: float, peak_src: str, validation: dict | None) -> dict:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFH_ABI_VERSION 1
+#define SFH_ABI_VERSION 2
 
 enum {
     SFH_OK = 0,
@@ -61,6 +61,12 @@ typedef struct sfh_timings {
     uint32_t launches;  /* kernels launched by the step                                             */
     uint32_t reserved;
     uint64_t faces;     /* triangle-evals of the step                                               */
+    /* ABI 2: surface_ms = classify_ms + wet_ms + clip_ms, and how the chunks of the crossing bodies were classified
+     * (dry chunks = chunks_surface - chunks_wet - chunks_clip are dropped unread)                              */
+    float classify_ms;  /* chunk classifier of the surface path                                     */
+    float wet_ms;       /* chunks entirely under water (no clipping)                                */
+    float clip_ms;      /* chunks the water line may cross (eight clipping classes)                 */
+    uint32_t chunks_surface, chunks_wet, chunks_clip;
 } sfh_timings;
 
 int sfh_abi_version(void);

@@ -77,7 +77,8 @@ class sfh_mesh_stats(C.Structure):
 class sfh_timings(C.Structure):
     _fields_ = [("prologue_ms", C.c_float), ("submerged_ms", C.c_float), ("surface_ms", C.c_float),
                 ("epilogue_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("reserved", C.c_uint32),
-                ("faces", C.c_uint64)]
+                ("faces", C.c_uint64), ("classify_ms", C.c_float), ("wet_ms", C.c_float), ("clip_ms", C.c_float),
+                ("chunks_surface", C.c_uint32), ("chunks_wet", C.c_uint32), ("chunks_clip", C.c_uint32)]
 
 
 # numpy structured dtypes with the same layout (used for vectorised scene building and comparisons)
@@ -151,7 +152,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.sfh_abi_version() != 1:
+    if lib.sfh_abi_version() != 2:
         raise RuntimeError("libsfh.so ABI version mismatch")
     if path is None:
         _lib = lib

@@ -40,8 +40,21 @@
 
 namespace sfh {
 
+// One record per chunk, read (coalesced, 32 bytes) by the chunk classifier of the surface path: the axis-aligned box of the
+// chunk's vertices in the mesh frame — centre and half extents, the extents rounded up so that the box contains every vertex —
+// and where the chunk lies in the packed stream. A box follows a flat, elongated patch of a hull far better than a sphere does
+// (cfg 3: 13 % of the chunks straddle the water line by their boxes, 61 % by their spheres).
+struct ChunkBounds {
+    float cx, cy, cz, hx;
+    float hy, hz;
+    uint32_t off16;  // offset of the chunk in the stream, 16-byte units
+    uint32_t bytes;  // its size (multiple of 16)
+};
+static_assert(sizeof(ChunkBounds) == 32, "ChunkBounds is read as two float4");
+
 struct ChunkedMesh {
     std::vector<uint8_t> chunks;     // packed chunk stream
+    std::vector<ChunkBounds> bounds; // n_chunks
     std::vector<uint32_t> chunk_off; // n_chunks + 1 offsets into `chunks`, in 16-byte units
     std::vector<uint32_t> orig_face; // n_chunks * SFH_CH_FACES, 0xFFFFFFFF for unused slots
     uint32_t n_chunks = 0, n_faces = 0, n_verts = 0, n_chunk_verts = 0;
@@ -140,6 +153,17 @@ inline bool chunk_mesh(const void* pos, size_t stride, uint32_t n_verts, const u
         rad = std::nextafter(rad, 3.4e38f);
         const float sphere[4] = {cen[0], cen[1], cen[2], finite ? rad : NAN};
         std::memcpy(p + 16, sphere, sizeof(sphere));
+        ChunkBounds cb;
+        cb.cx = cen[0]; cb.cy = cen[1]; cb.cz = cen[2];
+        float half[3];
+        for (int k = 0; k < 3; ++k) { // largest distance from the (rounded) centre along the axis, rounded up; NaN if not finite
+            const double hk = std::max(hi3[k] - (double)cen[k], (double)cen[k] - lo3[k]) * (1.0 + 1e-6);
+            half[k] = finite && nv ? std::nextafter((float)hk, 3.4e38f) : NAN;
+        }
+        cb.hx = half[0]; cb.hy = half[1]; cb.hz = half[2];
+        cb.off16 = (uint32_t)(base / 16);
+        cb.bytes = bytes;
+        out.bounds.push_back(cb);
         std::memcpy(p + SFH_CH_HDR_BYTES, cx.data(), 4 * nv);
         std::memcpy(p + SFH_CH_HDR_BYTES + 4 * nv4, cy.data(), 4 * nv);
         std::memcpy(p + SFH_CH_HDR_BYTES + 8 * nv4, cz.data(), 4 * nv);

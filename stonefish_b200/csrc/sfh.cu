@@ -87,7 +87,12 @@ struct sfh_ctx {
     DevBuf<BodyDev> d_bodies;
     DevBuf<uint32_t> d_off_sub, d_off_surf, d_status;
     DevBuf<PartialSub> d_part_sub;
-    DevBuf<PartialSurf> d_part_surf;
+    DevBuf<PartialSurf> d_part_wet, d_part_clip;
+    // the surface path's chunk lists (sfh_surface.cuh)
+    DevBuf<uint4> d_items;
+    DevBuf<uint32_t> d_before, d_wet_off, d_clip_off, d_surf_ctrl;
+    DevBuf<uint2> d_tile_cnt;
+    uint32_t max_mesh_chunks = 0; // largest n_chunks of any uploaded mesh: bounds the work list of a device-resident step
     DevBuf<OceanDev> d_ocean;
     DevBuf<uint8_t> d_codes;
     DevBuf<uint64_t> d_code_base;
@@ -110,13 +115,13 @@ struct sfh_ctx {
     // occupancy cache: blocks per SM for [kernel variant]
     int occ_sub[2] = {0, 0};
     int occ_aero[2] = {0, 0};
-    int occ_surf[2][2] = {{0, 0}, {0, 0}};
+    int occ_wet[2][2] = {{0, 0}, {0, 0}}, occ_clip[2][2] = {{0, 0}, {0, 0}};
 
     // CUDA-graph replay of small steps (launch-latency bound): see step_host
     struct GraphKey {
         uint32_t n, n_currents, n_meshes, flags; // flags: general | waves<<1 | may_sub<<2 | may_surf<<3
-        uint64_t chunks_ub;
-        const void *d_states, *d_info, *h_states, *h_info, *h_ocean, *d_ocean, *d_meshes, *d_bodies, *d_part_sub, *d_part_surf, *wave_ch0;
+        uint64_t chunks_ub, surf_ub;
+        const void *d_states, *d_info, *h_states, *h_info, *h_ocean, *d_ocean, *d_meshes, *d_bodies, *d_part_sub, *d_part_wet, *wave_ch0;
         int32_t wave_n;
         float wave_gx, wave_gy;
     };
@@ -134,7 +139,7 @@ struct sfh_ctx {
 
     // profiling
     bool profiling = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [6], [7]: after k_classify, after k_surface_wet
     bool ev_sub = false, ev_surf = false, ev_valid = false;
     uint32_t last_launches = 0;
     uint64_t last_faces = 0;
@@ -223,7 +228,7 @@ int arena_alloc(sfh_ctx* ctx, size_t bytes, uint8_t** out)
 }
 
 template <typename K>
-int occupancy(sfh_ctx* ctx, K kernel, int* cache, int threads = SFH_BLOCK)
+int occupancy(sfh_ctx* ctx, K kernel, int* cache, int threads = SFH_SUB_THREADS)
 {
     if (*cache == 0) {
         int n = 0;
@@ -310,7 +315,7 @@ int sync_mesh_table(sfh_ctx* ctx)
     MeshDev* h = static_cast<MeshDev*>(ctx->h_mesh_table.p);
     CU(ctx, cudaStreamSynchronize(ctx->stream)); // previous async copy from this staging buffer is done
     // a released id keeps its slot with n_faces = SFH_MESH_TOMBSTONE: k_prologue flags bodies that still refer to it
-    for (size_t i = 0; i < ctx->meshes.size(); ++i) h[i] = ctx->meshes[i].live ? ctx->meshes[i].dev : MeshDev{nullptr, nullptr, nullptr, 0, SFH_MESH_TOMBSTONE};
+    for (size_t i = 0; i < ctx->meshes.size(); ++i) h[i] = ctx->meshes[i].live ? ctx->meshes[i].dev : MeshDev{nullptr, nullptr, nullptr, nullptr, 0, SFH_MESH_TOMBSTONE};
     CU(ctx, cudaMemcpyAsync(ctx->d_meshes.p, h, ctx->meshes.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
     ctx->mesh_table_dirty = false;
     return SFH_OK;
@@ -324,13 +329,25 @@ struct StepPlan {
     bool zero_copy_out = false;  // d_out is pinned HOST memory; the epilogue publishes status + sequence number to h_status
     bool may_sub = true, may_surf = true; // host knows no body can reach the kernel -> skip the launch
     uint64_t chunks_ub = 0;      // upper bound of work items (host variant), 0 = unknown
+    uint64_t surf_ub = 0;        // ... of the surface path's items (bodies that may cross the surface); 0 = unknown
     uint64_t faces = 0;
 };
 
 template <int CUR, bool DEBUG, bool AERO = false>
 void launch_sub(const StepParams& P, int grid, cudaStream_t s) { k_submerged<CUR, DEBUG, AERO><<<grid, SFH_SUB_THREADS, 0, s>>>(P); }
-template <bool WAVES, int CUR, bool DEBUG>
-void launch_surf(const StepParams& P, int grid, cudaStream_t s) { k_surface<WAVES, CUR, DEBUG><<<grid, SFH_BLOCK, 0, s>>>(P); }
+template <bool CLIP, bool WAVES, int CUR, bool DEBUG>
+void launch_list(const SurfParams& P, int grid, cudaStream_t s) { k_surface_list<CLIP, WAVES, CUR, DEBUG><<<grid, SFH_SUB_THREADS, 0, s>>>(P); }
+template <bool CLIP>
+void launch_list_variant(const SurfParams& P, int grid, cudaStream_t s, bool waves, bool general, bool debug)
+{
+    if (debug) {
+        if (waves) { if (general) launch_list<CLIP, true, 1, true>(P, grid, s); else launch_list<CLIP, true, 0, true>(P, grid, s); }
+        else       { if (general) launch_list<CLIP, false, 1, true>(P, grid, s); else launch_list<CLIP, false, 0, true>(P, grid, s); }
+    } else {
+        if (waves) { if (general) launch_list<CLIP, true, 1, false>(P, grid, s); else launch_list<CLIP, true, 0, false>(P, grid, s); }
+        else       { if (general) launch_list<CLIP, false, 1, false>(P, grid, s); else launch_list<CLIP, false, 0, false>(P, grid, s); }
+    }
+}
 
 int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n, sfh_info* d_out, const StepPlan& plan)
 {
@@ -339,46 +356,71 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     if ((rc = stage_ocean(ctx, ocean, &general, plan.graph_path)) != SFH_OK) return rc;
     if ((rc = sync_mesh_table(ctx)) != SFH_OK) return rc;
     const bool waves = ocean->has_waves != 0;
+    const int gi = general ? 1 : 0, wi = waves ? 1 : 0;
 
     // persistent grids
     if (plan.aero) {
-        if (general) rc = occupancy(ctx, k_submerged<1, false, true>, &ctx->occ_aero[1], SFH_SUB_THREADS);
-        else         rc = occupancy(ctx, k_submerged<0, false, true>, &ctx->occ_aero[0], SFH_SUB_THREADS);
+        if (general) rc = occupancy(ctx, k_submerged<1, false, true>, &ctx->occ_aero[1]);
+        else         rc = occupancy(ctx, k_submerged<0, false, true>, &ctx->occ_aero[0]);
     } else {
-        if (general) rc = occupancy(ctx, k_submerged<1, false>, &ctx->occ_sub[1], SFH_SUB_THREADS);
-        else         rc = occupancy(ctx, k_submerged<0, false>, &ctx->occ_sub[0], SFH_SUB_THREADS);
+        if (general) rc = occupancy(ctx, k_submerged<1, false>, &ctx->occ_sub[1]);
+        else         rc = occupancy(ctx, k_submerged<0, false>, &ctx->occ_sub[0]);
     }
     if (rc != SFH_OK) return rc;
-    int* occs = &ctx->occ_surf[waves ? 1 : 0][general ? 1 : 0];
     if (waves) {
-        if (general) rc = occupancy(ctx, k_surface<true, 1, false>, occs); else rc = occupancy(ctx, k_surface<true, 0, false>, occs);
+        if (general) { rc = occupancy(ctx, k_surface_list<false, true, 1, false>, &ctx->occ_wet[1][1]); if (rc == SFH_OK) rc = occupancy(ctx, k_surface_list<true, true, 1, false>, &ctx->occ_clip[1][1]); }
+        else         { rc = occupancy(ctx, k_surface_list<false, true, 0, false>, &ctx->occ_wet[1][0]); if (rc == SFH_OK) rc = occupancy(ctx, k_surface_list<true, true, 0, false>, &ctx->occ_clip[1][0]); }
     } else {
-        if (general) rc = occupancy(ctx, k_surface<false, 1, false>, occs); else rc = occupancy(ctx, k_surface<false, 0, false>, occs);
+        if (general) { rc = occupancy(ctx, k_surface_list<false, false, 1, false>, &ctx->occ_wet[0][1]); if (rc == SFH_OK) rc = occupancy(ctx, k_surface_list<true, false, 1, false>, &ctx->occ_clip[0][1]); }
+        else         { rc = occupancy(ctx, k_surface_list<false, false, 0, false>, &ctx->occ_wet[0][0]); if (rc == SFH_OK) rc = occupancy(ctx, k_surface_list<true, false, 0, false>, &ctx->occ_clip[0][0]); }
     }
     if (rc != SFH_OK) return rc;
-    uint64_t g_sub = (uint64_t)ctx->num_sms * (uint64_t)(plan.aero ? ctx->occ_aero : ctx->occ_sub)[general ? 1 : 0];
-    uint64_t g_surf = (uint64_t)ctx->num_sms * (uint64_t)*occs;
-    // g_sub counts BLOCKS; each block runs SFH_SUB_WPB independent streams (one partial record per stream and body)
+    // grids count BLOCKS; each block runs SFH_SUB_WPB independent streams (warps)
+    uint64_t g_sub = (uint64_t)ctx->num_sms * (uint64_t)(plan.aero ? ctx->occ_aero : ctx->occ_sub)[gi];
+    uint64_t g_wet = (uint64_t)ctx->num_sms * (uint64_t)ctx->occ_wet[wi][gi], g_clip = (uint64_t)ctx->num_sms * (uint64_t)ctx->occ_clip[wi][gi];
     if (plan.chunks_ub) {
         if (g_sub * SFH_SUB_WPB > plan.chunks_ub) g_sub = (plan.chunks_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
-        if (g_surf > plan.chunks_ub) g_surf = plan.chunks_ub;
     }
-
-    // k_surface writes one partial record per (segment, body); k_scan_items sizes the segments so that there are at most
-    // SFH_SEG_PER_BLOCK per resident block (sfh_kernels.cuh)
-    const uint64_t n_seg_max = (g_surf ? g_surf : 1) * SFH_SEG_PER_BLOCK + 1;
+    // the surface path's lists hold every chunk of every body that may cross the surface: known exactly for host-side states,
+    // bounded by (bodies x largest mesh) for device-resident ones (k_classify flags a list that does not fit)
+    uint64_t items_ub = plan.surf_ub ? plan.surf_ub : (uint64_t)n * (ctx->max_mesh_chunks ? ctx->max_mesh_chunks : 1u);
+    if (items_ub > ((uint64_t)1 << 26)) items_ub = (uint64_t)1 << 26;
+    const uint64_t items_cap = ((items_ub + SFH_TILE - 1) / SFH_TILE) * SFH_TILE, tiles_cap = items_cap / SFH_TILE;
+    if (plan.surf_ub) {
+        if (g_wet * SFH_SUB_WPB > plan.surf_ub) g_wet = (plan.surf_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
+        if (g_clip * SFH_SUB_WPB > plan.surf_ub) g_clip = (plan.surf_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
+    }
+    uint64_t g_cls = tiles_cap < (uint64_t)ctx->num_sms ? tiles_cap : (uint64_t)ctx->num_sms;
+    if (g_cls == 0) g_cls = 1;
+    // one partial record per (segment, body); k_classify sizes the segments: at most SFH_SEG_PER_STREAM per resident stream
+    const uint64_t seg_wet_max = g_wet * SFH_SUB_WPB * SFH_SEG_PER_STREAM + 1, seg_clip_max = g_clip * SFH_SUB_WPB * SFH_SEG_PER_STREAM + 1;
+    const bool surf = plan.may_surf && !plan.aero;
 
     // buffers (growing them requires the stream to be idle: older kernels may still read the old ones)
-    const bool grow = n > ctx->d_bodies.cap || n + 1 > ctx->d_off_sub.cap || g_sub * SFH_SUB_WPB + n > ctx->d_part_sub.cap || n_seg_max + n > ctx->d_part_surf.cap;
+    bool grow = n > ctx->d_bodies.cap || n + 1 > ctx->d_off_sub.cap || g_sub * SFH_SUB_WPB + n > ctx->d_part_sub.cap;
+    if (surf) grow = grow || seg_wet_max + n > ctx->d_part_wet.cap || seg_clip_max + n > ctx->d_part_clip.cap || items_cap > ctx->d_items.cap ||
+                     tiles_cap + 1 > ctx->d_wet_off.cap;
     if (grow) CU(ctx, cudaStreamSynchronize(ctx->stream));
     if ((rc = ensure_dev(ctx, ctx->d_bodies, n)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_off_sub, n + 1)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_off_surf, n + 1)) != SFH_OK) return rc;
     if ((rc = ensure_dev(ctx, ctx->d_part_sub, g_sub * SFH_SUB_WPB + n)) != SFH_OK) return rc;
-    if ((rc = ensure_dev(ctx, ctx->d_part_surf, n_seg_max + n)) != SFH_OK) return rc;
-    if (!ctx->d_status.p) { // [0] error flags, [1] epilogue blocks finished, [2..3] k_surface segments, [4] zero-copy sequence number
+    if (surf) {
+        if ((rc = ensure_dev(ctx, ctx->d_part_wet, seg_wet_max + n)) != SFH_OK) return rc;
+        if ((rc = ensure_dev(ctx, ctx->d_part_clip, seg_clip_max + n)) != SFH_OK) return rc;
+        if ((rc = ensure_dev(ctx, ctx->d_items, items_cap)) != SFH_OK) return rc;
+        if ((rc = ensure_dev(ctx, ctx->d_before, items_cap)) != SFH_OK) return rc;
+        if ((rc = ensure_dev(ctx, ctx->d_wet_off, tiles_cap + 1)) != SFH_OK) return rc;
+        if ((rc = ensure_dev(ctx, ctx->d_clip_off, tiles_cap + 1)) != SFH_OK) return rc;
+        if ((rc = ensure_dev(ctx, ctx->d_tile_cnt, tiles_cap)) != SFH_OK) return rc;
+    }
+    if (!ctx->d_status.p) { // [0] error flags, [1] epilogue blocks finished, [4] zero-copy sequence number
         if ((rc = ensure_dev(ctx, ctx->d_status, 8)) != SFH_OK) return rc;
         CU(ctx, cudaMemsetAsync(ctx->d_status.p, 0, 8 * sizeof(uint32_t), ctx->stream));
+    }
+    if (!ctx->d_surf_ctrl.p) { // control words of the surface path; SC_ITEMS = 0 until a step classifies something
+        if ((rc = ensure_dev(ctx, ctx->d_surf_ctrl, SC_WORDS)) != SFH_OK) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->d_surf_ctrl.p, 0, SC_WORDS * sizeof(uint32_t), ctx->stream));
     }
 
     const bool prof = ctx->profiling;
@@ -390,11 +432,11 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     pp.off_sub = ctx->d_off_sub.p; pp.off_surf = ctx->d_off_surf.p; pp.status = ctx->d_status.p; pp.aero = plan.aero ? 1u : 0u;
     uint32_t launches;
     if (n <= 1024) {
-        k_prologue_scan<<<1, 1024, 0, ctx->stream>>>(pp, ctx->d_status.p + 2, (uint32_t)g_surf);
+        k_prologue_scan<<<1, 1024, 0, ctx->stream>>>(pp);
         launches = 1;
     } else {
         k_prologue<<<(n + 127) / 128, 128, 0, ctx->stream>>>(pp);
-        k_scan_items<<<1, 1024, 0, ctx->stream>>>(ctx->d_off_sub.p, ctx->d_off_surf.p, n, ctx->d_status.p + 2, (uint32_t)g_surf);
+        k_scan_items<<<1, 1024, 0, ctx->stream>>>(ctx->d_off_sub.p, ctx->d_off_surf.p, n);
         launches = 2;
     }
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -402,7 +444,6 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     StepParams sp;
     sp.bodies = ctx->d_bodies.p; sp.n_bodies = n; sp.ocean = ctx->d_ocean.p; sp.waves = ctx->waves;
     sp.codes = plan.debug ? ctx->d_codes.p : nullptr; sp.code_base = plan.debug ? ctx->d_code_base.p : nullptr;
-    sp.seg_info = ctx->d_status.p + 2;
 
     ctx->ev_sub = ctx->ev_surf = false;
     if (plan.may_sub && g_sub > 0) {
@@ -418,17 +459,25 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
         ctx->ev_sub = true;
     }
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (plan.may_surf && g_surf > 0) {
-        sp.item_off = ctx->d_off_surf.p; sp.partials = ctx->d_part_surf.p;
-        const int g = (int)g_surf;
-        if (plan.debug) {
-            if (waves) { if (general) launch_surf<true, 1, true>(sp, g, ctx->stream); else launch_surf<true, 0, true>(sp, g, ctx->stream); }
-            else       { if (general) launch_surf<false, 1, true>(sp, g, ctx->stream); else launch_surf<false, 0, true>(sp, g, ctx->stream); }
-        } else {
-            if (waves) { if (general) launch_surf<true, 1, false>(sp, g, ctx->stream); else launch_surf<true, 0, false>(sp, g, ctx->stream); }
-            else       { if (general) launch_surf<false, 1, false>(sp, g, ctx->stream); else launch_surf<false, 0, false>(sp, g, ctx->stream); }
-        }
-        ++launches;
+
+    SurfLists L;
+    L.items = ctx->d_items.p; L.before = ctx->d_before.p; L.wet_off = ctx->d_wet_off.p; L.clip_off = ctx->d_clip_off.p;
+    L.tile_cnt = ctx->d_tile_cnt.p; L.ctrl = ctx->d_surf_ctrl.p; L.items_cap = (uint32_t)items_cap;
+    if (surf && g_wet > 0 && g_clip > 0) {
+        ClassifyParams cp;
+        cp.bodies = ctx->d_bodies.p; cp.off_surf = ctx->d_off_surf.p; cp.n_bodies = n; cp.ocean = ctx->d_ocean.p; cp.waves = ctx->waves;
+        cp.L = L; cp.status = ctx->d_status.p; cp.wet_streams = (uint32_t)(g_wet * SFH_SUB_WPB); cp.clip_streams = (uint32_t)(g_clip * SFH_SUB_WPB);
+        k_classify<<<(unsigned)g_cls, SFH_TILE, 0, ctx->stream>>>(cp);
+        if (prof) CU(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+        SurfParams up;
+        up.bodies = ctx->d_bodies.p; up.n_bodies = n; up.ocean = ctx->d_ocean.p; up.waves = ctx->waves; up.L = L; up.off_surf = ctx->d_off_surf.p;
+        up.codes = sp.codes; up.code_base = sp.code_base;
+        up.partials = ctx->d_part_wet.p;
+        launch_list_variant<false>(up, (int)g_wet, ctx->stream, waves, general, plan.debug);
+        if (prof) CU(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+        up.partials = ctx->d_part_clip.p;
+        launch_list_variant<true>(up, (int)g_clip, ctx->stream, waves, general, plan.debug);
+        launches += 3;
         ctx->ev_surf = true;
     }
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -436,8 +485,8 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     EpilogueParams ep;
     ep.states = d_states; ep.bodies = ctx->d_bodies.p; ep.n_bodies = n; ep.ocean = ctx->d_ocean.p;
     ep.off_sub = ctx->d_off_sub.p; ep.off_surf = ctx->d_off_surf.p;
-    ep.part_sub = ctx->d_part_sub.p; ep.part_surf = ctx->d_part_surf.p;
-    ep.grid_sub = (uint32_t)(g_sub * SFH_SUB_WPB); ep.seg_info = ctx->d_status.p + 2; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
+    ep.part_sub = ctx->d_part_sub.p; ep.part_wet = ctx->d_part_wet.p; ep.part_clip = ctx->d_part_clip.p;
+    ep.grid_sub = (uint32_t)(g_sub * SFH_SUB_WPB); ep.L = L; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
     ep.zc_host = nullptr; ep.zc_dev = ctx->d_status.p;
     if (plan.zero_copy_out) {
         void* dp = nullptr;
@@ -484,7 +533,7 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
             if (s.mode == SFH_POS_OUTSIDE) continue;
             plan.chunks_ub += m.stats.n_chunks;
             if (s.mode != SFH_POS_CROSSING) plan.may_sub = true;
-            if (s.mode != SFH_POS_INSIDE) plan.may_surf = true;
+            if (s.mode != SFH_POS_INSIDE) { plan.may_surf = true; plan.surf_ub += m.stats.n_chunks; }
             plan.faces += m.stats.n_faces; // AUTO bodies that turn out OUTSIDE are subtracted by callers via info.n_faces
         }
     }
@@ -527,10 +576,10 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
         }
         key.flags = (general ? 1u : 0u) | (ocean->has_waves ? 2u : 0u) | (plan.may_sub ? 4u : 0u) | (plan.may_surf ? 8u : 0u) | (aero ? 16u : 0u) |
                     (zc ? 32u : 0u);
-        key.chunks_ub = plan.chunks_ub;
+        key.chunks_ub = plan.chunks_ub; key.surf_ub = plan.surf_ub;
         key.d_states = ctx->d_states.p; key.d_info = ctx->d_info.p; key.h_states = ctx->h_states.p; key.h_info = ctx->h_info.p;
         key.h_ocean = ctx->h_ocean.p; key.d_ocean = ctx->d_ocean.p; key.d_meshes = ctx->d_meshes.p; key.d_bodies = ctx->d_bodies.p;
-        key.d_part_sub = ctx->d_part_sub.p; key.d_part_surf = ctx->d_part_surf.p;
+        key.d_part_sub = ctx->d_part_sub.p; key.d_part_wet = ctx->d_part_wet.p;
         key.wave_ch0 = ctx->waves.ch0; key.wave_n = ctx->waves.N; key.wave_gx = ctx->waves.gx; key.wave_gy = ctx->waves.gy;
 
         std::memcpy(ctx->h_states.p, states, sbytes);
@@ -680,7 +729,8 @@ void sfh_destroy(sfh_ctx* ctx)
     cudaFree(ctx->d_wg_bf_src.p); cudaFree(ctx->d_wg_bf_w.p);
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_wave_rgba.p); cudaFree(ctx->d_wave_ch0.p); cudaFree(ctx->d_wave_ch1.p); cudaFree(ctx->d_wave_hmax.p);
     cudaFree(ctx->d_states.p); cudaFree(ctx->d_info.p); cudaFree(ctx->d_bodies.p); cudaFree(ctx->d_off_sub.p);
-    cudaFree(ctx->d_off_surf.p); cudaFree(ctx->d_status.p); cudaFree(ctx->d_part_sub.p); cudaFree(ctx->d_part_surf.p);
+    cudaFree(ctx->d_off_surf.p); cudaFree(ctx->d_status.p); cudaFree(ctx->d_part_sub.p); cudaFree(ctx->d_part_wet.p); cudaFree(ctx->d_part_clip.p);
+    cudaFree(ctx->d_items.p); cudaFree(ctx->d_before.p); cudaFree(ctx->d_wet_off.p); cudaFree(ctx->d_clip_off.p); cudaFree(ctx->d_surf_ctrl.p); cudaFree(ctx->d_tile_cnt.p);
     cudaFree(ctx->d_ocean.p); cudaFree(ctx->d_codes.p); cudaFree(ctx->d_code_base.p);
     for (cudaEvent_t e : ctx->ocean_ev)
         if (e) cudaEventDestroy(e);
@@ -712,9 +762,11 @@ int sfh_mesh_upload(sfh_ctx* ctx, const void* pos, size_t stride_bytes, uint32_t
     hm.stats.algorithmic_bytes = 12ull * n_faces + 12ull * n_verts;
     hm.dev.n_chunks = cm.n_chunks; hm.dev.n_faces = n_faces;
     if (cm.n_chunks) {
-        uint8_t *d_chunks = nullptr, *d_off = nullptr, *d_orig = nullptr;
+        uint8_t *d_chunks = nullptr, *d_off = nullptr, *d_orig = nullptr, *d_bounds = nullptr;
         int rc;
         if ((rc = arena_alloc(ctx, cm.chunks.size(), &d_chunks)) != SFH_OK) return rc;
+        if ((rc = arena_alloc(ctx, cm.bounds.size() * sizeof(ChunkBounds), &d_bounds)) != SFH_OK) return rc;
+        CU(ctx, cudaMemcpy(d_bounds, cm.bounds.data(), cm.bounds.size() * sizeof(ChunkBounds), cudaMemcpyHostToDevice));
         if ((rc = arena_alloc(ctx, cm.chunk_off.size() * sizeof(uint32_t), &d_off)) != SFH_OK) return rc;
         if ((rc = arena_alloc(ctx, cm.orig_face.size() * sizeof(uint32_t), &d_orig)) != SFH_OK) return rc;
         CU(ctx, cudaMemcpy(d_chunks, cm.chunks.data(), cm.chunks.size(), cudaMemcpyHostToDevice));
@@ -727,6 +779,8 @@ int sfh_mesh_upload(sfh_ctx* ctx, const void* pos, size_t stride_bytes, uint32_t
         hm.dev.chunks = d_chunks;
         hm.dev.chunk_off = reinterpret_cast<const uint32_t*>(d_off);
         hm.dev.orig_face = reinterpret_cast<const uint32_t*>(d_orig);
+        hm.dev.bounds = reinterpret_cast<const ChunkBounds*>(d_bounds);
+        if (cm.n_chunks > ctx->max_mesh_chunks) ctx->max_mesh_chunks = cm.n_chunks;
     }
     hm.live = true;
     ctx->meshes.push_back(hm);
@@ -1149,7 +1203,16 @@ int sfh_get_timings(sfh_ctx* ctx, sfh_timings* out)
     CU(ctx, cudaEventSynchronize(ctx->ev[5]));
     CU(ctx, cudaEventElapsedTime(&out->prologue_ms, ctx->ev[1], ctx->ev[2]));
     if (ctx->ev_sub) CU(ctx, cudaEventElapsedTime(&out->submerged_ms, ctx->ev[2], ctx->ev[3]));
-    if (ctx->ev_surf) CU(ctx, cudaEventElapsedTime(&out->surface_ms, ctx->ev[3], ctx->ev[4]));
+    if (ctx->ev_surf) {
+        CU(ctx, cudaEventElapsedTime(&out->surface_ms, ctx->ev[3], ctx->ev[4]));
+        CU(ctx, cudaEventElapsedTime(&out->classify_ms, ctx->ev[3], ctx->ev[6]));
+        CU(ctx, cudaEventElapsedTime(&out->wet_ms, ctx->ev[6], ctx->ev[7]));
+        CU(ctx, cudaEventElapsedTime(&out->clip_ms, ctx->ev[7], ctx->ev[4]));
+        uint32_t ctrl[SC_WORDS];
+        CU(ctx, cudaMemcpyAsync(ctrl, ctx->d_surf_ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        out->chunks_surface = ctrl[SC_ITEMS]; out->chunks_wet = ctrl[SC_WET_TOTAL]; out->chunks_clip = ctrl[SC_CLIP_TOTAL];
+    }
     CU(ctx, cudaEventElapsedTime(&out->epilogue_ms, ctx->ev[4], ctx->ev[5]));
     CU(ctx, cudaEventElapsedTime(&out->total_ms, ctx->ev[0], ctx->ev[5]));
     out->launches = ctx->last_launches;

@@ -6,6 +6,7 @@
 // in its baseline ISA (hard part 1). Denormals are kept (no -ftz).
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -21,6 +22,7 @@ struct MeshDev {
     const uint8_t* chunks;     // packed chunk stream (mesh_chunker.hpp)
     const uint32_t* chunk_off; // n_chunks + 1 offsets into `chunks`, 16-byte units
     const uint32_t* orig_face; // n_chunks * SFH_CH_FACES (debug only)
+    const ChunkBounds* bounds; // n_chunks boxes + stream positions (the chunk classifier of the surface path)
     uint32_t n_chunks;
     uint32_t n_faces;
 };
@@ -48,7 +50,10 @@ struct BodyDev {
     uint32_t pad;
     const uint32_t* chunk_off;
     const uint32_t* orig_face;
+    const ChunkBounds* bounds;
+    uint64_t pad2;
 };
+static_assert(sizeof(BodyDev) % 16 == 0 && offsetof(BodyDev, chunks) % 16 == 0, "the chunk prefetcher reads {chunks, first_bytes} as one uint4");
 
 // Ocean parameters staged on the device once per step.
 struct OceanDev {
@@ -75,7 +80,7 @@ struct PartialSub {
 struct PartialSurf {
     double a[SFH_NACC_SURF]; // Fdq Tdq Fdf Tdf | Fb[3] Tb[3] | Swet Vsub | CBsub[3]
     double pad0;
-    uint32_t cls[8];
+    uint32_t cls[8];         // cls[0] is not counted: class 0 = the body's faces that are in no other class
     uint32_t n_degenerate, n_quadratic, n_skin, pad;
 };
 

@@ -1,31 +1,35 @@
-// sfh_kernels.cuh — the four kernels of one hydrodynamics step (sm_100a).
+// sfh_kernels.cuh — the kernels of one hydrodynamics step (sm_100a).
 //
-//   k_prologue   1 thread/body  per-body: CheckBodyFluidPosition (a9), dispatcher gates (a10), fp64->fp32
-//                               narrowing of transforms/velocities, position-independent current sum,
-//   k_scan_items 1 block        exclusive scan of the per-body chunk counts -> two work lists (submerged / surface)
-//   k_submerged  persistent     per-face ComputeHydrodynamicForcesSubmerged (a1) over (body, chunk) items, one stream per WARP
-//   k_surface    persistent     per-face ComputeHydrodynamicForcesSurface  (a2) incl. waves (a3/a4)
-//   k_epilogue   1 warp/body    fixed-order reduction of the per-block partials, finalisation (A.5),
-//                               INSIDE analytic buoyancy and CorrectHydrodynamicForces (a11)
+//   k_prologue      1 thread/body  per-body: CheckBodyFluidPosition (a9), dispatcher gates (a10), fp64->fp32
+//                                  narrowing of transforms/velocities, position-independent current sum,
+//   k_scan_items    1 block        exclusive scan of the per-body chunk counts -> two work lists (submerged / surface)
+//   k_submerged     persistent     per-face ComputeHydrodynamicForcesSubmerged (a1) over (body, chunk) items, one stream per WARP
+//   k_classify      persistent     surface list -> dry (dropped) / wet / clip chunk lists          (sfh_surface.cuh)
+//   k_surface_wet   persistent     per-face ComputeHydrodynamicForcesSurface (a2), chunks entirely under water, incl. waves (a3/a4)
+//   k_surface_clip  persistent     ... chunks the water line may cross: the eight clipping classes
+//   k_epilogue      1 warp/body    fixed-order reduction of the partial records, finalisation (A.5),
+//                                  INSIDE analytic buoyancy and CorrectHydrodynamicForces (a11)
 //
-// Work decomposition: the work list is the concatenation of every active body's chunks; stream `blk` of G streams
-// (a stream = one block of k_surface, one warp of k_submerged) owns the contiguous item range [blk*W/G, (blk+1)*W/G).
+// Work decomposition of k_submerged: the work list is the concatenation of every active body's chunks; stream `blk` of G streams
+// (a stream = one warp) owns the contiguous item range [blk*W/G, (blk+1)*W/G).
 // A stream keeps fp64 partial sums in registers and writes ONE record per (stream, body) it touched at index blk + body — those indices are unique
 // because block ranges are contiguous and monotone in the body index — so no atomics, no zero-fill, and the
 // epilogue reduces each body's records in a fixed order: results are bitwise reproducible for a given G.
+// The surface kernels hand out SEGMENTS of their lists through an atomic counter and write one record per (segment, body).
 #pragma once
 
 #include "sfh_device.cuh"
 
 namespace sfh {
 
-#ifndef SFH_BLOCK
-#define SFH_BLOCK 128 /* threads of a k_surface block: 128 or 64 */
-#endif
-#define SFH_SURF_FPT (256 / SFH_BLOCK) /* faces (and vertices) of a chunk per k_surface thread */
 #define SFH_FULL 0xffffffffu
-#define SFH_SPILL_EVERY 100u /* chunks between counter spills: 8 faces/lane/chunk keeps k_submerged's 10-bit fields < 1023 */
-#define SFH_SURF_SPILL_EVERY (250u / SFH_SURF_FPT) /* ... and SFH_SURF_FPT faces/thread/chunk k_surface's 8-bit fields < 255 */
+#define SFH_SPILL_EVERY 100u     /* chunks between counter spills of k_submerged */
+#define SFH_LIST_SPILL_EVERY 31u /* ... of the surface kernels */
+// Event counters are packed per lane: 10-bit fields (degenerate | quadratic | skin) and, in k_surface_clip, 8-bit class fields.
+// A lane sees SFH_CH_FACES / 32 faces per chunk, so the fields hold that many events times the chunks between two spills.
+static_assert((SFH_CH_FACES / 32u) * SFH_SPILL_EVERY < 1024u, "k_submerged: 10-bit event counters would overflow between spills");
+static_assert((SFH_CH_FACES / 32u) * SFH_LIST_SPILL_EVERY < 256u, "k_surface_clip: 8-bit class counters would overflow between spills");
+static_assert(SFH_CH_FACES == 256u && SFH_CH_VERTS == 256u, "vertex slots are bytes of the packed face word; the warp kernels transform 8 x 32 vertex slots");
 
 struct StepParams {
     const BodyDev* bodies;
@@ -36,14 +40,7 @@ struct StepParams {
     void* partials;
     uint8_t* codes;            // debug: per-face codes, nullptr otherwise
     const uint64_t* code_base; // debug: first code index of each body
-    uint32_t* seg_info;        // k_surface: [0] next segment to hand out (zeroed by k_scan_items), [1] items per segment
 };
-
-// k_surface hands out its work list in SEGMENTS of seg_info[1] consecutive items through an atomic counter: crossing bodies
-// mix dry chunks (dropped after 32 bytes) with clipped and submerged ones, and a static split leaves SMs idle for a third
-// of the kernel. At most SFH_SEG_PER_BLOCK segments per resident block, at least SFH_SEG_MIN items per segment.
-#define SFH_SEG_PER_BLOCK 16u
-#define SFH_SEG_MIN 1u
 
 __device__ __forceinline__ uint32_t block_of_item(uint64_t w, uint64_t G, uint64_t W)
 {
@@ -66,25 +63,6 @@ __device__ __forceinline__ double warp_sum(double v)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v = dadd(v, __shfl_down_sync(SFH_FULL, v, off));
     return v;
-}
-
-template <int NACC>
-__device__ __forceinline__ void block_reduce_store(double (&acc)[NACC], double (*red)[NACC], double* out)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) {
-        double v = warp_sum(acc[i]);
-        if (lane == 0) red[warp][i] = v;
-        acc[i] = 0.0;
-    }
-    __syncthreads();
-    if (threadIdx.x < NACC) {
-        double s = red[0][threadIdx.x];
-#pragma unroll
-        for (int w = 1; w < SFH_BLOCK / 32; ++w) s = dadd(s, red[w][threadIdx.x]);
-        out[threadIdx.x] = s;
-    }
 }
 
 struct BodyRegs { // hot per-body constants
@@ -125,13 +103,6 @@ __device__ __forceinline__ uint32_t damping_terms(const BodyRegs& B, const sfh_c
     return code;
 }
 
-__device__ __forceinline__ void load_body(BodyDev* sb, const BodyDev* __restrict__ src)
-{
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
-    uint32_t* d = reinterpret_cast<uint32_t*>(sb);
-    for (uint32_t i = threadIdx.x; i < sizeof(BodyDev) / 4; i += SFH_BLOCK) d[i] = __ldg(s + i);
-}
-
 // current parameters and their fp32 pre-test records into shared memory (published by the caller's next block barrier)
 __device__ __forceinline__ void stage_currents(sfh_current* s_cur, CurGuard* s_guard, const OceanDev* __restrict__ ocean, uint32_t n_cur)
 {
@@ -141,353 +112,12 @@ __device__ __forceinline__ void stage_currents(sfh_current* s_cur, CurGuard* s_g
     for (uint32_t i = threadIdx.x; i < n_cur; i += blockDim.x) s_guard[i] = make_cur_guard(ocean->currents[i]);
 }
 
-// 3 x 10-bit event counters (degenerate | quadratic << 10 | skin << 20) -> shared u32 counters
-__device__ __forceinline__ void spill_epack(uint32_t& epack, uint32_t* s_cnt)
-{
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        uint32_t v = __reduce_add_sync(SFH_FULL, (epack >> (10 * k)) & 1023u);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], v);
-    }
-    epack = 0;
-}
-__device__ __forceinline__ void spill_cpack(uint64_t& cpack, uint32_t* s_cls)
-{
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t v = __reduce_add_sync(SFH_FULL, (uint32_t)(cpack >> (8 * k)) & 255u);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cls[k], v);
-    }
-    cpack = 0;
-}
-
 } // namespace sfh
 
-#include "sfh_submerged.cuh" // k_submerged (two faces per thread, packed fp32)
+#include "sfh_submerged.cuh" // k_submerged (two faces per lane side by side)
+#include "sfh_surface.cuh"   // k_classify, k_surface_wet, k_surface_clip
 
 namespace sfh {
-
-// ---------------------------------------------------------------------------------------------
-// k_surface — SolidEntity::ComputeHydrodynamicForcesSurface (SolidEntity.cpp:1337-1687)
-// acc: [0..11] Fdq Tdq Fdf Tdf | [12..14] Fb | [15..17] Tb | [18] Swet | [19] Vsub | [20..22] CBsub
-// ---------------------------------------------------------------------------------------------
-#ifndef SFH_SURF_MIN_BLOCKS
-#define SFH_SURF_MIN_BLOCKS (4 * 128 / SFH_BLOCK)
-#endif
-template <bool WAVES, int CUR, bool DEBUG>
-__global__ void __launch_bounds__(SFH_BLOCK, SFH_SURF_MIN_BLOCKS) k_surface(StepParams P)
-{
-    __shared__ ChunkPipe s_pipe;
-    __shared__ float4 s_v2[2][SFH_CH_VERTS]; // world x,y,z and depth, one buffer per staging buffer
-    __shared__ BodyDev s_body;
-    __shared__ double s_red[SFH_BLOCK / 32][SFH_NACC_SURF];
-    __shared__ uint32_t s_cnt[12]; // [0..2] degenerate quadratic skin, [4..11] classes
-    __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
-    __shared__ CurGuard s_guard[CUR ? SFH_MAX_CURRENTS : 1];
-
-    const uint32_t tid = threadIdx.x;
-    // effective grid = min(launched blocks, work items): every participating block owns >= 1 item, so the
-    // epilogue's [first block, last block] range of a body never contains a block that wrote no record
-    __shared__ uint32_t s_seg;
-    const uint32_t W = P.item_off[P.n_bodies], SC = P.seg_info[1];
-    ItemWalk it;
-    it.s = 0;
-    it.parity = 0;
-
-    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
-    if (CUR) stage_currents(s_cur, s_guard, P.ocean, n_cur);
-    if (tid < 12) s_cnt[tid] = 0;
-    const WavesDev wv = P.waves;
-    const float hmax = WAVES ? __fadd_ru(__uint_as_float(__ldg(wv.hmax)), __uint_as_float(__ldg(wv.hmax + 1))) : 0.f;
-    const WaveConst wc = WAVES ? wave_const(wv) : WaveConst{};
-
-    double acc[SFH_NACC_SURF];
-#pragma unroll
-    for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = 0.0;
-    uint32_t epack = 0, since_spill = 0;
-    uint64_t cpack = 0;
-
-    const PipeAddr pa = pipe_init(s_pipe); // includes a block barrier (publishes s_cur / s_guard / s_cnt)
-    uint32_t seg = 0;
-    BodyRegs B;
-    F3 p0;
-    bool buoy, damp;
-    float zrow;  // >= |row z of T_C|
-    float rnorm; // >= the 2-norm of the linear part of T_C (Frobenius norm)
-
-    auto flush = [&](uint32_t body) {
-        spill_epack(epack, s_cnt);
-        spill_cpack(cpack, s_cnt + 4);
-        since_spill = 0;
-        PartialSurf* rec = reinterpret_cast<PartialSurf*>(P.partials) + (seg + body); // one record per (segment, body)
-        __syncthreads();
-        block_reduce_store<SFH_NACC_SURF>(acc, s_red, rec->a);
-        if (tid < 3) (&rec->n_degenerate)[tid] = s_cnt[tid];
-        if (tid >= 4 && tid < 12) rec->cls[tid - 4] = s_cnt[tid];
-        __syncthreads();
-        if (tid < 12) s_cnt[tid] = 0;
-    };
-    auto fetch_regs = [&]() {
-        B.p = F3{s_body.p[0], s_body.p[1], s_body.p[2]};
-        B.v = F3{s_body.v[0], s_body.v[1], s_body.v[2]};
-        B.omega = F3{s_body.omega[0], s_body.omega[1], s_body.omega[2]};
-        B.cur = F3{s_body.cur[0], s_body.cur[1], s_body.cur[2]};
-        p0 = F3{B.p.x, B.p.y, 0.f}; // SolidEntity.cpp:1332-1334
-        buoy = (s_body.flags & BF_BUOYANCY) != 0;
-        damp = (s_body.flags & BF_DAMPING) != 0;
-        zrow = sqrtf(s_body.R[6] * s_body.R[6] + s_body.R[7] * s_body.R[7] + s_body.R[8] * s_body.R[8]) * 1.000001f;
-        float fro = 0.f;
-        for (int k = 0; k < 9; ++k) fro += s_body.R[k] * s_body.R[k];
-        rnorm = sqrtf(fro) * 1.000001f;
-    };
-
-    for (;;) { // segments
-    __syncthreads(); // the previous segment is flushed and s_seg has been read by everyone
-    if (tid == 0) s_seg = atomicAdd(&P.seg_info[0], 1u);
-    __syncthreads();
-    seg = s_seg;
-    if ((uint64_t)seg * SC >= W) break;
-    it.w = seg * SC;
-    it.w1 = min(it.w + SC, W);
-    it.b = body_of_item(P.item_off, P.n_bodies, it.w);
-    it.b_begin = P.item_off[it.b];
-    it.b_end = P.item_off[it.b + 1];
-    load_body(&s_body, P.bodies + it.b);
-    __syncthreads();
-    if (tid == 0) walk_issue_first(pa, it, s_body);
-    fetch_regs();
-
-    for (;;) { // chunks of the segment
-        pipe_wait(pa, it.s, (it.parity >> it.s) & 1u);
-        it.parity ^= 1u << it.s;
-        const ChunkView cv = chunk_view(s_pipe.buf[it.s]);
-        const uint32_t nf = cv.nf, b = it.b, c = it.w - it.b_begin;
-        // Entirely above the highest possible water surface? Every vertex v of the chunk satisfies |v - centre| <= r in the mesh
-        // frame, so its world z is at most (T_C * centre).z + |row z of T_C| * r (Cauchy-Schwarz; any linear T_C) and its depth
-        // at most that + hmax (z points down, the surface is within +-hmax of z = 0); the last term covers the fp32 rounding
-        // of both transforms. Then every face is class 0 and adds nothing (SolidEntity.cpp:1353-1360).
-        const F3 cw = xform(s_body.R, s_body.t, cv.sphere.x, cv.sphere.y, cv.sphere.z);
-        const float reach = fabsf(s_body.t[2]) + fabsf(cv.sphere.x) + fabsf(cv.sphere.y) + fabsf(cv.sphere.z) + cv.sphere.w;
-        const bool dry = cw.z + zrow * cv.sphere.w + hmax + (4e-6f * reach + 1e-6f) < 0.f;
-        // ... or entirely below the lowest possible surface: every vertex is under water whatever the waves do, every face is
-        // class 7, and the per-vertex wave lookups (used for nothing but the classification then) can be skipped
-        const bool deep = WAVES && cw.z - zrow * cv.sphere.w - hmax - (4e-6f * reach + 1e-6f) > 0.f;
-        // which Jet / Pipe fields can reach this chunk at all (every face centroid lies inside the sphere)
-        const uint64_t cur_may =
-            CUR ? chunk_current_mask(s_guard, n_cur, cw, rnorm * cv.sphere.w + (4e-6f * (reach + fabsf(s_body.t[0]) + fabsf(s_body.t[1])) + 1e-6f)) : 0ull;
-
-        const uint8_t* nsrc = nullptr;
-        uint32_t nbytes = 0;
-        // ONE block barrier per chunk. The vertex buffer alternates with the staging buffer, so the vertex phase of chunk c may
-        // start while other warps still read chunk c-1 (they use the other pair of buffers); the barrier after the vertex phase
-        // publishes s_v AND proves that every thread has left chunk c-1, and only then the copy of chunk c+1 overwrites it
-        // (it still has the whole face phase of chunk c to land). With a barrier on either side of the vertex phase the kernel
-        // was 2 % slower (0.541 -> 0.531 ms per 16 M faces on cfg 5).
-        float4* const s_v = s_v2[it.s];
-        bool under = !dry; // every vertex of the chunk is under water: !(depth < 0), the reference's own test (:1353)
-        if (!dry) {
-#pragma unroll
-        for (int k = 0; k < SFH_SURF_FPT; ++k) {
-            const uint32_t i = tid + k * SFH_BLOCK;
-            if (i < cv.nv) {
-                F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
-                // Ocean::GetDepth per vertex (SolidEntity.cpp:1349-1351): same bits for every incident face
-                const float depth = deep ? 1.f : get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z); // only its sign matters for class 7
-                s_v[i] = make_float4(pw.x, pw.y, pw.z, depth);
-                under = under && !(depth < 0.f);
-            }
-        }
-        // The pair path pays on a flat sea only: with waves its two centroid lookups (and, with Jet/Pipe, two field evaluations)
-        // per thread cost more in registers and instruction fetch than the pairing saves (0.54 -> 0.63 ms on cfg 5).
-        }
-        const bool all_wet = __syncthreads_and(under) != 0 && !WAVES; // the chunk's one block barrier (dry chunks included)
-        if (tid == 0) walk_issue_next(pa, it, P, cv.next_bytes, nsrc, nbytes);
-        if (dry) { // block-uniform
-#pragma unroll
-            for (int k = 0; k < SFH_SURF_FPT; ++k) cpack += tid + k * SFH_BLOCK < nf ? 1ull : 0ull; // class 0, code 0 (the debug buffer is zero-filled)
-        } else {
-
-        if (all_wet) {
-            // Every face of the chunk is class 7 (no clipping): the triangle branch of the reference (:1605-1687) for faces tid
-            // and tid + 128 side by side, in the pair arithmetic of k_submerged (same per-face terms bit for bit).
-#pragma unroll 1
-            for (uint32_t tA = tid; tA < SFH_CH_FACES; tA += 2u * SFH_BLOCK) {
-            const uint32_t tB = tA + SFH_BLOCK;
-            const bool vA = tA < nf, vB = tB < nf;
-            const uint32_t fA = vA ? cv.faces[tA] : 0u, fB = vB ? cv.faces[tB] : 0u;
-            const float4 a1 = s_v[__byte_perm(fA, 0, 0x4440)], a2 = s_v[__byte_perm(fA, 0, 0x4441)], a3 = s_v[__byte_perm(fA, 0, 0x4442)];
-            const float4 b1 = s_v[__byte_perm(fB, 0, 0x4440)], b2 = s_v[__byte_perm(fB, 0, 0x4441)], b3 = s_v[__byte_perm(fB, 0, 0x4442)];
-            const V3P q1 = {pk(a1.x, b1.x), pk(a1.y, b1.y), pk(a1.z, b1.z)};
-            const V3P q2 = {pk(a2.x, b2.x), pk(a2.y, b2.y), pk(a2.z, b2.z)};
-            const V3P q3 = {pk(a3.x, b3.x), pk(a3.y, b3.y), pk(a3.z, b3.z)};
-            cpack += ((vA ? 1ull : 0ull) + (vB ? 1ull : 0ull)) << 56; // class 7
-            if (buoy) { // tetrahedron (p0, p1, p2, p3) of the submerged volume (SolidEntity.cpp:1612-1618)
-                const V3P o0 = {pk1(p0.x), pk1(p0.y), pk1(p0.z)};
-                const V3P t1 = q1 - o0, t2 = q2 - o0, t3 = q3 - o0;
-                const P2 v6 = dot(t1, cross(t2, t3));
-                if (!WAVES) {
-                    const V3P m = (((t1 + t2) + t3) * pk1(0.25f)) * v6;
-                    acc3_if(vA, acc + 20, lo(m.x), lo(m.y), lo(m.z));
-                    acc3_if(vB, acc + 20, hi(m.x), hi(m.y), hi(m.z));
-                }
-                acc1_if(vA, acc[19], lo(v6));
-                acc1_if(vB, acc[19], hi(v6));
-            }
-            const V3P fn = cross(q2 - q1, q3 - q1);
-            const P2 len2 = dot(fn, fn);
-            const bool dA = lo(len2) < 1e-12f, dB = hi(len2) < 1e-12f;
-            const bool mA = vA && !dA, mB = vB && !dB;
-            epack += (vA && dA ? 1u : 0u) + (vB && dB ? 1u : 0u);
-            uint32_t code = 0;
-            if (__any_sync(SFH_FULL, mA | mB)) {
-                const P2 len = ieee_sqrt2(len2); // lanes with len2 < 1e-12 compute garbage that is masked out
-                const P2 A = len * pk1(0.5f);
-                const V3P csum = (q1 + q2) + q3;
-                V3P fn1, fc;
-                if ((min_key(fn) >= SFH_NUM_KEY) & (min_key(csum) >= SFH_TINY_KEY)) {
-                    fn1 = normalize_fast(fn, len);
-                    fc = V3P{ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)};
-                } else {
-                    normalize_centroid_slow(fn, len, csum, fn1, fc);
-                }
-                const V3P pp = {pk1(B.p.x), pk1(B.p.y), pk1(B.p.z)};
-                if (WAVES && buoy) { // pressure buoyancy at the centroid (SolidEntity.cpp:1650-1658)
-                    const float dcA = get_depth<WAVES>(wv, wc, lo(fc.x), lo(fc.y), lo(fc.z));
-                    const float dcB = get_depth<WAVES>(wv, wc, hi(fc.x), hi(fc.y), hi(fc.z));
-                    const P2 nA = neg(A);
-                    const V3P Fbi = (fn1 * nA) * pk(dcA, dcB); // ((-fn1) * A) * depthc: negating A instead of fn1 flips the same sign bits
-                    const V3P Tbi = cross(fc - pp, Fbi);
-                    acc6_if(mA, acc + 12, lo(Fbi.x), lo(Fbi.y), lo(Fbi.z), lo(Tbi.x), lo(Tbi.y), lo(Tbi.z));
-                    acc6_if(mB, acc + 12, hi(Fbi.x), hi(Fbi.y), hi(Fbi.z), hi(Tbi.x), hi(Tbi.y), hi(Tbi.z));
-                }
-                if (damp) {
-                    BodyP2 BP;
-                    BP.p = pp;
-                    BP.v = V3P{pk1(B.v.x), pk1(B.v.y), pk1(B.v.z)};
-                    BP.omega = V3P{pk1(B.omega.x), pk1(B.omega.y), pk1(B.omega.z)};
-                    BP.cur = V3P{pk1(B.cur.x), pk1(B.cur.y), pk1(B.cur.z)};
-                    code = damping_pair<CUR>(BP, s_cur, cur_may, n_cur, fc, fn1, A, mA, mB, acc, epack);
-                }
-                acc1_if(mA, acc[18], lo(A)); // Swet (SolidEntity.cpp:1686)
-                acc1_if(mB, acc[18], hi(A));
-            }
-            if (DEBUG) {
-                const uint32_t* of = s_body.orig_face + (size_t)c * SFH_CH_FACES;
-                if (vA) P.codes[P.code_base[b] + of[tA]] = (uint8_t)(7u | (dA ? SFH_FACE_DEGENERATE : 0u) | (code & 255u));
-                if (vB) P.codes[P.code_base[b] + of[tB]] = (uint8_t)(7u | (dB ? SFH_FACE_DEGENERATE : 0u) | (code >> 8));
-            }
-            } // pairs
-        } else {
-
-#pragma unroll 1 // interleaving the two faces costs more in instruction fetch than it gains in ILP (0.72 -> 0.87 ms)
-        for (int k = 0; k < SFH_SURF_FPT; ++k) {
-            const uint32_t slot = tid + k * SFH_BLOCK;
-            if (slot >= nf) continue;
-            const uint32_t fp = cv.faces[slot];
-            const float4 a4 = s_v[fp & 255u], b4 = s_v[(fp >> 8) & 255u], c4 = s_v[(fp >> 16) & 255u];
-            F3 p1 = {a4.x, a4.y, a4.z}, p2 = {b4.x, b4.y, b4.z}, p3 = {c4.x, c4.y, c4.z};
-            const float d0 = a4.w, d1 = b4.w, d2 = c4.w;
-            const bool a0 = d0 < 0.f, a1 = d1 < 0.f, a2 = d2 < 0.f;
-            const uint32_t cls = (a0 ? 0u : 4u) | (a1 ? 0u : 2u) | (a2 ? 0u : 1u);
-            cpack += 1ull << (8 * cls);
-            uint32_t code = cls;
-            if (cls != 0) {
-                // waterline point on the edge from the submerged vertex pu (du >= 0) to the dry vertex pa (da < 0)
-                auto clip = [](F3 pa, F3 pu, float da, float du) { return pu + (pa - pu) * fdiv(du, fadd(fabsf(da), du)); };
-                // tetrahedron (p0, a, b, c) of the submerged volume (SolidEntity.cpp:1371-1377 and twins)
-                // Vsub / CBsub only reach an output through the buoyancy block (SolidEntity.cpp:1690-1708), and CBsub only on a flat
-                // sea (:1703-1706): they are not accumulated where the reference computes them in vain.
-                auto tetra = [&](F3 pa, F3 pb, F3 pc) {
-                    if (!buoy) return;
-                    float v6 = dot(pa, cross(pb, pc));
-                    if (!WAVES) {
-                        F3 cg = ((pa + pb) + pc) * 0.25f; // "/ 4.f": an exact scaling either way
-                        F3 m = cg * v6;
-                        acc[20] = dadd(acc[20], (double)m.x); acc[21] = dadd(acc[21], (double)m.y); acc[22] = dadd(acc[22], (double)m.z);
-                    }
-                    acc[19] = dadd(acc[19], (double)v6);
-                };
-                F3 p4 = p1, fv1, fv2, fv3, fv4;
-                bool is_quad = false;
-                switch (cls) {
-                case 1: p1 = clip(p1, p3, d0, d2); p2 = clip(p2, p3, d1, d2); break;
-                case 2: p1 = clip(p1, p2, d0, d1); p3 = clip(p3, p2, d2, d1); break;
-                case 3: p4 = clip(p1, p3, d0, d2); p1 = clip(p1, p2, d0, d1); is_quad = true; break;
-                case 4: p2 = clip(p2, p1, d1, d0); p3 = clip(p3, p1, d2, d0); break;
-                case 5: p4 = clip(p2, p3, d1, d2); p2 = clip(p2, p1, d1, d0); is_quad = true; break;
-                case 6: p4 = clip(p3, p1, d2, d0); p3 = clip(p3, p2, d2, d1); is_quad = true; break;
-                default: break;
-                }
-                const F3 p01 = p1 - p0, p02 = p2 - p0, p03 = p3 - p0;
-                tetra(p01, p02, p03);
-                F3 fc;
-                if (is_quad) {
-                    const F3 p04 = p4 - p0;
-                    if (cls == 5) { tetra(p02, p04, p03); fv2 = p3 - p1; }
-                    else          { tetra(p01, p03, p04); fv2 = p4 - p1; }
-                    fv1 = p2 - p1; fv3 = p2 - p3; fv4 = p4 - p3;
-                    fc = (((p1 + p2) + p3) + p4) * 0.25f;
-                } else {
-                    fv1 = p2 - p1; fv2 = p3 - p1;
-                    const F3 cs = (p1 + p2) + p3;
-                    fc = F3{div3(cs.x), div3(cs.y), div3(cs.z)};
-                }
-                F3 fn = cross(fv1, fv2);
-                float len = length2(fn);
-                if (len < 1e-12f) {
-                    epack += 1u;
-                    code |= SFH_FACE_DEGENERATE;
-                } else {
-                    len = ieee_sqrt1(len); // len >= 1e-12
-                    // fn / len: |fn_i| <= len, len >= 1e-6 > 2^-20; components below 2^-36 (not zero) take the hardware division
-                    F3 fn1;
-                    if (min(min(tiny_key(fn.x), tiny_key(fn.y)), tiny_key(fn.z)) >= SFH_NUM_KEY) {
-                        const float r = refined_rcp1(len);
-                        fn1 = F3{ieee_div_r1(fn.x, len, r), ieee_div_r1(fn.y, len, r), ieee_div_r1(fn.z, len, r)};
-                    } else {
-                        fn1 = fn / len;
-                    }
-                    float A; // "/ 2.f": exact scaling
-                    if (is_quad) {
-                        const float l2 = length2(cross(fv3, fv4));
-                        A = fmul(fadd(len, l2 >= 0x1p-100f ? ieee_sqrt1(l2) : fsqrt(l2)), 0.5f);
-                    } else {
-                        A = fmul(len, 0.5f);
-                    }
-                    if (WAVES && buoy) { // SolidEntity.cpp:1650-1658
-                        float depthc = get_depth<WAVES>(wv, wc, fc.x, fc.y, fc.z);
-                        F3 Fbi = ((-fn1) * A) * depthc;
-                        F3 Tbi = cross(fc - B.p, Fbi);
-                        acc[12] = dadd(acc[12], (double)Fbi.x); acc[13] = dadd(acc[13], (double)Fbi.y); acc[14] = dadd(acc[14], (double)Fbi.z);
-                        acc[15] = dadd(acc[15], (double)Tbi.x); acc[16] = dadd(acc[16], (double)Tbi.y); acc[17] = dadd(acc[17], (double)Tbi.z);
-                    }
-                    if (damp) code |= damping_terms<CUR>(B, s_cur, cur_may, n_cur, fc, fn1, A, acc, epack);
-                    acc[18] = dadd(acc[18], (double)A); // SolidEntity.cpp:1686
-                }
-            }
-            if (DEBUG) P.codes[P.code_base[b] + s_body.orig_face[(size_t)c * SFH_CH_FACES + slot]] = (uint8_t)code;
-        }
-        } // !all_wet
-        } // !dry
-        if (++since_spill == SFH_SURF_SPILL_EVERY) { spill_epack(epack, s_cnt); spill_cpack(cpack, s_cnt + 4); since_spill = 0; }
-
-        if (++it.w >= it.w1) break;
-        it.s ^= 1;
-        it.src = nsrc;
-        it.bytes = nbytes;
-        if (it.w >= it.b_end) {
-            flush(it.b);
-            do { ++it.b; it.b_end = P.item_off[it.b + 1]; } while (it.w >= it.b_end);
-            it.b_begin = P.item_off[it.b];
-            load_body(&s_body, P.bodies + it.b);
-            __syncthreads();
-            fetch_regs();
-        }
-    }
-    it.s ^= 1; // the next segment's first copy goes to the other staging buffer
-    flush(it.b);
-    } // segments
-}
 
 // ---------------------------------------------------------------------------------------------
 // k_prologue — per-body gates and narrowing, then the two work-list scans. One block of 1024 threads.
@@ -562,7 +192,7 @@ __device__ __forceinline__ void prologue_body(const PrologueParams& P, uint32_t 
         if (dispatch && !(st.flags & SFH_F_BUOYANT)) buoyancy = false; // SolidEntity.cpp:1844
         kind = KIND_SURFACE;
     }
-    MeshDev m = {nullptr, nullptr, nullptr, 0, 0};
+    MeshDev m = {nullptr, nullptr, nullptr, nullptr, 0, 0};
     bool known = st.mesh_id < P.n_meshes;
     if (known) {
         m = P.meshes[st.mesh_id];
@@ -587,6 +217,8 @@ __device__ __forceinline__ void prologue_body(const PrologueParams& P, uint32_t 
     bd.pad = 0;
     bd.chunk_off = m.chunk_off;
     bd.orig_face = m.orig_face;
+    bd.bounds = m.bounds;
+    bd.pad2 = 0;
     P.bodies[i] = bd;
     // chunk counts; k_scan_items turns them into the two work lists
     P.off_sub[i] = (kind == KIND_SUBMERGED) ? bd.n_chunks : 0u;
@@ -600,7 +232,7 @@ __global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
 }
 
 // In-place exclusive scan of the per-body chunk counts (n_bodies entries -> n_bodies + 1 offsets). One block.
-__device__ __forceinline__ void scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies, uint32_t* seg_info, uint32_t grid_surf)
+__device__ __forceinline__ void scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies)
 {
     __shared__ uint32_t s_warp[2][32];
     __shared__ uint32_t s_carry[2];
@@ -638,23 +270,18 @@ __device__ __forceinline__ void scan_items(uint32_t* off_sub, uint32_t* off_surf
     if (tid == 0) {
         off_sub[n_bodies] = s_carry[0];
         off_surf[n_bodies] = s_carry[1];
-        // k_surface's segment size: at most SFH_SEG_PER_BLOCK segments per resident block
-        const uint32_t cap = max(grid_surf, 1u) * SFH_SEG_PER_BLOCK;
-        seg_info[0] = 0;
-        seg_info[1] = max(SFH_SEG_MIN, (s_carry[1] + cap - 1) / cap);
     }
 }
-__global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies, uint32_t* seg_info,
-                                                     uint32_t grid_surf)
+__global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies)
 {
-    scan_items(off_sub, off_surf, n_bodies, seg_info, grid_surf);
+    scan_items(off_sub, off_surf, n_bodies);
 }
 // Steps of at most 1024 bodies: prologue and scan in one launch (single-body steps are launch-latency bound)
-__global__ void __launch_bounds__(1024) k_prologue_scan(PrologueParams P, uint32_t* seg_info, uint32_t grid_surf)
+__global__ void __launch_bounds__(1024) k_prologue_scan(PrologueParams P)
 {
     if (threadIdx.x < P.n_bodies) prologue_body(P, threadIdx.x);
     __syncthreads();
-    scan_items(P.off_sub, P.off_surf, P.n_bodies, seg_info, grid_surf);
+    scan_items(P.off_sub, P.off_surf, P.n_bodies);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -668,9 +295,10 @@ struct EpilogueParams {
     const uint32_t* off_sub;
     const uint32_t* off_surf;
     const PartialSub* part_sub;
-    const PartialSurf* part_surf;
+    const PartialSurf* part_wet;  // one record per (segment, body) of k_surface_wet
+    const PartialSurf* part_clip; // ... of k_surface_clip
     uint32_t grid_sub;
-    const uint32_t* seg_info; // [1] = items per k_surface segment
+    SurfLists L;                  // the surface path's lists: which segments hold a body's wet / clip chunks
     uint32_t aero;
     sfh_info* out;
     // zero-copy steps (few bodies: `states` and `out` are pinned HOST memory, no copy nodes): the last block to finish
@@ -779,17 +407,26 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
             }
         }
     } else if (kind == KIND_SURFACE) {
-        const uint32_t o0 = P.off_surf[b], o1 = P.off_surf[b + 1];
-        if (o1 > o0) {
-            const uint32_t SC = P.seg_info[1], k0 = o0 / SC, k1 = (o1 - 1) / SC; // segments that overlap this body's items
-            for (uint32_t k = k0 + lane; k <= k1; k += 32) {
-                const PartialSurf& r = P.part_surf[k + b];
+        const uint32_t o0 = P.off_surf[b], o1 = P.off_surf[b + 1], W = P.L.ctrl[SC_ITEMS]; // W = 0: the lists did not fit (status flag)
+        if (o1 > o0 && o1 <= W) {
+            // position of item w in the wet (shift 0) / clip (shift 16) list = entries of earlier tiles + earlier entries of its tile
+            auto rank = [&](const uint32_t* off, uint32_t w, int shift) {
+                return (w & (SFH_TILE - 1u)) == 0u ? off[w / SFH_TILE] : off[w / SFH_TILE] + ((P.L.before[w] >> shift) & 0xffffu);
+            };
+            auto add_records = [&](const PartialSurf* part, uint32_t r0, uint32_t r1, uint32_t SC) {
+                if (r1 <= r0) return;
+                const uint32_t k0 = r0 / SC, k1 = (r1 - 1) / SC; // segments that overlap this body's entries
+                for (uint32_t k = k0 + lane; k <= k1; k += 32) {
+                    const PartialSurf& r = part[k + b];
 #pragma unroll
-                for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = dadd(acc[i], r.a[i]);
-                cnt[0] += r.n_degenerate; cnt[1] += r.n_quadratic; cnt[2] += r.n_skin;
+                    for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = dadd(acc[i], r.a[i]);
+                    cnt[0] += r.n_degenerate; cnt[1] += r.n_quadratic; cnt[2] += r.n_skin;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) cnt[3 + i] += r.cls[i];
-            }
+                    for (int i = 1; i < 8; ++i) cnt[3 + i] += r.cls[i];
+                }
+            };
+            add_records(P.part_wet, rank(P.L.wet_off, o0, 0), rank(P.L.wet_off, o1, 0), P.L.ctrl[SC_WET_SEG]);
+            add_records(P.part_clip, rank(P.L.clip_off, o0, 16), rank(P.L.clip_off, o1, 16), P.L.ctrl[SC_CLIP_SEG]);
         }
     }
     if (kind != KIND_NONE) {
@@ -809,6 +446,11 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
     o.n_faces = (kind != KIND_NONE) ? bd.n_faces : 0u;
     o.n_degenerate = cnt[0]; o.n_quadratic = cnt[1]; o.n_skin = cnt[2];
     for (int k = 0; k < 8; ++k) o.class_count[k] = cnt[3 + k];
+    if (kind == KIND_SURFACE) { // every face is in exactly one class; class 0 (all three vertices dry) is the one nobody counts
+        uint32_t others = 0;
+        for (int k = 1; k < 8; ++k) others += cnt[3 + k];
+        o.class_count[0] = bd.n_faces - others;
+    }
 
     if (P.aero) { // SolidEntity.cpp:1920-1922, then CorrectAerodynamicForces
         const double k = dmul(0.5, oc.density);

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sfh.h but not exported by libsfh.so"
     assert sorted(_abi.PROTOTYPES) == names, "stonefish_b200/_abi.py PROTOTYPES out of sync with include/sfh.h"
-    assert lib.sfh_abi_version() == 1
+    assert lib.sfh_abi_version() == 2
 
 
 def test_struct_layouts_match_the_c_headers(tmp_path):

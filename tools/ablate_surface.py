@@ -8,8 +8,14 @@ st = sc.bind(ctx)
 ctx.set_profiling(True)
 def run(tag):
     for _ in range(3): ctx.compute(sc.ocean, st)
-    t = [ctx.timings().surface_ms for _ in range(5) if ctx.compute(sc.ocean, st) is not None]
-    print(f"{tag:40s} k_surface {np.mean(t):.3f} ms  ({16e6/np.mean(t)/1e6:.1f} G faces/s)")
+    ts = []
+    for _ in range(5):
+        ctx.compute(sc.ocean, st)
+        x = ctx.timings()
+        ts.append((x.surface_ms, x.classify_ms, x.wet_ms, x.clip_ms))
+    t, c, w, k = np.mean(ts, axis=0)
+    fw, fk = x.chunks_wet * 255.1 / 1e6, x.chunks_clip * 255.1 / 1e6
+    print(f"{tag:32s} surface {t:.3f} ms ({16e6/t/1e6:.1f} G faces/s) = classify {c:.3f} + wet {w:.3f} ({fw/w:.1f} G/s on {x.chunks_wet} chunks) + clip {k:.3f} ({fk/k:.1f} G/s on {x.chunks_clip})")
 run("waves + Jet+Pipe")
 sc.ocean.DisableCurrents(); run("waves, no currents")
 sc.ocean.EnableCurrents(); sc.ocean.setWaves(None); run("flat, Jet+Pipe")
