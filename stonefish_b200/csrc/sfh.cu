@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -92,6 +93,8 @@ struct sfh_ctx {
     DevBuf<uint4> d_items;
     DevBuf<uint32_t> d_before, d_wet_off, d_clip_off, d_surf_ctrl;
     DevBuf<uint2> d_tile_cnt;
+    DevBuf<PartialSurf> d_slice_part; // second stage of the epilogue's reduction (few bodies)
+    DevBuf<uint32_t> d_slice_ticket;
     uint32_t max_mesh_chunks = 0; // largest n_chunks of any uploaded mesh: bounds the work list of a device-resident step
     DevBuf<OceanDev> d_ocean;
     DevBuf<uint8_t> d_codes;
@@ -115,7 +118,7 @@ struct sfh_ctx {
     // occupancy cache: blocks per SM for [kernel variant]
     int occ_sub[2] = {0, 0};
     int occ_aero[2] = {0, 0};
-    int occ_wet[2][2] = {{0, 0}, {0, 0}}, occ_clip[2][2] = {{0, 0}, {0, 0}};
+    int occ_surf[2][2] = {{0, 0}, {0, 0}};
 
     // CUDA-graph replay of small steps (launch-latency bound): see step_host
     struct GraphKey {
@@ -139,7 +142,8 @@ struct sfh_ctx {
 
     // profiling
     bool profiling = false;
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [6], [7]: after k_classify, after k_surface_wet
+    bool profile_roles = false; // SFH_PROFILE_ROLES=1: while profiling, time the wet and the clip role in launches of their own
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [6], [7]: after k_classify, after the wet role of k_surface_lists
     bool ev_sub = false, ev_surf = false, ev_valid = false;
     uint32_t last_launches = 0;
     uint64_t last_faces = 0;
@@ -335,17 +339,16 @@ struct StepPlan {
 
 template <int CUR, bool DEBUG, bool AERO = false>
 void launch_sub(const StepParams& P, int grid, cudaStream_t s) { k_submerged<CUR, DEBUG, AERO><<<grid, SFH_SUB_THREADS, 0, s>>>(P); }
-template <bool CLIP, bool WAVES, int CUR, bool DEBUG>
-void launch_list(const SurfParams& P, int grid, cudaStream_t s) { k_surface_list<CLIP, WAVES, CUR, DEBUG><<<grid, SFH_SUB_THREADS, 0, s>>>(P); }
-template <bool CLIP>
-void launch_list_variant(const SurfParams& P, int grid, cudaStream_t s, bool waves, bool general, bool debug)
+template <bool WAVES, int CUR, bool DEBUG>
+void launch_lists(const SurfParams& P, int grid, cudaStream_t s) { k_surface_lists<WAVES, CUR, DEBUG><<<grid, SFH_SUB_THREADS, 0, s>>>(P); }
+void launch_lists_variant(const SurfParams& P, int grid, cudaStream_t s, bool waves, bool general, bool debug)
 {
     if (debug) {
-        if (waves) { if (general) launch_list<CLIP, true, 1, true>(P, grid, s); else launch_list<CLIP, true, 0, true>(P, grid, s); }
-        else       { if (general) launch_list<CLIP, false, 1, true>(P, grid, s); else launch_list<CLIP, false, 0, true>(P, grid, s); }
+        if (waves) { if (general) launch_lists<true, 1, true>(P, grid, s); else launch_lists<true, 0, true>(P, grid, s); }
+        else       { if (general) launch_lists<false, 1, true>(P, grid, s); else launch_lists<false, 0, true>(P, grid, s); }
     } else {
-        if (waves) { if (general) launch_list<CLIP, true, 1, false>(P, grid, s); else launch_list<CLIP, true, 0, false>(P, grid, s); }
-        else       { if (general) launch_list<CLIP, false, 1, false>(P, grid, s); else launch_list<CLIP, false, 0, false>(P, grid, s); }
+        if (waves) { if (general) launch_lists<true, 1, false>(P, grid, s); else launch_lists<true, 0, false>(P, grid, s); }
+        else       { if (general) launch_lists<false, 1, false>(P, grid, s); else launch_lists<false, 0, false>(P, grid, s); }
     }
 }
 
@@ -367,17 +370,13 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
         else         rc = occupancy(ctx, k_submerged<0, false>, &ctx->occ_sub[0]);
     }
     if (rc != SFH_OK) return rc;
-    if (waves) {
-        if (general) { rc = occupancy(ctx, k_surface_list<false, true, 1, false>, &ctx->occ_wet[1][1]); if (rc == SFH_OK) rc = occupancy(ctx, k_surface_list<true, true, 1, false>, &ctx->occ_clip[1][1]); }
-        else         { rc = occupancy(ctx, k_surface_list<false, true, 0, false>, &ctx->occ_wet[1][0]); if (rc == SFH_OK) rc = occupancy(ctx, k_surface_list<true, true, 0, false>, &ctx->occ_clip[1][0]); }
-    } else {
-        if (general) { rc = occupancy(ctx, k_surface_list<false, false, 1, false>, &ctx->occ_wet[0][1]); if (rc == SFH_OK) rc = occupancy(ctx, k_surface_list<true, false, 1, false>, &ctx->occ_clip[0][1]); }
-        else         { rc = occupancy(ctx, k_surface_list<false, false, 0, false>, &ctx->occ_wet[0][0]); if (rc == SFH_OK) rc = occupancy(ctx, k_surface_list<true, false, 0, false>, &ctx->occ_clip[0][0]); }
-    }
+    int* occs = &ctx->occ_surf[wi][gi];
+    if (waves) { if (general) rc = occupancy(ctx, k_surface_lists<true, 1, false>, occs); else rc = occupancy(ctx, k_surface_lists<true, 0, false>, occs); }
+    else       { if (general) rc = occupancy(ctx, k_surface_lists<false, 1, false>, occs); else rc = occupancy(ctx, k_surface_lists<false, 0, false>, occs); }
     if (rc != SFH_OK) return rc;
     // grids count BLOCKS; each block runs SFH_SUB_WPB independent streams (warps)
     uint64_t g_sub = (uint64_t)ctx->num_sms * (uint64_t)(plan.aero ? ctx->occ_aero : ctx->occ_sub)[gi];
-    uint64_t g_wet = (uint64_t)ctx->num_sms * (uint64_t)ctx->occ_wet[wi][gi], g_clip = (uint64_t)ctx->num_sms * (uint64_t)ctx->occ_clip[wi][gi];
+    uint64_t g_wet = (uint64_t)ctx->num_sms * (uint64_t)*occs, g_clip = g_wet; // the two roles of k_surface_lists
     if (plan.chunks_ub) {
         if (g_sub * SFH_SUB_WPB > plan.chunks_ub) g_sub = (plan.chunks_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
     }
@@ -386,11 +385,11 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     uint64_t items_ub = plan.surf_ub ? plan.surf_ub : (uint64_t)n * (ctx->max_mesh_chunks ? ctx->max_mesh_chunks : 1u);
     if (items_ub > ((uint64_t)1 << 26)) items_ub = (uint64_t)1 << 26;
     const uint64_t items_cap = ((items_ub + SFH_TILE - 1) / SFH_TILE) * SFH_TILE, tiles_cap = items_cap / SFH_TILE;
-    if (plan.surf_ub) {
-        if (g_wet * SFH_SUB_WPB > plan.surf_ub) g_wet = (plan.surf_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
-        if (g_clip * SFH_SUB_WPB > plan.surf_ub) g_clip = (plan.surf_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
+    if (plan.surf_ub) { // a list entry is handed out as up to 4 (wet) / 2 (clip) sub-items when there are fewer entries than streams
+        if (g_wet * SFH_SUB_WPB > 4 * plan.surf_ub) g_wet = (4 * plan.surf_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
+        if (g_clip * SFH_SUB_WPB > 2 * plan.surf_ub) g_clip = (2 * plan.surf_ub + SFH_SUB_WPB - 1) / SFH_SUB_WPB;
     }
-    uint64_t g_cls = tiles_cap < (uint64_t)ctx->num_sms ? tiles_cap : (uint64_t)ctx->num_sms;
+    uint64_t g_cls = tiles_cap < (uint64_t)ctx->num_sms * 8 ? tiles_cap : (uint64_t)ctx->num_sms * 8;
     if (g_cls == 0) g_cls = 1;
     // one partial record per (segment, body); k_classify sizes the segments: at most SFH_SEG_PER_STREAM per resident stream
     const uint64_t seg_wet_max = g_wet * SFH_SUB_WPB * SFH_SEG_PER_STREAM + 1, seg_clip_max = g_clip * SFH_SUB_WPB * SFH_SEG_PER_STREAM + 1;
@@ -426,6 +425,19 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     const bool prof = ctx->profiling;
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
+    SurfLists L;
+    L.items = ctx->d_items.p; L.before = ctx->d_before.p; L.wet_off = ctx->d_wet_off.p; L.clip_off = ctx->d_clip_off.p;
+    L.tile_cnt = ctx->d_tile_cnt.p; L.ctrl = ctx->d_surf_ctrl.p; L.items_cap = (uint32_t)items_cap;
+    ClassifyParams cp;
+    cp.bodies = ctx->d_bodies.p; cp.off_surf = ctx->d_off_surf.p; cp.n_bodies = n; cp.ocean = ctx->d_ocean.p; cp.waves = ctx->waves;
+    cp.L = L; cp.status = ctx->d_status.p; cp.wet_streams = (uint32_t)(g_wet * SFH_SUB_WPB); cp.clip_streams = (uint32_t)(g_clip * SFH_SUB_WPB);
+    // Direct mode (sfh_surface.cuh): decided on the device from the number of surface items and T = the consumer's streams. Off
+    // when the two roles are launched one by one to be timed (SFH_PROFILE_ROLES, tools/ablate_surface.py).
+    const bool time_roles = prof && ctx->profile_roles;
+    const uint32_t direct_streams = time_roles ? 0u : (uint32_t)((g_wet + g_clip) * SFH_SUB_WPB);
+    cp.direct_streams = direct_streams;
+    // with host-side states the host knows when the step is certain to run in direct mode: k_classify is not even launched
+    const bool surely_direct = direct_streams && plan.surf_ub && plan.surf_ub <= direct_streams;
     PrologueParams pp;
     pp.states = d_states; pp.meshes = ctx->d_meshes.p; pp.n_meshes = (uint32_t)ctx->meshes.size(); pp.n_bodies = n;
     pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;
@@ -460,24 +472,29 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     }
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
 
-    SurfLists L;
-    L.items = ctx->d_items.p; L.before = ctx->d_before.p; L.wet_off = ctx->d_wet_off.p; L.clip_off = ctx->d_clip_off.p;
-    L.tile_cnt = ctx->d_tile_cnt.p; L.ctrl = ctx->d_surf_ctrl.p; L.items_cap = (uint32_t)items_cap;
     if (surf && g_wet > 0 && g_clip > 0) {
-        ClassifyParams cp;
-        cp.bodies = ctx->d_bodies.p; cp.off_surf = ctx->d_off_surf.p; cp.n_bodies = n; cp.ocean = ctx->d_ocean.p; cp.waves = ctx->waves;
-        cp.L = L; cp.status = ctx->d_status.p; cp.wet_streams = (uint32_t)(g_wet * SFH_SUB_WPB); cp.clip_streams = (uint32_t)(g_clip * SFH_SUB_WPB);
-        k_classify<<<(unsigned)g_cls, SFH_TILE, 0, ctx->stream>>>(cp);
+        if (!surely_direct) {
+            k_classify<<<(unsigned)g_cls, SFH_TILE, 0, ctx->stream>>>(cp);
+            ++launches;
+        }
         if (prof) CU(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
         SurfParams up;
         up.bodies = ctx->d_bodies.p; up.n_bodies = n; up.ocean = ctx->d_ocean.p; up.waves = ctx->waves; up.L = L; up.off_surf = ctx->d_off_surf.p;
         up.codes = sp.codes; up.code_base = sp.code_base;
-        up.partials = ctx->d_part_wet.p;
-        launch_list_variant<false>(up, (int)g_wet, ctx->stream, waves, general, plan.debug);
-        if (prof) CU(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
-        up.partials = ctx->d_part_clip.p;
-        launch_list_variant<true>(up, (int)g_clip, ctx->stream, waves, general, plan.debug);
-        launches += 3;
+        up.part_wet = ctx->d_part_wet.p; up.part_clip = ctx->d_part_clip.p; up.direct_streams = direct_streams;
+        if (time_roles) { // one launch per role, so that each can be timed
+            up.wet_blocks = (uint32_t)g_wet;
+            launch_lists_variant(up, (int)g_wet, ctx->stream, waves, general, plan.debug);
+            CU(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+            up.wet_blocks = 0;
+            launch_lists_variant(up, (int)g_clip, ctx->stream, waves, general, plan.debug);
+            launches += 2;
+        } else {
+            up.wet_blocks = (uint32_t)g_wet;
+            launch_lists_variant(up, (int)(g_wet + g_clip), ctx->stream, waves, general, plan.debug);
+            if (prof) CU(ctx, cudaEventRecord(ctx->ev[7], ctx->stream)); // wet_ms = the whole consumer, clip_ms = 0
+            ++launches;
+        }
         ctx->ev_surf = true;
     }
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -487,13 +504,32 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     ep.off_sub = ctx->d_off_sub.p; ep.off_surf = ctx->d_off_surf.p;
     ep.part_sub = ctx->d_part_sub.p; ep.part_wet = ctx->d_part_wet.p; ep.part_clip = ctx->d_part_clip.p;
     ep.grid_sub = (uint32_t)(g_sub * SFH_SUB_WPB); ep.L = L; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
+    ep.direct_streams = surf ? direct_streams : 0u;
+    ep.team = n <= 256 ? 128u : 32u;
+    // slices of >= 256 records: a body has at most one record per stream (or sub-item) that touched it
+    uint64_t rec_ub = (uint64_t)ctx->num_sms * 16 * SFH_SUB_WPB;
+    if (plan.chunks_ub && 4 * plan.chunks_ub < rec_ub) rec_ub = 4 * plan.chunks_ub;
+    ep.slices = 1;
+    if (ep.team == 128u) {
+        const uint64_t want = rec_ub / n / 256, room = 512u / n;
+        ep.slices = (uint32_t)(want < 1 ? 1 : (want > 16 ? 16 : want));
+        if (ep.slices > room) ep.slices = room ? (uint32_t)room : 1u;
+    }
+    if (ep.slices > 1) {
+        const bool fresh = !ctx->d_slice_ticket.p || n > ctx->d_slice_ticket.cap;
+        if (fresh || (size_t)n * ep.slices > ctx->d_slice_part.cap) CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((rc = ensure_dev(ctx, ctx->d_slice_part, (size_t)n * ep.slices)) != SFH_OK) return rc;
+        if ((rc = ensure_dev(ctx, ctx->d_slice_ticket, n)) != SFH_OK) return rc;
+        if (fresh) CU(ctx, cudaMemsetAsync(ctx->d_slice_ticket.p, 0, ctx->d_slice_ticket.cap * sizeof(uint32_t), ctx->stream)); // the kernel leaves zeros behind
+    }
+    ep.slice_part = ctx->d_slice_part.p; ep.slice_ticket = ctx->d_slice_ticket.p;
     ep.zc_host = nullptr; ep.zc_dev = ctx->d_status.p;
     if (plan.zero_copy_out) {
         void* dp = nullptr;
         CU(ctx, cudaHostGetDevicePointer(&dp, ctx->h_status.p, 0));
         ep.zc_host = static_cast<uint32_t*>(dp);
     }
-    k_epilogue<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ep);
+    k_epilogue<<<ep.team == 128u ? n * ep.slices : (n + 3) / 4, 128, 0, ctx->stream>>>(ep);
     ++launches;
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     CU(ctx, cudaGetLastError());
@@ -730,7 +766,7 @@ void sfh_destroy(sfh_ctx* ctx)
     cudaFree(ctx->d_meshes.p); cudaFree(ctx->d_wave_rgba.p); cudaFree(ctx->d_wave_ch0.p); cudaFree(ctx->d_wave_ch1.p); cudaFree(ctx->d_wave_hmax.p);
     cudaFree(ctx->d_states.p); cudaFree(ctx->d_info.p); cudaFree(ctx->d_bodies.p); cudaFree(ctx->d_off_sub.p);
     cudaFree(ctx->d_off_surf.p); cudaFree(ctx->d_status.p); cudaFree(ctx->d_part_sub.p); cudaFree(ctx->d_part_wet.p); cudaFree(ctx->d_part_clip.p);
-    cudaFree(ctx->d_items.p); cudaFree(ctx->d_before.p); cudaFree(ctx->d_wet_off.p); cudaFree(ctx->d_clip_off.p); cudaFree(ctx->d_surf_ctrl.p); cudaFree(ctx->d_tile_cnt.p);
+    cudaFree(ctx->d_items.p); cudaFree(ctx->d_before.p); cudaFree(ctx->d_wet_off.p); cudaFree(ctx->d_clip_off.p); cudaFree(ctx->d_surf_ctrl.p); cudaFree(ctx->d_tile_cnt.p); cudaFree(ctx->d_slice_part.p); cudaFree(ctx->d_slice_ticket.p);
     cudaFree(ctx->d_ocean.p); cudaFree(ctx->d_codes.p); cudaFree(ctx->d_code_base.p);
     for (cudaEvent_t e : ctx->ocean_ev)
         if (e) cudaEventDestroy(e);
@@ -1190,6 +1226,8 @@ int sfh_set_profiling(sfh_ctx* ctx, int enabled)
 {
     if (!ctx) return SFH_ERR_INVALID;
     ctx->profiling = enabled != 0;
+    const char* roles = getenv("SFH_PROFILE_ROLES");
+    ctx->profile_roles = roles && roles[0] == '1';
     ctx->ev_valid = false;
     return SFH_OK;
 }
@@ -1211,7 +1249,7 @@ int sfh_get_timings(sfh_ctx* ctx, sfh_timings* out)
         uint32_t ctrl[SC_WORDS];
         CU(ctx, cudaMemcpyAsync(ctrl, ctx->d_surf_ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        out->chunks_surface = ctrl[SC_ITEMS]; out->chunks_wet = ctrl[SC_WET_TOTAL]; out->chunks_clip = ctrl[SC_CLIP_TOTAL];
+        out->chunks_surface = ctrl[SC_ITEMS]; out->chunks_wet = ctrl[SC_WET_ENTRIES]; out->chunks_clip = ctrl[SC_CLIP_ENTRIES];
     }
     CU(ctx, cudaEventElapsedTime(&out->epilogue_ms, ctx->ev[4], ctx->ev[5]));
     CU(ctx, cudaEventElapsedTime(&out->total_ms, ctx->ev[0], ctx->ev[5]));

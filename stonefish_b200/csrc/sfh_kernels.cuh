@@ -5,8 +5,8 @@
 //   k_scan_items    1 block        exclusive scan of the per-body chunk counts -> two work lists (submerged / surface)
 //   k_submerged     persistent     per-face ComputeHydrodynamicForcesSubmerged (a1) over (body, chunk) items, one stream per WARP
 //   k_classify      persistent     surface list -> dry (dropped) / wet / clip chunk lists          (sfh_surface.cuh)
-//   k_surface_wet   persistent     per-face ComputeHydrodynamicForcesSurface (a2), chunks entirely under water, incl. waves (a3/a4)
-//   k_surface_clip  persistent     ... chunks the water line may cross: the eight clipping classes
+//   k_surface_lists persistent     per-face ComputeHydrodynamicForcesSurface (a2) incl. waves (a3/a4), one launch, two roles:
+//                                  wet = chunks entirely under water, clip = chunks the water line may cross (eight classes)
 //   k_epilogue      1 warp/body    fixed-order reduction of the partial records, finalisation (A.5),
 //                                  INSIDE analytic buoyancy and CorrectHydrodynamicForces (a11)
 //
@@ -115,7 +115,7 @@ __device__ __forceinline__ void stage_currents(sfh_current* s_cur, CurGuard* s_g
 } // namespace sfh
 
 #include "sfh_submerged.cuh" // k_submerged (two faces per lane side by side)
-#include "sfh_surface.cuh"   // k_classify, k_surface_wet, k_surface_clip
+#include "sfh_surface.cuh"   // k_classify, k_surface_lists
 
 namespace sfh {
 
@@ -299,6 +299,13 @@ struct EpilogueParams {
     const PartialSurf* part_clip; // ... of k_surface_clip
     uint32_t grid_sub;
     SurfLists L;                  // the surface path's lists: which segments hold a body's wet / clip chunks
+    uint32_t direct_streams;      // T of direct_split (sfh_surface.cuh)
+    uint32_t team;                // threads that reduce one body's records: 32 (4 bodies per block) or 128 (one body per block)
+    // Few bodies with thousands of partial records each (a single hull: one record per warp of the face kernel): `slices` blocks
+    // per body add a share of the records each and leave a slice total; the last one to finish adds the totals in slice order.
+    uint32_t slices;              // blocks per body (team == 128 only); 1 = no second stage
+    PartialSurf* slice_part;      // n_bodies * slices
+    uint32_t* slice_ticket;       // n_bodies, zero between steps
     uint32_t aero;
     sfh_info* out;
     // zero-copy steps (few bodies: `states` and `out` are pinned HOST memory, no copy nodes): the last block to finish
@@ -361,13 +368,18 @@ __device__ inline void correct_aero(double* Fda, double* Tda, const double* Cd, 
     for (int k = 0; k < 3; ++k) { Fda[k] = dmul(Fda[k], cor); Tda[k] = dmul(Tda[k], cor); }
 }
 
-__device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t b, uint32_t lane);
+__device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t b, uint32_t t, uint32_t team, double (*s_red)[SFH_NACC_SURF],
+                                              uint32_t (*s_cnt)[11]);
 
+// Few bodies (a small scene, a single hull with thousands of partial records): one body per BLOCK, its records spread over 128
+// threads; otherwise one body per warp. Either way the order of the sums is fixed.
 __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b < P.n_bodies) epilogue_body(P, b, lane);
+    __shared__ double s_red[4][SFH_NACC_SURF];
+    __shared__ uint32_t s_cnt[4][11];
+    const uint32_t per_block = 128u / P.team;
+    const uint32_t b = P.team == 128u ? blockIdx.x / P.slices : blockIdx.x * per_block + threadIdx.x / P.team;
+    if (b < P.n_bodies) epilogue_body(P, b, threadIdx.x % P.team, P.team, s_red, s_cnt);
     if (P.zc_host) {
         __threadfence_system(); // this thread's record (if it wrote one) is visible to the host before the flag can be
         __syncthreads();
@@ -382,7 +394,8 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
     }
 }
 
-__device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t b, uint32_t lane)
+__device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t b, uint32_t t, uint32_t team, double (*s_red)[SFH_NACC_SURF],
+                                              uint32_t (*s_cnt)[11])
 {
     const BodyDev& bd = P.bodies[b];
     const uint32_t kind = bd.kind & 255u, pos = bd.kind >> 8;
@@ -394,12 +407,14 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
 #pragma unroll
     for (int i = 0; i < 11; ++i) cnt[i] = 0;
 
+    // this block's share of the records: every (slices)-th group of `team` records, starting at group `sl`
+    const uint32_t S = team == 128u ? P.slices : 1u, sl = team == 128u ? blockIdx.x % S : 0u, stride = team * S, first = t + sl * team;
     if (kind == KIND_SUBMERGED) {
         const uint32_t o0 = P.off_sub[b], o1 = P.off_sub[b + 1];
         if (o1 > o0) {
             const uint64_t W = P.off_sub[P.n_bodies], G = min((uint64_t)P.grid_sub, W);
             const uint32_t k0 = block_of_item(o0, G, W), k1 = block_of_item(o1 - 1, G, W);
-            for (uint32_t k = k0 + lane; k <= k1; k += 32) {
+            for (uint32_t k = k0 + first; k <= k1; k += stride) {
                 const PartialSub& r = P.part_sub[k + b];
 #pragma unroll
                 for (int i = 0; i < SFH_NACC_SUB; ++i) acc[i] = dadd(acc[i], r.a[i]);
@@ -407,35 +422,92 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
             }
         }
     } else if (kind == KIND_SURFACE) {
-        const uint32_t o0 = P.off_surf[b], o1 = P.off_surf[b + 1], W = P.L.ctrl[SC_ITEMS]; // W = 0: the lists did not fit (status flag)
-        if (o1 > o0 && o1 <= W) {
+        const uint32_t o0 = P.off_surf[b], o1 = P.off_surf[b + 1], Wall = P.off_surf[P.n_bodies];
+        auto add_records = [&](const PartialSurf* part, uint32_t r0, uint32_t r1, uint32_t SC) {
+            if (r1 <= r0) return;
+            const uint32_t k0 = r0 / SC, k1 = (r1 - 1) / SC; // segments that overlap this body's entries
+            for (uint32_t k = k0 + first; k <= k1; k += stride) {
+                const PartialSurf& r = part[k + b];
+#pragma unroll
+                for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = dadd(acc[i], r.a[i]);
+                cnt[0] += r.n_degenerate; cnt[1] += r.n_quadratic; cnt[2] += r.n_skin;
+#pragma unroll
+                for (int i = 1; i < 8; ++i) cnt[3 + i] += r.cls[i];
+            }
+        };
+        const uint32_t dsplit = direct_split(Wall <= P.L.items_cap ? Wall : 0u, P.direct_streams);
+        if (dsplit) { // direct mode: one record per sub-item, `dsplit` consecutive ones per chunk
+            add_records(P.part_wet, o0 * dsplit, o1 * dsplit, 1u);
+        } else if (o1 > o0 && o1 <= P.L.ctrl[SC_ITEMS]) { // SC_ITEMS = 0: the lists did not fit (status flag)
             // position of item w in the wet (shift 0) / clip (shift 16) list = entries of earlier tiles + earlier entries of its tile
             auto rank = [&](const uint32_t* off, uint32_t w, int shift) {
                 return (w & (SFH_TILE - 1u)) == 0u ? off[w / SFH_TILE] : off[w / SFH_TILE] + ((P.L.before[w] >> shift) & 0xffffu);
             };
-            auto add_records = [&](const PartialSurf* part, uint32_t r0, uint32_t r1, uint32_t SC) {
-                if (r1 <= r0) return;
-                const uint32_t k0 = r0 / SC, k1 = (r1 - 1) / SC; // segments that overlap this body's entries
-                for (uint32_t k = k0 + lane; k <= k1; k += 32) {
-                    const PartialSurf& r = part[k + b];
-#pragma unroll
-                    for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = dadd(acc[i], r.a[i]);
-                    cnt[0] += r.n_degenerate; cnt[1] += r.n_quadratic; cnt[2] += r.n_skin;
-#pragma unroll
-                    for (int i = 1; i < 8; ++i) cnt[3 + i] += r.cls[i];
-                }
-            };
-            add_records(P.part_wet, rank(P.L.wet_off, o0, 0), rank(P.L.wet_off, o1, 0), P.L.ctrl[SC_WET_SEG]);
-            add_records(P.part_clip, rank(P.L.clip_off, o0, 16), rank(P.L.clip_off, o1, 16), P.L.ctrl[SC_CLIP_SEG]);
+            // segments count sub-items: `split` consecutive ones per list entry
+            const uint32_t ws = P.L.ctrl[SC_WET_SPLIT], cs = P.L.ctrl[SC_CLIP_SPLIT];
+            add_records(P.part_wet, rank(P.L.wet_off, o0, 0) * ws, rank(P.L.wet_off, o1, 0) * ws, P.L.ctrl[SC_WET_SEG]);
+            add_records(P.part_clip, rank(P.L.clip_off, o0, 16) * cs, rank(P.L.clip_off, o1, 16) * cs, P.L.ctrl[SC_CLIP_SEG]);
         }
     }
+    const uint32_t lane = t & 31u;
     if (kind != KIND_NONE) {
 #pragma unroll
         for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = warp_sum(acc[i]);
 #pragma unroll
         for (int i = 0; i < 11; ++i) cnt[i] = __reduce_add_sync(SFH_FULL, cnt[i]);
     }
-    if (lane != 0) return;
+    if (team == 128u) { // the four warps' sums, added in warp order
+        const uint32_t wp = t >> 5;
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < SFH_NACC_SURF; ++i) s_red[wp][i] = acc[i];
+#pragma unroll
+            for (int i = 0; i < 11; ++i) s_cnt[wp][i] = cnt[i];
+        }
+        __syncthreads();
+        if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = dadd(dadd(dadd(s_red[0][i], s_red[1][i]), s_red[2][i]), s_red[3][i]);
+#pragma unroll
+            for (int i = 0; i < 11; ++i) cnt[i] = s_cnt[0][i] + s_cnt[1][i] + s_cnt[2][i] + s_cnt[3][i];
+        }
+        if (S > 1u) { // second stage: slice totals, added in slice order by the block that finishes last
+            __shared__ uint32_t s_last;
+            PartialSurf* mine = P.slice_part + (size_t)b * S;
+            if (t == 0) {
+                PartialSurf& o = mine[sl];
+#pragma unroll
+                for (int i = 0; i < SFH_NACC_SURF; ++i) o.a[i] = acc[i];
+                o.n_degenerate = cnt[0]; o.n_quadratic = cnt[1]; o.n_skin = cnt[2];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o.cls[i] = cnt[3 + i];
+                __threadfence();
+                s_last = atomicAdd(&P.slice_ticket[b], 1u) == S - 1u ? 1u : 0u;
+            }
+            __syncthreads();
+            if (!s_last) return;
+            __threadfence();
+            if (t < (uint32_t)SFH_NACC_SURF) {
+                double v = 0.0;
+                for (uint32_t k = 0; k < S; ++k) v = dadd(v, __ldcg(&mine[k].a[t]));
+                s_red[0][t] = v;
+            } else if (t >= 32u && t < 43u) {
+                const uint32_t f = t - 32u;
+                uint32_t c = 0;
+                for (uint32_t k = 0; k < S; ++k) c += f < 3u ? __ldcg(&mine[k].n_degenerate + f) : __ldcg(&mine[k].cls[f - 3u]);
+                s_cnt[0][f] = c;
+            }
+            __syncthreads();
+            if (t == 0) {
+#pragma unroll
+                for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = s_red[0][i];
+#pragma unroll
+                for (int i = 0; i < 11; ++i) cnt[i] = s_cnt[0][i];
+                P.slice_ticket[b] = 0;
+            }
+        }
+    }
+    if (t != 0) return;
 
     const sfh_body_state& st = P.states[b];
     const OceanDev& oc = *P.ocean;

@@ -44,6 +44,34 @@ __device__ __forceinline__ void normalize_centroid_slow(V3P fn, P2 len, V3P s, V
     fc.z = pk(__fdiv_rn(lo(s.z), 3.f), __fdiv_rn(hi(s.z), 3.f));
 }
 
+// The scalar per-face pieces of a pair — the fp64 current evaluation, the wave lookups — run as a two-trip loop that is NOT
+// unrolled: one copy of ~300 (currents) / ~200 (waves) instructions instead of two. The face kernels are bound by instruction
+// issue AND by instruction fetch (k_surface_wet under waves and Jet + Pipe: 163 KB of SASS, `no_instruction` 1.0 warps per issue
+// cycle), so code that is executed twice should exist once.
+__device__ __forceinline__ V3P fluid_velocity_pair(const sfh_current* s_cur, uint64_t cur_may, uint32_t n_cur, V3P fc)
+{
+    F3 out[2];
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {
+        const F3 c = f ? F3{hi(fc.x), hi(fc.y), hi(fc.z)} : F3{lo(fc.x), lo(fc.y), lo(fc.z)};
+        const F3 r = fluid_velocity_masked(s_cur, cur_may, n_cur, c);
+        if (f) out[1] = r; else out[0] = r;
+    }
+    return V3P{pk(out[0].x, out[1].x), pk(out[0].y, out[1].y), pk(out[0].z, out[1].z)};
+}
+template <bool WAVES>
+__device__ __forceinline__ P2 depth_pair(const WavesDev& wv, const WaveConst& wc, V3P fc)
+{
+    float out[2];
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {
+        const F3 c = f ? F3{hi(fc.x), hi(fc.y), hi(fc.z)} : F3{lo(fc.x), lo(fc.y), lo(fc.z)};
+        const float d = get_depth<WAVES>(wv, wc, c.x, c.y, c.z);
+        if (f) out[1] = d; else out[0] = d;
+    }
+    return pk(out[0], out[1]);
+}
+
 struct BodyP2 { // per-body constants broadcast to both lanes
     V3P p, v, omega, cur;
     float R[9], t[3]; // T_C, for the per-chunk vertex transform
@@ -56,11 +84,7 @@ __device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_curr
                                                  V3P fn1, P2 A, bool mA, bool mB, double* acc, uint32_t& epack)
 {
     V3P fluid = B.cur; // sum of the enabled Uniform fields; complete when no Jet / Pipe field reaches the chunk
-    if (CUR && cur_may) {
-        const F3 fa = fluid_velocity_masked(s_cur, cur_may, n_cur, F3{lo(fc.x), lo(fc.y), lo(fc.z)});
-        const F3 fb = fluid_velocity_masked(s_cur, cur_may, n_cur, F3{hi(fc.x), hi(fc.y), hi(fc.z)});
-        fluid = V3P{pk(fa.x, fb.x), pk(fa.y, fb.y), pk(fa.z, fb.z)};
-    }
+    if (CUR && cur_may) fluid = fluid_velocity_pair(s_cur, cur_may, n_cur, fc);
     const V3P r = fc - B.p;
     const V3P vc = fluid - (B.v + cross(B.omega, r));
     const P2 vc_n = dot(vc, fn1);
@@ -100,11 +124,7 @@ __device__ __forceinline__ uint32_t aero_pair(const BodyP2& B, const sfh_current
                                               V3P fn1, P2 A, bool mA, bool mB, double* acc, uint32_t& epack)
 {
     V3P fluid = B.cur; // sum of the enabled Uniform fields; complete when no Jet / Pipe field reaches the chunk
-    if (CUR && cur_may) {
-        const F3 fa = fluid_velocity_masked(s_cur, cur_may, n_cur, F3{lo(fc.x), lo(fc.y), lo(fc.z)});
-        const F3 fb = fluid_velocity_masked(s_cur, cur_may, n_cur, F3{hi(fc.x), hi(fc.y), hi(fc.z)});
-        fluid = V3P{pk(fa.x, fb.x), pk(fa.y, fb.y), pk(fa.z, fb.z)};
-    }
+    if (CUR && cur_may) fluid = fluid_velocity_pair(s_cur, cur_may, n_cur, fc);
     const V3P r = fc - B.p;
     const V3P vc = fluid - (B.v + cross(B.omega, r));
     const V3P vn = fn1 * dot(vc, fn1);

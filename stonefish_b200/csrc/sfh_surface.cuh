@@ -11,10 +11,11 @@
 //                   around its value at the footprint's centre). Items are compacted per tile of 1024 into two lists of
 //                   descriptors (wet from the front of the tile's region, clip from its back); the last block to finish scans
 //                   the tile counts and sizes the consumers' segments.
-//   k_surface_wet   k_submerged's machinery — one stream per WARP, chunks staged by bulk async copies, vertices transformed once
+//   k_surface_lists one launch, two roles by block index:
+//    wet role       k_submerged's machinery — one stream per WARP, chunks staged by bulk async copies, vertices transformed once
 //                   per chunk, two faces per lane side by side in one straight-line block, no block barrier — plus the tetrahedron
 //                   sums of the submerged volume, the pressure term (one wave lookup per face centroid) and Swet. Also under waves.
-//   k_surface_clip  the reference's eight classes, one face per lane at a time; the same warp streams.
+//    clip role      the reference's eight classes, one face per lane at a time; the same warp streams.
 //
 // The classification is conservative: "dry" and "wet" are only claimed when the bound proves them for every vertex with the
 // reference's own fp32 arithmetic (margins below); everything else is "clip", which is exact for any input. The per-face class
@@ -28,11 +29,14 @@
 
 namespace sfh {
 
-#define SFH_TILE 1024u        /* items per classification tile = threads of a k_classify block */
+#define SFH_TILE 128u         /* items per classification tile = threads of a k_classify block. Small: the classifier of a single
+                                 hull (783 chunks) then runs on 7 SMs instead of one, whose L1 miss path its ~40 texel loads per item saturated */
 #define SFH_SEG_PER_STREAM 16u /* at most this many segments per resident stream (warp) */
 enum { CK_DRY = 0, CK_WET = 1, CK_CLIP = 2 };
 // control words of the surface path (device, zeroed once): the classifier's last block fills them in for the consumers
-enum { SC_TICKET = 0, SC_WET_NEXT = 2, SC_WET_SEG = 3, SC_CLIP_NEXT = 4, SC_CLIP_SEG = 5, SC_WET_TOTAL = 6, SC_CLIP_TOTAL = 7, SC_ITEMS = 8, SC_WORDS = 16 };
+// (totals and segment sizes count SUB-ITEMS: entries x split, see finish_lists)
+enum { SC_TICKET = 0, SC_WET_NEXT = 2, SC_WET_SEG = 3, SC_CLIP_NEXT = 4, SC_CLIP_SEG = 5, SC_WET_TOTAL = 6, SC_CLIP_TOTAL = 7, SC_ITEMS = 8,
+       SC_WET_SPLIT = 9, SC_CLIP_SPLIT = 10, SC_WET_ENTRIES = 11, SC_CLIP_ENTRIES = 12, SC_WORDS = 16 };
 
 // A work item of the consumers: where the chunk is, whose it is. w = chunk index | size in 16-byte units << 23.
 // (16 bytes per item against >= 3 KB of chunk data.)
@@ -48,13 +52,24 @@ struct SurfLists {
 
 __device__ __forceinline__ int floor_div(int a, int n) { return a >= 0 ? a / n : -((n - 1 - a) / n); }
 
+// DIRECT MODE: a step with no more surface items than consumer streams (a single hull, a small scene) is bound by latency, and
+// every kernel of the chain costs 5-15 us of dependent round trips whatever it computes. Such a step skips the lists: warp u of
+// k_surface_lists classifies its own (sub-)item, works on it and writes one record. Every kernel decides alike from W (surface
+// items) and T (consumer streams): 0 = list mode, else the number of sub-items per item.
+__device__ __forceinline__ uint32_t direct_split(uint32_t W, uint32_t T)
+{
+    if (W == 0u || W > T) return 0u;
+    return (uint64_t)W * 4u <= T ? 4u : ((uint64_t)W * 2u <= T ? 2u : 1u);
+}
+
 // Range [lo, hi] of the reference's bilinear lookup of one channel (OpenGLRealOcean.cpp:280-319) for every point of the world
 // rectangle [cx +- ex] x [cy +- ey]. The lookup at texel coordinates X = x / g * N reads columns floor(X - 0.5) and floor(X + 0.5)
 // (mod N) and returns a convex combination of four texels, so the minimum and maximum of the texels the rectangle can touch bound
-// it; inside one period the interpolant is also continuous with slopes bounded by the largest difference of adjacent texels, which
-// bounds it around its value at the centre (tighter when the rectangle is a fraction of a texel, as the chunks of a fine hull are).
+// it (this function: footprints of up to 8 x 8 texels, period boundaries included). Inside one period the interpolant is also
+// continuous with slopes bounded by the largest difference of adjacent texels, which bounds it around its value at the centre —
+// tighter when the rectangle is a fraction of a texel, as the chunks of a fine hull are (chan_window / chan_reduce below).
 // At a period boundary the reference's index can become N (the fraction 1 - |tiny| rounds to 1.0f, :291-296): it then reads
-// column 0 of the NEXT row, or the spill-over row N*N..N*N+N; those texels join the candidates and the slope bound is not used.
+// column 0 of the NEXT row, or the spill-over row N*N..N*N+N; those texels join the candidates.
 // Falls back to the global bound +-hmax (which includes the spill-over texels) for large or non-finite rectangles and NaN texels.
 __device__ __noinline__ void wave_channel_bounds(const float* __restrict__ ch, int N, float g, float hmax, float cx, float cy, float ex,
                                                  float ey, float& lo, float& hi)
@@ -70,47 +85,95 @@ __device__ __noinline__ void wave_channel_bounds(const float* __restrict__ ch, i
     if (!(fb - fa < 8.f && gb - ga < 8.f && fabsf(fa) < 1e8f && fabsf(ga) < 1e8f)) return; // large, or NaN
     const int ia = (int)fa, ib = (int)fb, ja = (int)ga, jb = (int)gb;
     const bool wrap_i = floor_div(ia, N) != floor_div(ib, N), wrap_j = floor_div(ja, N) != floor_div(jb, N);
-    float mn = __int_as_float(0x7f800000), mx = -mn, Lx = 0.f, Ly = 0.f;
+    float mn = __int_as_float(0x7f800000), mx = -mn;
     bool bad = false;
     auto see = [&](float v) { mn = fminf(mn, v); mx = fmaxf(mx, v); bad |= (v != v); };
+    // minimum and maximum of up to 8 x 8 texels: rows one at a time, the eight loads of a row in flight together (a plain double
+    // loop waits for an L2 round trip per texel, which made the classifier of a single hull slower than its face kernels)
+    int col[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { const int i = min(ia + c, ib); col[c] = i - N * floor_div(i, N); }
     for (int j = ja; j <= jb; ++j) {
-        const int jm = j - N * floor_div(j, N), jp = (j - 1) - N * floor_div(j - 1, N);
-        float prev = 0.f;
-        for (int i = ia; i <= ib; ++i) {
-            const int im = i - N * floor_div(i, N);
-            const float v = __ldg(ch + jm * N + im);
-            see(v);
-            if (i > ia) Lx = fmaxf(Lx, fabsf(v - prev));
-            if (j > ja) Ly = fmaxf(Ly, fabsf(v - __ldg(ch + jp * N + im)));
-            prev = v;
-        }
-        if (wrap_i) see(__ldg(ch + jm * N + N)); // index N of this row
+        const float* row = ch + (j - N * floor_div(j, N)) * N;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldg(row + col[c]);
+        const float q = wrap_i ? __ldg(row + N) : v[0]; // index N of this row
+#pragma unroll
+        for (int c = 0; c < 8; ++c) see(v[c]);
+        see(q);
     }
     if (wrap_j) {
-        for (int i = ia; i <= ib; ++i) see(__ldg(ch + N * N + (i - N * floor_div(i, N))));
-        if (wrap_i) see(__ldg(ch + N * N + N));
+        const float* row = ch + N * N;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) see(__ldg(row + col[c]));
+        if (wrap_i) see(__ldg(row + N));
     }
     if (bad) return;
-    if (!wrap_i && !wrap_j) { // value at the centre (plain fp32; its error is inside the caller's margin) +- slopes x half widths
-        const float x0 = floorf(Xc - 0.5f), y0 = floorf(Yc - 0.5f), a = Xc - 0.5f - x0, b = Yc - 0.5f - y0;
-        const int i0 = (int)x0 - N * floor_div((int)x0, N), i1 = ((int)x0 + 1) - N * floor_div((int)x0 + 1, N);
-        const int j0 = (int)y0 - N * floor_div((int)y0, N), j1 = ((int)y0 + 1) - N * floor_div((int)y0 + 1, N);
-        const float bc = (1.f - a) * (1.f - b) * __ldg(ch + j0 * N + i0) + a * (1.f - b) * __ldg(ch + j0 * N + i1) +
-                         (1.f - a) * b * __ldg(ch + j1 * N + i0) + a * b * __ldg(ch + j1 * N + i1);
-        const float w = Lx * (wx + dx) + Ly * (wy + dy);
-        mn = fmaxf(mn, bc - w);
-        mx = fminf(mx, bc + w);
-    }
     lo = mn;
     hi = mx;
 }
 
-// Kind of one chunk of a crossing body. R, t: T_C as fp32 (BodyDev); cb: the chunk's box in the mesh frame.
+// The same bound for footprints of at most 4 x 4 texels that do not touch a period boundary — every chunk of a fine hull — as
+// straight-line code: the index arithmetic of BOTH channels first, then all 40 texel loads in flight together, then the
+// reductions. (The loop version above waits for one L2 round trip per texel: 27 us for the 783 chunks of a single 200k-face
+// hull, more than the face kernels take.)
+struct ChanWin {
+    bool fast;            // footprint fits the 4 x 4 window, inside one period
+    int idx[16], cen[4];  // texel indices of the window (clamped duplicates at its edges) and of the centre's four texels
+    float a, b, wx, wy;   // centre weights; half widths incl. margins, texels
+};
+__device__ __forceinline__ ChanWin chan_window(int N, float g, float cx, float cy, float ex, float ey)
+{
+    ChanWin w;
+    const float fN = (float)N, s = fN / g;
+    const float Xc = cx * s, Yc = cy * s, wx = fabsf(ex * s), wy = fabsf(ey * s);
+    const float dx = 0.02f + 8e-6f * fabsf(Xc), dy = 0.02f + 8e-6f * fabsf(Yc);
+    const float fa = floorf(Xc - wx - 0.5f - dx), fb = floorf(Xc + wx + 0.5f + dx);
+    const float ga = floorf(Yc - wy - 0.5f - dy), gb = floorf(Yc + wy + 0.5f + dy);
+    w.fast = fb - fa < 4.f && gb - ga < 4.f && fabsf(fa) < 1e8f && fabsf(ga) < 1e8f; // false for NaN
+    const int ia = w.fast ? (int)fa : 0, ib = w.fast ? (int)fb : 0, ja = w.fast ? (int)ga : 0, jb = w.fast ? (int)gb : 0;
+    if (floor_div(ia, N) != floor_div(ib, N) || floor_div(ja, N) != floor_div(jb, N)) w.fast = false;
+    const int i0 = ia - N * floor_div(ia, N), j0 = ja - N * floor_div(ja, N), ni = ib - ia, nj = jb - ja; // no wrap: i0 + ni < N
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w.idx[4 * r + c] = w.fast ? (j0 + min(r, nj)) * N + i0 + min(c, ni) : 0;
+    const float x0 = floorf(Xc - 0.5f), y0 = floorf(Yc - 0.5f);
+    w.a = Xc - 0.5f - x0;
+    w.b = Yc - 0.5f - y0;
+    const int xi = w.fast ? (int)x0 : 0, yi = w.fast ? (int)y0 : 0; // columns xi, xi + 1 and rows yi, yi + 1 lie inside the window
+    const int ci = xi - N * floor_div(xi, N), cj = yi - N * floor_div(yi, N);
+    w.cen[0] = w.fast ? cj * N + ci : 0; w.cen[1] = w.fast ? cj * N + ci + 1 : 0;
+    w.cen[2] = w.fast ? (cj + 1) * N + ci : 0; w.cen[3] = w.fast ? (cj + 1) * N + ci + 1 : 0;
+    w.wx = wx + dx;
+    w.wy = wy + dy;
+    return w;
+}
+__device__ __forceinline__ void chan_reduce(const ChanWin& w, const float (&v)[16], const float (&c)[4], float& lo, float& hi)
+{
+    float mn = v[0], mx = v[0], Lx = 0.f, Ly = 0.f;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mn = fminf(mn, v[k]); mx = fmaxf(mx, v[k]); bad |= (v[k] != v[k]);
+        if ((k & 3) != 0) Lx = fmaxf(Lx, fabsf(v[k] - v[k - 1]));
+        if (k >= 4) Ly = fmaxf(Ly, fabsf(v[k] - v[k - 4]));
+    }
+    const float bc = (1.f - w.a) * (1.f - w.b) * c[0] + w.a * (1.f - w.b) * c[1] + (1.f - w.a) * w.b * c[2] + w.a * w.b * c[3];
+    const float r = Lx * w.wx + Ly * w.wy;
+    if (bad) return;
+    lo = fmaxf(mn, bc - r);
+    hi = fminf(mx, bc + r);
+}
+
+// Kind of one chunk of a crossing body. R, t: T_C as fp32 (BodyDev); b0, b1: the chunk's box in the mesh frame (ChunkBounds).
 __device__ __forceinline__ uint32_t classify_chunk(const float* __restrict__ R, const float* __restrict__ t, float4 b0, float2 b1, bool waves,
                                                    const WavesDev& wv, float hmax0, float hmax1)
 {
     const float cx = b0.x, cy = b0.y, cz = b0.z, hx = b0.w, hy = b1.x, hz = b1.y;
     float cw[3], ext[3], M = 0.f;
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float r0 = R[3 * k], r1 = R[3 * k + 1], r2 = R[3 * k + 2];
         cw[k] = r0 * cx + r1 * cy + r2 * cz + t[k];
@@ -128,9 +191,18 @@ __device__ __forceinline__ uint32_t classify_chunk(const float* __restrict__ R, 
     if (zmax + H + E < 0.f) return CK_DRY;
     if (zmin - H - E > 0.f) return CK_WET;
     if (!(zmax + H + E >= 0.f)) return CK_CLIP; // NaN somewhere: the general path
-    float lo0, hi0, lo1, hi1;
-    wave_channel_bounds(wv.ch0, wv.N, wv.gx, hmax0, cw[0], cw[1], ext[0] + e, ext[1] + e, lo0, hi0);
-    wave_channel_bounds(wv.ch1, wv.N, wv.gy, hmax1, cw[0], cw[1], ext[0] + e, ext[1] + e, lo1, hi1);
+    float lo0 = -hmax0, hi0 = hmax0, lo1 = -hmax1, hi1 = hmax1;
+    const ChanWin w0 = chan_window(wv.N, wv.gx, cw[0], cw[1], ext[0] + e, ext[1] + e);
+    const ChanWin w1 = chan_window(wv.N, wv.gy, cw[0], cw[1], ext[0] + e, ext[1] + e);
+    float v0[16], v1[16], c0[4], c1[4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { v0[k] = __ldg(wv.ch0 + w0.idx[k]); v1[k] = __ldg(wv.ch1 + w1.idx[k]); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c0[k] = __ldg(wv.ch0 + w0.cen[k]); c1[k] = __ldg(wv.ch1 + w1.cen[k]); }
+    if (w0.fast) chan_reduce(w0, v0, c0, lo0, hi0);
+    else wave_channel_bounds(wv.ch0, wv.N, wv.gx, hmax0, cw[0], cw[1], ext[0] + e, ext[1] + e, lo0, hi0);
+    if (w1.fast) chan_reduce(w1, v1, c1, lo1, hi1);
+    else wave_channel_bounds(wv.ch1, wv.N, wv.gy, hmax1, cw[0], cw[1], ext[0] + e, ext[1] + e, lo1, hi1);
     if (zmax + (hi0 + hi1) + E < 0.f) return CK_DRY;
     if (zmin + (lo0 + lo1) - E > 0.f) return CK_WET;
     return CK_CLIP;
@@ -145,24 +217,20 @@ struct ClassifyParams {
     SurfLists L;
     uint32_t* status;         // [0] |= 2 if the work list does not fit items_cap
     uint32_t wet_streams, clip_streams; // resident warps of the two consumers (segment sizing)
+    uint32_t direct_streams;            // T of direct_split (0: direct mode off)
 };
 
-__global__ void __launch_bounds__(SFH_TILE, 1) k_classify(ClassifyParams P)
+// Tiles first_tile, first_tile + stride, ... of the surface work list: classify, rank, compact. Block-wide (SFH_TILE threads).
+__device__ __forceinline__ void classify_tiles(const ClassifyParams& P, uint32_t W, uint32_t first_tile, uint32_t stride)
 {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_last;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t W = P.off_surf[P.n_bodies];
-    if (W > P.L.items_cap) { // cannot happen with host-side states (the host sizes the lists); device-resident steps are bounded
-        if (blockIdx.x == 0 && tid == 0) atomicOr(P.status, 2u);
-        W = 0;
-    }
     const uint32_t n_tiles = (W + SFH_TILE - 1) / SFH_TILE;
     const bool waves = P.ocean->has_waves != 0;
     float hmax0 = 0.f, hmax1 = 0.f;
     if (waves) { hmax0 = __uint_as_float(__ldg(P.waves.hmax)); hmax1 = __uint_as_float(__ldg(P.waves.hmax + 1)); }
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = first_tile; tile < n_tiles; tile += stride) {
         const uint32_t w = tile * SFH_TILE + tid;
         uint32_t kind = CK_DRY;
         uint4 desc = make_uint4(0, 0, 0, 0);
@@ -175,7 +243,7 @@ __global__ void __launch_bounds__(SFH_TILE, 1) k_classify(ClassifyParams P)
             const unsigned long long addr = (unsigned long long)(bd.chunks + (size_t)__float_as_uint(b1.z) * 16u);
             desc = make_uint4((uint32_t)addr, (uint32_t)(addr >> 32), b, c | ((__float_as_uint(b1.w) >> 4) << 23));
         }
-        // block-wide exclusive ranks of the wet (low half) and clip (high half) items: at most 1024 of each, 16 bits suffice
+        // block-wide exclusive ranks of the wet (low half) and clip (high half) items: at most SFH_TILE of each, 16 bits suffice
         const uint32_t flag = (kind == CK_WET ? 1u : 0u) | (kind == CK_CLIP ? 0x10000u : 0u);
         uint32_t x = flag;
 #pragma unroll
@@ -186,7 +254,7 @@ __global__ void __launch_bounds__(SFH_TILE, 1) k_classify(ClassifyParams P)
         if (lane == 31) s_warp[warp] = x;
         __syncthreads();
         if (warp == 0) {
-            uint32_t v = s_warp[lane];
+            uint32_t v = lane < SFH_TILE / 32u ? s_warp[lane] : 0u;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const uint32_t y = __shfl_up_sync(SFH_FULL, v, off);
@@ -202,23 +270,32 @@ __global__ void __launch_bounds__(SFH_TILE, 1) k_classify(ClassifyParams P)
         if (tid == SFH_TILE - 1u) P.L.tile_cnt[tile] = make_uint2((excl + flag) & 0xffffu, (excl + flag) >> 16);
         __syncthreads(); // s_warp is reused by the next tile
     }
+}
 
-    // the last block to finish turns the tile counts into offsets and sizes the consumers' segments
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&P.L.ctrl[SC_TICKET], 1u) == gridDim.x - 1u) ? 1u : 0u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+// Tile counts -> offsets, and the consumers' schedule. Block-wide, by ONE block, after every tile has been written.
+// SPLIT: with fewer list entries than resident streams (a single hull: 783 chunks for 1776 warps) the step is bound by the time
+// ONE warp needs for ONE chunk (4 face pairs per lane in sequence). A list entry is then handed out as 2 or 4 sub-items — each
+// stages the chunk and transforms its vertices again (cheap next to the faces) and evaluates a half / a quarter of the faces.
+__device__ __forceinline__ void finish_lists(const ClassifyParams& P, uint32_t W)
+{
+    constexpr uint32_t PER = 8; // tiles per thread and round
     __shared__ uint32_t s_carry[2];
     __shared__ uint32_t s_w2[2][32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_tiles = (W + SFH_TILE - 1) / SFH_TILE;
     if (tid < 2) s_carry[tid] = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < n_tiles; base += SFH_TILE) {
-        const uint32_t i = base + tid;
-        uint2 c = make_uint2(0, 0);
-        if (i < n_tiles) c = __ldcg(&P.L.tile_cnt[i]); // written by other blocks of this launch: read through L2
-        uint32_t xs = c.x, xf = c.y;
+    for (uint32_t base = 0; base < n_tiles; base += SFH_TILE * PER) {
+        const uint32_t i0 = base + tid * PER;
+        uint2 c[PER];
+        uint32_t ts = 0, tf = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < PER; ++k) {
+            c[k] = make_uint2(0, 0);
+            if (i0 + k < n_tiles) c[k] = __ldcg(&P.L.tile_cnt[i0 + k]); // possibly written by other blocks of this launch: read through L2
+            ts += c[k].x; tf += c[k].y;
+        }
+        uint32_t xs = ts, xf = tf;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const uint32_t ys = __shfl_up_sync(SFH_FULL, xs, off), yf = __shfl_up_sync(SFH_FULL, xf, off);
@@ -227,7 +304,7 @@ __global__ void __launch_bounds__(SFH_TILE, 1) k_classify(ClassifyParams P)
         if (lane == 31) { s_w2[0][warp] = xs; s_w2[1][warp] = xf; }
         __syncthreads();
         if (warp == 0) {
-            uint32_t ws = s_w2[0][lane], wf = s_w2[1][lane];
+            uint32_t ws = lane < SFH_TILE / 32u ? s_w2[0][lane] : 0u, wf = lane < SFH_TILE / 32u ? s_w2[1][lane] : 0u;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const uint32_t ys = __shfl_up_sync(SFH_FULL, ws, off), yf = __shfl_up_sync(SFH_FULL, wf, off);
@@ -236,9 +313,11 @@ __global__ void __launch_bounds__(SFH_TILE, 1) k_classify(ClassifyParams P)
             s_w2[0][lane] = ws; s_w2[1][lane] = wf;
         }
         __syncthreads();
-        if (i < n_tiles) {
-            P.L.wet_off[i] = s_carry[0] + (warp ? s_w2[0][warp - 1] : 0u) + xs - c.x;
-            P.L.clip_off[i] = s_carry[1] + (warp ? s_w2[1][warp - 1] : 0u) + xf - c.y;
+        uint32_t rs = s_carry[0] + (warp ? s_w2[0][warp - 1] : 0u) + xs - ts, rf = s_carry[1] + (warp ? s_w2[1][warp - 1] : 0u) + xf - tf;
+#pragma unroll
+        for (uint32_t k = 0; k < PER; ++k) {
+            if (i0 + k < n_tiles) { P.L.wet_off[i0 + k] = rs; P.L.clip_off[i0 + k] = rf; }
+            rs += c[k].x; rf += c[k].y;
         }
         __syncthreads();
         if (tid == 0) { s_carry[0] += s_w2[0][31]; s_carry[1] += s_w2[1][31]; }
@@ -248,17 +327,51 @@ __global__ void __launch_bounds__(SFH_TILE, 1) k_classify(ClassifyParams P)
         const uint32_t wet = s_carry[0], clip = s_carry[1];
         P.L.wet_off[n_tiles] = wet;
         P.L.clip_off[n_tiles] = clip;
+        uint32_t wet_split = 1, clip_split = 1;
+        while (wet_split < 4u && (uint64_t)wet * wet_split * 2u <= P.wet_streams) wet_split *= 2u;
+        if ((uint64_t)clip * 2u <= P.clip_streams) clip_split = 2u; // its per-vertex wave lookups are not cheap: halves only
+        const uint32_t wet_sub = wet * wet_split, clip_sub = clip * clip_split;
         const uint32_t cap_w = max(P.wet_streams, 1u) * SFH_SEG_PER_STREAM, cap_c = max(P.clip_streams, 1u) * SFH_SEG_PER_STREAM;
         uint32_t* ctrl = P.L.ctrl;
         ctrl[SC_TICKET] = 0;
-        ctrl[SC_WET_NEXT] = 0;
-        ctrl[SC_WET_SEG] = max(1u, (wet + cap_w - 1) / cap_w);
-        ctrl[SC_CLIP_NEXT] = 0;
-        ctrl[SC_CLIP_SEG] = max(1u, (clip + cap_c - 1) / cap_c);
-        ctrl[SC_WET_TOTAL] = wet;
-        ctrl[SC_CLIP_TOTAL] = clip;
+        ctrl[SC_WET_NEXT] = P.wet_streams; // every stream starts with the segment of its own index (no atomic, one round trip less)
+        ctrl[SC_WET_SEG] = max(1u, (wet_sub + cap_w - 1) / cap_w);
+        ctrl[SC_CLIP_NEXT] = P.clip_streams;
+        ctrl[SC_CLIP_SEG] = max(1u, (clip_sub + cap_c - 1) / cap_c);
+        ctrl[SC_WET_TOTAL] = wet_sub;
+        ctrl[SC_CLIP_TOTAL] = clip_sub;
         ctrl[SC_ITEMS] = W;
+        ctrl[SC_WET_SPLIT] = wet_split;
+        ctrl[SC_CLIP_SPLIT] = clip_split;
+        ctrl[SC_WET_ENTRIES] = wet;
+        ctrl[SC_CLIP_ENTRIES] = clip;
     }
+}
+
+__device__ __forceinline__ uint32_t surface_items(const ClassifyParams& P)
+{
+    uint32_t W = P.off_surf[P.n_bodies];
+    if (W > P.L.items_cap) { // cannot happen with host-side states (the host sizes the lists); device-resident steps are bounded
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(P.status, 2u);
+        W = 0;
+    }
+    return W;
+}
+
+__global__ void __launch_bounds__(SFH_TILE, 4) k_classify(ClassifyParams P)
+{
+    __shared__ uint32_t s_last;
+    const uint32_t W = surface_items(P);
+    if (direct_split(W, P.direct_streams)) return; // the consumers classify for themselves
+    classify_tiles(P, W, blockIdx.x, gridDim.x);
+    // the last block to finish turns the tile counts into offsets and sizes the consumers' segments
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&P.L.ctrl[SC_TICKET], 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    finish_lists(P, W);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -303,16 +416,16 @@ struct SurfParams {
     WavesDev waves;
     SurfLists L;
     const uint32_t* off_surf;
-    PartialSurf* partials;
+    PartialSurf* part_wet;     // one record per (segment, body) of the wet role
+    PartialSurf* part_clip;    // ... of the clip role
+    uint32_t wet_blocks;       // blocks [0, wet_blocks) of the grid work on the wet list, the others on the clip list
+    uint32_t direct_streams;   // T of direct_split (0: direct mode off)
     uint8_t* codes;            // debug: per-face codes, nullptr otherwise
     const uint64_t* code_base; // debug: first code index of each body
 };
 
-#ifndef SFH_WET_MIN_BLOCKS
-#define SFH_WET_MIN_BLOCKS 6
-#endif
-#ifndef SFH_CLIP_MIN_BLOCKS
-#define SFH_CLIP_MIN_BLOCKS 6
+#ifndef SFH_SURF_MIN_BLOCKS
+#define SFH_SURF_MIN_BLOCKS 6
 #endif
 
 struct SurfBody { // per-body constants of the consumers
@@ -355,11 +468,11 @@ __device__ __forceinline__ uint64_t surf_current_mask(const BodyDev& sb, const C
 template <bool WAVES, int CUR, bool DEBUG, bool BUOY, bool DAMP>
 __device__ __forceinline__ void wet_chunk(const SurfParams& P, const ChunkView& cv, const float4* __restrict__ s_v, const SurfBody& S,
                                           const sfh_current* s_cur, uint64_t cur_may, uint32_t n_cur, const WaveConst& wc, double* acc,
-                                          uint32_t& epack, uint32_t body, const uint32_t* __restrict__ orig, uint32_t lane)
+                                          uint32_t& epack, uint32_t body, const uint32_t* __restrict__ orig, uint32_t lane, uint32_t f0,
+                                          uint32_t nf /* faces [f0, nf) of the chunk */)
 {
-    const uint32_t nf = cv.nf;
 #pragma unroll 1
-    for (uint32_t base = 0; base < nf; base += 64u) {
+    for (uint32_t base = f0; base < nf; base += 64u) {
         const uint32_t iA = base + lane, iB = iA + 32u;
         const bool vA = iA < nf, vB = iB < nf;
         const uint32_t fA = vA ? cv.faces[iA] : 0u, fB = vB ? cv.faces[iB] : 0u;
@@ -400,9 +513,7 @@ __device__ __forceinline__ void wet_chunk(const SurfParams& P, const ChunkView& 
             if (!cheap_ok && !((min_key(fn) >= SFH_NUM_KEY) & (min_key(csum) >= SFH_TINY_KEY)))
                 normalize_centroid_slow(fn, len, csum, fn1, fc);
             if (WAVES && BUOY) { // pressure buoyancy at the centroid (SolidEntity.cpp:1650-1658)
-                const float dcA = get_depth<WAVES>(P.waves, wc, lo(fc.x), lo(fc.y), lo(fc.z));
-                const float dcB = get_depth<WAVES>(P.waves, wc, hi(fc.x), hi(fc.y), hi(fc.z));
-                const V3P Fbi = (fn1 * neg(A)) * pk(dcA, dcB); // ((-fn1) * A) * depthc: negating A instead of fn1 flips the same sign bits
+                const V3P Fbi = (fn1 * neg(A)) * depth_pair<WAVES>(P.waves, wc, fc); // ((-fn1) * A) * depthc: negating A instead of fn1 flips the same sign bits
                 const V3P Tbi = cross(fc - S.B.p, Fbi);
                 acc6_if(mA, acc + 12, lo(Fbi.x), lo(Fbi.y), lo(Fbi.z), lo(Tbi.x), lo(Tbi.y), lo(Tbi.z));
                 acc6_if(mB, acc + 12, hi(Fbi.x), hi(Fbi.y), hi(Fbi.z), hi(Tbi.x), hi(Tbi.y), hi(Tbi.z));
@@ -418,20 +529,34 @@ __device__ __forceinline__ void wet_chunk(const SurfParams& P, const ChunkView& 
     }
 }
 
+// Vertex phase of a clip chunk: world position and Ocean::GetDepth per vertex (SolidEntity.cpp:1343-1351; same bits for every incident
+// face). (Two vertices per lane and trip, to overlap their texel loads, was measured: 13 % slower at full size — it evaluates up to
+// 63 slots past the last vertex — and no faster on a single small hull.)
+template <bool WAVES>
+__device__ __forceinline__ void clip_vertices(const WavesDev& wv, const WaveConst& wc, const BodyDev& sb, const ChunkView& cv, float4* __restrict__ s_v,
+                                              uint32_t lane)
+{
+#pragma unroll 1
+    for (uint32_t i = lane; i < cv.nv; i += 32u) {
+        const F3 pw = xform(sb.R, sb.t, cv.x[i], cv.y[i], cv.z[i]);
+        s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z));
+    }
+}
+
 // One chunk the water line may cross: per-vertex depths were left in s_v[].w; the reference's eight classes, one face per lane
 // at a time (SolidEntity.cpp:1347-1687).
 template <bool WAVES, int CUR, bool DEBUG>
 __device__ __forceinline__ void clip_chunk(const SurfParams& P, const ChunkView& cv, const float4* __restrict__ s_v, const SurfBody& S,
                                            const sfh_current* s_cur, uint64_t cur_may, uint32_t n_cur, const WaveConst& wc, double* acc,
-                                           uint32_t& epack, uint64_t& cpack, uint32_t body, const uint32_t* __restrict__ orig, uint32_t lane)
+                                           uint32_t& epack, uint64_t& cpack, uint32_t body, const uint32_t* __restrict__ orig, uint32_t lane,
+                                           uint32_t f0, uint32_t nf /* faces [f0, nf) of the chunk */)
 {
-    const uint32_t nf = cv.nf;
     const bool buoy = S.buoy, damp = S.damp;
     BodyRegs B;
     B.p = S.p; B.v = S.v; B.omega = S.omega; B.cur = S.cur;
     const F3 p0 = S.p0;
 #pragma unroll 1
-    for (uint32_t slot = lane; slot < nf; slot += 32u) {
+    for (uint32_t slot = f0 + lane; slot < nf; slot += 32u) {
         const uint32_t fp = cv.faces[slot];
         const float4 a4 = s_v[fp & 255u], b4 = s_v[(fp >> 8) & 255u], c4 = s_v[(fp >> 16) & 255u];
         F3 p1 = {a4.x, a4.y, a4.z}, p2 = {b4.x, b4.y, b4.z}, p3 = {c4.x, c4.y, c4.z};
@@ -518,28 +643,20 @@ __device__ __forceinline__ void clip_chunk(const SurfParams& P, const ChunkView&
     }
 }
 
-// The consumers. CLIP = false: k_surface_wet over the wet list; CLIP = true: k_surface_clip over the clip list.
+// One role of the consumer kernel: CLIP = false works through the wet list, CLIP = true through the clip list.
 template <bool CLIP, bool WAVES, int CUR, bool DEBUG>
-__global__ void __launch_bounds__(SFH_SUB_THREADS, CLIP ? SFH_CLIP_MIN_BLOCKS : SFH_WET_MIN_BLOCKS) k_surface_list(SurfParams P)
+__device__ __forceinline__ void surface_role(const SurfParams& P, WarpStage& St, const sfh_current* s_cur, const CurGuard* s_guard, uint32_t n_cur,
+                                             uint32_t lane, uint32_t stream /* this warp's index among the role's warps */)
 {
-    __shared__ WarpStage s_stage[SFH_SUB_WPB];
-    __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
-    __shared__ CurGuard s_guard[CUR ? SFH_MAX_CURRENTS : 1];
-
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
-    if constexpr (CUR != 0) {
-        stage_currents(s_cur, s_guard, P.ocean, n_cur);
-        __syncthreads(); // the only block barrier of the kernel, before any warp can leave
-    }
     uint32_t* const ctrl = P.L.ctrl;
-    const uint32_t total = ctrl[CLIP ? SC_CLIP_TOTAL : SC_WET_TOTAL], SC = ctrl[CLIP ? SC_CLIP_SEG : SC_WET_SEG];
+    const uint32_t total = ctrl[CLIP ? SC_CLIP_TOTAL : SC_WET_TOTAL], SC = ctrl[CLIP ? SC_CLIP_SEG : SC_WET_SEG]; // in sub-items
     if (total == 0) return;
-    WarpStage& St = s_stage[warp];
+    const uint32_t split = ctrl[CLIP ? SC_CLIP_SPLIT : SC_WET_SPLIT], sh = 31u - __clz(split), part = SFH_CH_FACES >> sh;
     BodyDev& s_body = St.body;
     float4* const s_v = St.v;
     const PipeAddr pa = warp_pipe_init(St.pipe, lane);
     const WaveConst wc = WAVES ? wave_const(P.waves) : WaveConst{};
+    PartialSurf* const partials = CLIP ? P.part_clip : P.part_wet;
 
     ListWalk lw;
     lw.items = P.L.items;
@@ -571,7 +688,7 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, CLIP ? SFH_CLIP_MIN_BLOCKS : 
     };
     auto flush = [&](uint32_t seg, uint32_t body) { // one partial record per (segment, body)
         spill();
-        PartialSurf* rec = P.partials + (seg + body);
+        PartialSurf* rec = partials + (seg + body);
 #pragma unroll
         for (int i = 0; i < SFH_NACC_SURF; ++i) {
             const double v = warp_sum(acc[i]);
@@ -587,32 +704,45 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, CLIP ? SFH_CLIP_MIN_BLOCKS : 
 #pragma unroll
         for (int k = 0; k < 8; ++k) cls[k] = 0;
     };
+    auto issue = [&](int buf, const uint4& d) {
+        pipe_issue(pa, buf, reinterpret_cast<const uint8_t*>(((unsigned long long)d.y << 32) | d.x), (d.w >> 23) << 4);
+    };
 
-    for (;;) { // segments
-        uint32_t seg = 0;
-        if (lane == 0) seg = atomicAdd(&ctrl[CLIP ? SC_CLIP_NEXT : SC_WET_NEXT], 1u);
-        seg = __shfl_sync(SFH_FULL, seg, 0);
+    bool first = true;
+    for (;;) { // segments of sub-items: the stream's own index first, then whatever the counter hands out
+        uint32_t seg = stream;
+        if (!first) {
+            if (lane == 0) seg = atomicAdd(&ctrl[CLIP ? SC_CLIP_NEXT : SC_WET_NEXT], 1u);
+            seg = __shfl_sync(SFH_FULL, seg, 0);
+        }
+        first = false;
         const uint64_t R0 = (uint64_t)seg * SC;
         if (R0 >= total) break;
         const uint32_t R1 = (uint32_t)min(R0 + SC, (uint64_t)total);
         uint32_t R = (uint32_t)R0;
-        lw.locate(R);
-        uint4 d_cur = lw.get(), d_next = d_cur, d_after = d_cur;
-        if (lane == 0) pipe_issue(pa, s, reinterpret_cast<const uint8_t*>(((unsigned long long)d_cur.y << 32) | d_cur.x), (d_cur.w >> 23) << 4);
-        if (R + 1 < R1) { lw.next(); d_next = lw.get(); }
+        // sub-item R = part (R & (split - 1)) of list entry R >> sh; (dw, qw) is the furthest sub-item fetched so far
+        lw.locate(R >> sh);
+        uint4 dw = lw.get();
+        uint32_t qw = R & (split - 1u);
+        auto step = [&]() {
+            if (++qw == split) { qw = 0; lw.next(); dw = lw.get(); }
+        };
+        uint4 d_cur = dw, d_next = dw, d_after = dw;
+        uint32_t q_cur = qw, q_next = qw, q_after = qw;
+        if (lane == 0) issue(s, d_cur);
+        if (R + 1 < R1) { step(); d_next = dw; q_next = qw; }
         uint32_t body = d_cur.z;
         __syncwarp();
         warp_load_body(&s_body, P.bodies + body, lane);
         surf_fetch_body(s_body, S);
 
-        for (;;) { // chunks of the segment
+        for (;;) { // sub-items of the segment
             pipe_wait(pa, s, (parity >> s) & 1u);
             parity ^= 1u << s;
             const ChunkView cv = chunk_view(St.pipe.buf[s]);
             __syncwarp(); // every lane is done with the previous chunk: s_v and the other staging buffer are free
-            if (lane == 0 && R + 1 < R1)
-                pipe_issue(pa, s ^ 1, reinterpret_cast<const uint8_t*>(((unsigned long long)d_next.y << 32) | d_next.x), (d_next.w >> 23) << 4);
-            if (R + 2 < R1) { lw.next(); d_after = lw.get(); } // the descriptor after next has a whole chunk to arrive
+            if (lane == 0 && R + 1 < R1) issue(s ^ 1, d_next);
+            if (R + 2 < R1) { step(); d_after = dw; q_after = qw; } // the descriptor after next has a whole chunk to arrive
 
             if (!CLIP) { // vertices: slots 0..191 in one straight-line block, see k_submerged
                 auto xf = [&](uint32_t k) {
@@ -627,29 +757,26 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, CLIP ? SFH_CLIP_MIN_BLOCKS : 
                     if (cv.nv > 224u) xf(7u);
                 }
             } else { // ... and Ocean::GetDepth per vertex (SolidEntity.cpp:1349-1351): same bits for every incident face
-#pragma unroll 1
-                for (uint32_t i = lane; i < cv.nv; i += 32u) {
-                    const F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
-                    s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(P.waves, wc, pw.x, pw.y, pw.z));
-                }
+                clip_vertices<WAVES>(P.waves, wc, s_body, cv, s_v, lane);
             }
             __syncwarp();
 
             const uint64_t cur_may = CUR ? surf_current_mask(s_body, cv, s_guard, n_cur, S.rnorm) : 0ull;
             const uint32_t* orig = DEBUG ? s_body.orig_face + (size_t)(d_cur.w & 0x7fffffu) * SFH_CH_FACES : nullptr;
+            const uint32_t f0 = q_cur * part, f1 = min(cv.nf, f0 + part); // this sub-item's faces
             if (!CLIP) {
-                cls[7] += cv.nf;
+                cls[7] += f1 > f0 ? f1 - f0 : 0u;
                 if (S.buoy) {
-                    if (S.damp) wet_chunk<WAVES, CUR, DEBUG, true, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane);
-                    else        wet_chunk<WAVES, CUR, DEBUG, true, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane);
+                    if (S.damp) wet_chunk<WAVES, CUR, DEBUG, true, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
+                    else        wet_chunk<WAVES, CUR, DEBUG, true, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
                 } else {
-                    if (S.damp) wet_chunk<WAVES, CUR, DEBUG, false, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane);
-                    else        wet_chunk<WAVES, CUR, DEBUG, false, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane);
+                    if (S.damp) wet_chunk<WAVES, CUR, DEBUG, false, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
+                    else        wet_chunk<WAVES, CUR, DEBUG, false, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
                 }
             } else {
-                clip_chunk<WAVES, CUR, DEBUG>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, cpack, body, orig, lane);
+                clip_chunk<WAVES, CUR, DEBUG>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, cpack, body, orig, lane, f0, f1);
             }
-            if (++since_spill == SFH_LIST_SPILL_EVERY) spill(); // 8 faces per lane per chunk: 10-bit / 8-bit fields stay in range
+            if (++since_spill == SFH_LIST_SPILL_EVERY) spill(); // <= 8 faces per lane per sub-item: 10-bit / 8-bit fields stay in range
 
             if (++R >= R1) break;
             s ^= 1;
@@ -660,12 +787,116 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, CLIP ? SFH_CLIP_MIN_BLOCKS : 
                 warp_load_body(&s_body, P.bodies + body, lane);
                 surf_fetch_body(s_body, S);
             }
-            d_cur = d_next;
-            d_next = d_after;
+            d_cur = d_next; q_cur = q_next;
+            d_next = d_after; q_next = q_after;
         }
         s ^= 1; // the next segment's first copy goes to the other staging buffer
         flush(seg, body);
     }
+}
+
+// Direct mode: sub-item u of the UNCLASSIFIED surface list, start to finish by this warp; one record at index u + body, zeros
+// for a dry chunk. Same per-face code as the roles, so the per-face terms are the same bits whichever mode ran.
+template <bool WAVES, int CUR, bool DEBUG>
+__device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStage& St, const sfh_current* s_cur, const CurGuard* s_guard, uint32_t n_cur,
+                                               uint32_t lane, uint32_t u, uint32_t split)
+{
+    const uint32_t sh = 31u - __clz(split), part = SFH_CH_FACES >> sh;
+    const uint32_t w = u >> sh, q = u & (split - 1u);
+    const uint32_t body = body_of_item(P.off_surf, P.n_bodies, w), c = w - P.off_surf[body];
+    BodyDev& s_body = St.body;
+    float4* const s_v = St.v;
+    warp_load_body(&s_body, P.bodies + body, lane);
+    const float4* rec = reinterpret_cast<const float4*>(s_body.bounds + c);
+    const float4 b0 = __ldg(rec), b1 = __ldg(rec + 1);
+    float hmax0 = 0.f, hmax1 = 0.f;
+    if (WAVES) { hmax0 = __uint_as_float(__ldg(P.waves.hmax)); hmax1 = __uint_as_float(__ldg(P.waves.hmax + 1)); }
+    const uint32_t kind = classify_chunk(s_body.R, s_body.t, b0, make_float2(b1.x, b1.y), WAVES, P.waves, hmax0, hmax1);
+
+    double acc[SFH_NACC_SURF];
+#pragma unroll
+    for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = 0.0;
+    uint32_t epack = 0, cls7 = 0;
+    uint64_t cpack = 0;
+    if (kind != CK_DRY) {
+        const PipeAddr pa = warp_pipe_init(St.pipe, lane);
+        if (lane == 0) pipe_issue(pa, 0, s_body.chunks + (size_t)__float_as_uint(b1.z) * 16u, __float_as_uint(b1.w));
+        const WaveConst wc = WAVES ? wave_const(P.waves) : WaveConst{};
+        SurfBody S;
+        surf_fetch_body(s_body, S);
+        pipe_wait(pa, 0, 0u);
+        const ChunkView cv = chunk_view(St.pipe.buf[0]);
+        const uint64_t cur_may = CUR ? surf_current_mask(s_body, cv, s_guard, n_cur, S.rnorm) : 0ull;
+        const uint32_t* orig = DEBUG ? s_body.orig_face + (size_t)c * SFH_CH_FACES : nullptr;
+        const uint32_t f0 = q * part, f1 = min(cv.nf, f0 + part);
+        if (kind == CK_WET) {
+#pragma unroll 1
+            for (uint32_t i = lane; i < cv.nv; i += 32u) {
+                const F3 pw = xform(s_body.R, s_body.t, cv.x[i], cv.y[i], cv.z[i]);
+                s_v[i] = make_float4(pw.x, pw.y, pw.z, 0.f);
+            }
+            __syncwarp();
+            cls7 = f1 > f0 ? f1 - f0 : 0u;
+            if (S.buoy) {
+                if (S.damp) wet_chunk<WAVES, CUR, DEBUG, true, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
+                else        wet_chunk<WAVES, CUR, DEBUG, true, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
+            } else {
+                if (S.damp) wet_chunk<WAVES, CUR, DEBUG, false, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
+                else        wet_chunk<WAVES, CUR, DEBUG, false, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
+            }
+        } else {
+            clip_vertices<WAVES>(P.waves, wc, s_body, cv, s_v, lane);
+            __syncwarp();
+            clip_chunk<WAVES, CUR, DEBUG>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, cpack, body, orig, lane, f0, f1);
+        }
+    }
+    PartialSurf* out = P.part_wet + (u + body);
+#pragma unroll
+    for (int i = 0; i < SFH_NACC_SURF; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) out->a[i] = v;
+    }
+    uint32_t cnt[3], cl[8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cnt[k] = __reduce_add_sync(SFH_FULL, (epack >> (10 * k)) & 1023u);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) cl[k] = __reduce_add_sync(SFH_FULL, (uint32_t)(cpack >> (8 * k)) & 255u);
+    if (lane == 0) {
+        out->n_degenerate = cnt[0]; out->n_quadratic = cnt[1]; out->n_skin = cnt[2];
+        out->cls[0] = 0;
+#pragma unroll
+        for (int k = 1; k < 7; ++k) out->cls[k] = cl[k];
+        out->cls[7] = cl[7] + cls7;
+    }
+}
+
+// The consumer of both lists, ONE launch: blocks [0, wet_blocks) take the wet list, the others the clip list. On a full-size
+// step the wet blocks fill the machine first and clip blocks move in as they leave — no kernel boundary in between; on a small
+// step both roles are resident together and their latencies overlap.
+template <bool WAVES, int CUR, bool DEBUG>
+__global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SURF_MIN_BLOCKS) k_surface_lists(SurfParams P)
+{
+    __shared__ WarpStage s_stage[SFH_SUB_WPB];
+    __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
+    __shared__ CurGuard s_guard[CUR ? SFH_MAX_CURRENTS : 1];
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_cur = CUR ? P.ocean->n_currents : 0;
+    if constexpr (CUR != 0) {
+        stage_currents(s_cur, s_guard, P.ocean, n_cur);
+        __syncthreads(); // the only block barrier of the kernel, before any warp can leave
+    }
+    const uint32_t W = P.off_surf[P.n_bodies], dsplit = direct_split(W <= P.L.items_cap ? W : 0u, P.direct_streams);
+    if (dsplit) { // small step: every (sub-)item has a warp of its own, no lists
+        const uint32_t u = blockIdx.x * SFH_SUB_WPB + warp;
+        if (u < W * dsplit) surface_direct<WAVES, CUR, DEBUG>(P, s_stage[warp], s_cur, s_guard, n_cur, lane, u, dsplit);
+        if (u == 0 && lane == 0) { // what sfh_get_timings reports: no lists were built
+            P.L.ctrl[SC_ITEMS] = W; P.L.ctrl[SC_WET_ENTRIES] = 0; P.L.ctrl[SC_CLIP_ENTRIES] = 0;
+        }
+        return;
+    }
+    if (blockIdx.x < P.wet_blocks) surface_role<false, WAVES, CUR, DEBUG>(P, s_stage[warp], s_cur, s_guard, n_cur, lane, blockIdx.x * SFH_SUB_WPB + warp);
+    else surface_role<true, WAVES, CUR, DEBUG>(P, s_stage[warp], s_cur, s_guard, n_cur, lane, (blockIdx.x - P.wet_blocks) * SFH_SUB_WPB + warp);
 }
 
 } // namespace sfh

@@ -180,15 +180,17 @@ def config5(n_vessels: int = 128, segments: int = 1000, stacks: int = 501, uniqu
     return Scene(f"cfg5_vessels_{'unique' if unique_meshes else 'shared'}", meshes, body_mesh, ocean, st)
 
 
-def config1() -> Scene:
+def config1(real_meshes: dict | None = None) -> Scene:
     """FluidDynamicsTest scene (Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:81-161) as a static snapshot:
     flat sea, SUBMERGED-mode buoyant bodies at their initial poses, full dispatcher (AUTO position from the AABB,
     analytic INSIDE buoyancy, coefficient correction). Compounds enter as one body per external part sharing T_CG.
-    The two OBJ hulls are replaced by synthetic closed meshes with the same face counts (2880 / 960)."""
+    `real_meshes`: {"hull_hydro": Mesh, "sphere_R=1": Mesh} — the reference's own OBJ hulls (:111-114), e.g. from the fixture
+    tests/golden/ref_meshes.npz; without them synthetic closed meshes with the same face counts (2880 / 960) stand in."""
     sphere = M.icosphere(0.5, 3)                 # Sphere.cpp:63 -> 1280 faces
     boxm = M.box(1.0, 0.5, 0.2, 3)               # Box.cpp:72   -> 768 faces
-    hull = M.uv_ellipsoid(0.9, 0.18, 0.18, 40, 37)   # 2880 faces, stand-in for hull_hydro.obj
-    sph1 = M.uv_ellipsoid(1.0, 1.0, 1.0, 24, 21)     # 960 faces,  stand-in for sphere_R=1.obj
+    real_meshes = real_meshes or {}
+    hull = real_meshes.get("hull_hydro") or M.uv_ellipsoid(0.9, 0.18, 0.18, 40, 37)   # 2880 faces
+    sph1 = real_meshes.get("sphere_R=1") or M.uv_ellipsoid(1.0, 1.0, 1.0, 24, 21)     # 960 faces
     meshes = [sphere, boxm, hull, sph1]
     ocean = Ocean(1000.0, 9.81)
     I = (0.0, 0.0, 0.0, 1.0)

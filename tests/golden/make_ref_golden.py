@@ -66,6 +66,19 @@ out["wave_tables"] = {"sea_state": 1.0, "seed": 1234, "spectrum12": hashlib.sha2
                       "spectrum34": hashlib.sha256(s34.tobytes()).hexdigest(), "butterfly": hashlib.sha256(bf.tobytes()).hexdigest(),
                       "spectrum12_first_nonzero": [float(x).hex() for x in s12[np.nonzero(s12)[0][:8]]]}
 
+# the reference's own meshes (Tests/Data/*.obj): positions and faces as a fixture, the reference text's outputs on them
+from stonefish_b200 import meshes as M  # noqa: E402
+
+real = {n: M.load_obj(f"/root/reference/Tests/Data/{n}.obj") for n in rc.REAL_MESH_NAMES}
+np.savez_compressed(rc.REAL_MESH_FIXTURE, **{f"{n}/{k}": (m.positions if k == "v" else m.faces) for n, m in real.items() for k in ("v", "f")})
+real = rc.load_real_meshes()  # what the tests will see
+out["real_meshes"] = []
+for sc in rc.real_mesh_scenes(real):
+    fl = rs.ocean_fluid(sc.ocean)
+    out["real_meshes"].append({"scene": sc.name, "bodies": [info_rec(rs.body(sc.meshes[int(sc.body_mesh[i])], fl, sc.states[i:i + 1]))
+                                                             for i in range(sc.n_bodies)]})
+
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_golden.json")
 json.dump(out, open(path, "w"), indent=0)
 print("wrote", path, {k: (len(v) if isinstance(v, list) else 1) for k, v in out.items() if k != "doc"})
+print("wrote", rc.REAL_MESH_FIXTURE, os.path.getsize(rc.REAL_MESH_FIXTURE), "bytes")

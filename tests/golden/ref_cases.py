@@ -148,3 +148,59 @@ def cable_cases():
         line = np.stack([-4 + 8 * s + 0.05 * rng.standard_normal(n), -3 + 5 * s, -0.6 + 2.5 * s + 0.3 * np.sin(9 * s)], axis=1)
         out.append((oc, r, flags, line, rng.uniform(-0.8, 0.8, (n, 3))))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ the reference's own meshes
+# Tests/Data/*.obj of the reference checkout: irregular valence, seams and slivers that UV ellipsoids do not have. Their vertex
+# positions and faces are kept as a fixture (tests/golden/ref_meshes.npz, written by make_ref_golden.py where the reference is
+# mounted) so that the GPU box, which has no reference checkout, runs the CUDA path on them.
+REAL_MESH_NAMES = ("hull_hydro", "sphere_R=1", "boat", "base_link_hydro", "torus_R=1_r=025")
+REAL_MESH_FIXTURE = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "ref_meshes.npz")
+
+
+def load_real_meshes():
+    from stonefish_b200.hydro import Mesh
+
+    z = np.load(REAL_MESH_FIXTURE)
+    return {n: Mesh(z[n + "/v"], z[n + "/f"]) for n in REAL_MESH_NAMES}
+
+
+def real_mesh_scenes(real):
+    """Scenes on the reference's meshes: (a) the FluidDynamicsTest snapshot with its real hulls (FluidDynamicsTestManager.cpp:93-161),
+    (b) the FloatingTest boat (FloatingTestManager.cpp:54-89) crossing a flat and a wavy sea at three drafts, raw integrator and
+    dispatcher, (c) every mesh under water and crossing the surface in Uniform + Jet + Pipe currents."""
+    from stonefish_b200.scenes import CG2C, FULL, RAW, Scene, _fill_body, config1, euler_zyx_quat, wave_field
+    from stonefish_b200._abi import SFH_POS_CROSSING, SFH_POS_INSIDE
+
+    out = [config1(real)]
+    boat = real["boat"]
+    for waves in (False, True):
+        ocean = Ocean(1000.0, 9.81)
+        if waves:
+            ocean.setWaves(wave_field())
+        ocean.AddVelocityField(Uniform((0.2, -0.1, 0.0)))
+        ocean.EnableCurrents()
+        st = new_body_states(6)
+        for k in range(6):
+            draft = (-0.05, 0.08, 0.2)[k % 3]  # CG above / at / below the mean surface (z down)
+            q = euler_zyx_quat(0.4 * k, 0.03 * (k - 2), 0.06 * (k - 3))
+            T_CG = make_transform(quat_to_basis(q), (3.0 * k - 7.0, 2.0 - 0.7 * k, draft))
+            _fill_body(st, k, boat, T_CG, transform_mul(T_CG, CG2C), (0.9, 0.1 * k, 0.05), (0.02, 0.05, -0.1 + 0.03 * k),
+                       SFH_POS_CROSSING if k < 3 else SFH_POS_AUTO, RAW if k < 3 else FULL, Cd=(1.0, 0.9, 1.1), Cf=(0.05, 0.06, 0.07))
+        out.append(Scene("boat_" + ("waves" if waves else "flat"), [boat], np.zeros(6, dtype=np.int64), ocean, st))
+    names = list(REAL_MESH_NAMES)
+    ocean = field_ocean(True)
+    st = new_body_states(2 * len(names))
+    body_mesh = np.zeros(2 * len(names), dtype=np.int64)
+    quats = scenes.random_unit_quats(77, 2 * len(names))
+    for k in range(2 * len(names)):
+        mi = k % len(names)
+        body_mesh[k] = mi
+        under = k < len(names)
+        # under water inside the pipe / at the jet's outlet, then crossing the wavy surface above them
+        org = (-4.0 + 2.0 * mi, 0.2 * mi - 0.4, 1.6 + 0.1 * mi) if under else (-3.0 + 1.5 * mi, -2.5 + 0.5 * mi, 0.05 * mi - 0.1)
+        T_CG = make_transform(quat_to_basis(quats[k]), org)
+        _fill_body(st, k, real[names[mi]], T_CG, transform_mul(T_CG, CG2C), (0.3, -0.2, 0.1 * mi), (0.1, -0.05, 0.02 * k),
+                   SFH_POS_INSIDE if under else SFH_POS_CROSSING, FULL if k % 2 else RAW, Cd=(1.1, 0.8, 0.9), Cf=(0.1, 0.05, 0.08))
+    out.append(Scene("real_meshes_jetpipe", [real[n] for n in names], body_mesh, ocean, st))
+    return out

@@ -1,5 +1,6 @@
 """Where does k_surface spend its time? Same 16 x 1M-face vessels with waves / Jet+Pipe currents switched off in turn."""
-import sys, numpy as np
+import os, sys, numpy as np
+os.environ["SFH_PROFILE_ROLES"] = "1"  # time the wet and the clip role of k_surface_lists in launches of their own
 sys.path.insert(0, ".")
 from stonefish_b200 import HydroContext, scenes
 ctx = HydroContext(0)
