@@ -116,6 +116,29 @@ __device__ __forceinline__ uint32_t damping_pair(const BodyP2& B, const sfh_curr
     return code;
 }
 
+#ifdef SFH_SOL
+// SPEED-OF-LIGHT PROBE (never the product: results are not the reference's). The mandated fp32 chain of a face pair and nothing
+// else: no fp32->fp64 conversions, no fp64 adds, no event counters, no range guards, no predicates — the twelve sums are kept
+// alive by plain fp32 adds. Its time is the measured ceiling of ANY bit-exact k_submerged with this data path
+// (profiles/sol_k_submerged_r02.txt); build with -DSFH_SOL (tools/sol.sh), run with bench.py --no-validate.
+__device__ __forceinline__ void sol_pair(const BodyP2& B, V3P fc, V3P fn1, P2 A, float* accf)
+{
+    const V3P r = fc - B.p;
+    const V3P vc = B.cur - (B.v + cross(B.omega, r));
+    const P2 vc_n = dot(vc, fn1);
+    const V3P vn = fn1 * vc_n;
+    const V3P vt = vc - vn;
+    const P2 vmag2 = dot(vc, vc);
+    const V3P q = ((vc * ieee_sqrt2(vmag2)) * neg(vc_n)) * A;
+    const V3P tq = cross(r, q);
+    const V3P s = vt * A;
+    const V3P ts = cross(r, s);
+    const P2 t[12] = {q.x, q.y, q.z, tq.x, tq.y, tq.z, s.x, s.y, s.z, ts.x, ts.y, ts.z};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) accf[i] = __fadd_rn(__fadd_rn(accf[i], lo(t[i])), hi(t[i]));
+}
+#endif
+
 // Air-drag block for a pair of faces: SolidEntity::ComputeAerodynamicForces (SolidEntity.cpp:1909-1919). The reference
 // tests dot(fn1, vn), not dot(vc, fn1), and scales by vn.length() — glm's COMPONENT COUNT, 3 — through
 // glm/gtx/scalar_multiplication.hpp (vec3 * int -> vec3 *= 3.f); both are kept. acc[0..5] = Fda Tda.
@@ -256,6 +279,11 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
     double acc[SFH_NACC_SUB];
 #pragma unroll
     for (int i = 0; i < SFH_NACC_SUB; ++i) acc[i] = 0.0;
+#ifdef SFH_SOL
+    float accf[SFH_NACC_SUB];
+#pragma unroll
+    for (int i = 0; i < SFH_NACC_SUB; ++i) accf[i] = 0.f;
+#endif
     uint32_t epack = 0, since_spill = 0;
     uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0; // degenerate, quadratic, skin of the current body (warp-uniform)
 
@@ -288,6 +316,10 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
     };
     auto flush = [&](uint32_t body) { // one partial record per (warp, body)
         spill();
+#ifdef SFH_SOL
+#pragma unroll
+        for (int i = 0; i < SFH_NACC_SUB; ++i) { acc[i] = (double)accf[i]; accf[i] = 0.f; }
+#endif
         PartialSub* rec = reinterpret_cast<PartialSub*>(P.partials) + (wg + body);
 #pragma unroll
         for (int i = 0; i < SFH_NACC_SUB; ++i) {
@@ -355,6 +387,14 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
             const V3P fv2 = p3 - p1;
             const V3P fn = cross(fv1, fv2);
             const P2 len2 = dot(fn, fn);
+#ifdef SFH_SOL
+            {
+                const P2 len = ieee_sqrt2(len2);
+                const V3P csum = (p1 + p2) + p3;
+                sol_pair(B, V3P{ieee_div3_2(csum.x), ieee_div3_2(csum.y), ieee_div3_2(csum.z)}, normalize_fast(fn, len), len * pk1(0.5f), accf);
+                continue;
+            }
+#endif
             const bool dA = lo(len2) < 1e-12f, dB = hi(len2) < 1e-12f; // SolidEntity.cpp:1764
             const bool mA = vA && !dA, mB = vB && !dB;
             epack += (vA && dA ? 1u : 0u) + (vB && dB ? 1u : 0u);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (one kernel) into the numbers DESIGN.md / profiles/ quote: duration, DRAM traffic, pipe
 utilisation, issue efficiency, stall reasons, dynamic instruction mix and the hottest SASS lines.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [faces_per_launch] [--traffic-json profiles/ncu_traffic_rNN.json]
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [faces_per_launch] [--traffic-json profiles/ncu_traffic_rNN.json] [--report-name profiles/x.txt]
 (--traffic-json also writes the per-face DRAM traffic and the pipe utilisations bench.py quotes as roofline.traffic / .secondary)"""
 import collections, csv, io, json, re, subprocess, sys
 
@@ -10,6 +10,11 @@ traffic_json = None
 if "--traffic-json" in argv:
     i = argv.index("--traffic-json")
     traffic_json = argv[i + 1]
+    del argv[i:i + 2]
+report_name = "profiles/ncu_k_submerged_r02.txt"
+if "--report-name" in argv:
+    i = argv.index("--report-name")
+    report_name = argv[i + 1]
     del argv[i:i + 2]
 rep = argv[1]
 faces = float(argv[2]) if len(argv) > 2 else None
@@ -43,7 +48,7 @@ if traffic_json and faces:
                "command": "ncu --set full --clock-control none --import-source on -k regex:k_submerged -s 3 -c 1 python bench.py --bodies 1024 --steps 3 --warmup 1 --no-cpu",
                "faces_per_launch": int(faces), "dram_bytes_read": rd, "dram_bytes_write": wr,
                "dram_bytes_per_face": round((rd + wr) / faces, 5), "duration_us": num("gpu__time_duration.sum"),
-               "report": "profiles/ncu_k_submerged_r01.txt",
+               "report": report_name,
                "secondary": {"issue_slot_utilisation": round(num("smsp__issue_active.avg.pct_of_peak_sustained_active"), 3),
                              "fma_pipe": round(num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"), 3),
                              "xu_pipe": round(num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"), 3),
