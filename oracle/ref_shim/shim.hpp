@@ -167,6 +167,11 @@ struct Mesh {
     std::vector<Face> faces;
     std::vector<glm::vec3> pos;
     glm::vec3 getVertexPos(size_t faceID, unsigned short index) const { return pos[faces[faceID].vertexID[index]]; }
+    // what HydroGPU (integration/files/Library/src/core/HydroGPU.cpp) uploads: OpenGLDataStructs.h:174-200
+    void* getFaceDataPointer() const { return (void*)&faces[0].vertexID[0]; }
+    size_t getNumOfVertices() const { return pos.size(); }
+    void* getVertexDataPointer() const { return (void*)&pos[0].x; }
+    size_t getVertexSize() const { return sizeof(glm::vec3); }
 };
 
 // SimulationApp::getApp()->getSimulationManager()->getGravity()
@@ -187,6 +192,7 @@ public:
     virtual Vector3 GetVelocityAtPoint(const Vector3& p) const = 0;
     void setEnabled(bool en) { enabled = en; }
     bool isEnabled() const { return enabled; }
+    virtual VelocityFieldType getType() const = 0;
 protected:
     bool enabled = true;
 };
@@ -194,7 +200,9 @@ class Uniform : public VelocityField {
 public:
     Uniform(const Vector3& velocity);
     void setVelocity(const Vector3& x);
+    Vector3 getVelocity() const { return v; } // Uniform.cpp:59-62
     Vector3 GetVelocityAtPoint(const Vector3& p) const;
+    VelocityFieldType getType() const { return VelocityFieldType::UNIFORM; }
 private:
     Vector3 v;
 };
@@ -203,7 +211,9 @@ public:
     Jet(const Vector3& point, const Vector3& direction, Scalar radius, Scalar outletVelocity);
     void setOutletVelocity(Scalar x);
     Vector3 GetVelocityAtPoint(const Vector3& p) const;
+    VelocityFieldType getType() const { return VelocityFieldType::JET; }
 private:
+    friend class HydroGPU; // as integration/stonefish_v1.6.0.patch adds to Jet.h
     Vector3 c, n;
     Scalar r, vout;
 };
@@ -212,7 +222,9 @@ public:
     Pipe(const Vector3& point1, const Vector3& point2, Scalar radius1, Scalar radius2, Scalar inletVelocity, Scalar exponent);
     void setInletVelocity(Scalar v);
     Vector3 GetVelocityAtPoint(const Vector3& p) const;
+    VelocityFieldType getType() const { return VelocityFieldType::PIPE; }
 private:
+    friend class HydroGPU; // as the patch adds to Pipe.h
     Vector3 p1, n;
     Scalar l, r1, r2, vin, gamma;
 };
@@ -240,12 +252,14 @@ public:
     void GetSpectrumSample(int i, int j, float lengthScale, float kMin, float* result);
     float spectrum(float kx, float ky, bool omnispectrum = false);
     float omega(float k);
+    const OceanParams& getOceanParams() const { return params; } // accessor added by the patch (OpenGLOcean.h)
     OceanParams params;
 };
 class OpenGLRealOcean : public OpenGLOcean {
 public:
     GLfloat ComputeInterpolatedWaveData(GLfloat x, GLfloat y, GLuint channel);
     GLfloat ComputeWaveHeight(GLfloat x, GLfloat y);
+    const GLfloat* getFFTData() const { return fftData; }        // accessor added by the patch (OpenGLRealOcean.h)
     GLfloat* fftData = nullptr;
 };
 
@@ -257,6 +271,7 @@ public:
     glm::vec3 GetFluidVelocity(const glm::vec3& point) const;
     bool hasWaves() const { return waves; }
     Fluid getLiquid() const { return liquid; }
+    OpenGLOcean* getOpenGLOcean() { return glOcean; } // Ocean.h:141
     // data (filled by the harness)
     bool waves = false;
     Fluid liquid;

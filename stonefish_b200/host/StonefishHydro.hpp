@@ -106,6 +106,13 @@ public:
         const Scalar s = Scalar(1.0) / std::sqrt(direction.x * direction.x + direction.y * direction.y + direction.z * direction.z);
         n = Vector3(direction.x * s, direction.y * s, direction.z * s);
     }
+    //! From the members sf::Jet holds after construction (c, n already normalised, r, vout): no second normalisation, same bits
+    static Jet* FromMembers(const Vector3& c, const Vector3& n, Scalar r, Scalar vout)
+    {
+        Jet* j = new Jet(c, Vector3(1, 0, 0), r, vout);
+        j->n = n;
+        return j;
+    }
     void setOutletVelocity(Scalar x) { vout = x; }
     Scalar getOutletVelocity() const { return vout; }
     VelocityFieldType getType() const override { return VelocityFieldType::JET; }
@@ -131,6 +138,14 @@ public:
         l = std::sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
         const Scalar s = Scalar(1.0) / l; // btVector3 operator/(v, s) == v * (1/s)
         n = Vector3(d.x * s, d.y * s, d.z * s);
+    }
+    //! From the members sf::Pipe holds after construction (p1, n, l, r1, r2, vin, gamma)
+    static Pipe* FromMembers(const Vector3& p1, const Vector3& n, Scalar l, Scalar r1, Scalar r2, Scalar vin, Scalar gamma)
+    {
+        Pipe* p = new Pipe(p1, Vector3(p1.x + 1, p1.y, p1.z), r1, r2, vin, gamma);
+        p->n = n;
+        p->l = l;
+        return p;
     }
     void setInletVelocity(Scalar x) { vin = x; }
     Scalar getInletVelocity() const { return vin; }
@@ -249,6 +264,7 @@ enum class GeometryApproxType { AUTO, SPHERE, CYLINDER, ELLIPSOID };
 struct SolidBody {
     uint32_t meshId = 0;           // from HydroEngine::UploadMesh(getPhysicsMesh())
     bool buoyant = true;           // isBuoyant()
+    bool dampingForces = true;     // false: evaluated like an internal part of a Compound (pSettings.dampingForces = false, Compound.cpp:420)
     Vector3 fdCd{1, 1, 1}, fdCf{0, 0, 0};
     Scalar volume = 0, surface = 0;
     Vector3 P_CB;                  // centre of buoyancy in the CG frame
@@ -312,7 +328,7 @@ public:
             std::memset(&s, 0, sizeof(s));
             s.mesh_id = b.meshId;
             s.mode = SFH_POS_AUTO;
-            s.flags = (uint32_t)SFH_F_DISPATCH | (settings.dampingForces ? (uint32_t)SFH_F_DAMPING : 0u) |
+            s.flags = (uint32_t)SFH_F_DISPATCH | (settings.dampingForces && b.dampingForces ? (uint32_t)SFH_F_DAMPING : 0u) |
                       (settings.reallisticBuoyancy ? (uint32_t)SFH_F_BUOYANCY : 0u) | (b.buoyant ? (uint32_t)SFH_F_BUOYANT : 0u);
             std::memcpy(s.T_CG, b.T_CG.m, sizeof(s.T_CG));
             std::memcpy(s.T_C, b.T_C.m, sizeof(s.T_C));

@@ -180,6 +180,26 @@ def config5(n_vessels: int = 128, segments: int = 1000, stacks: int = 501, uniqu
     return Scene(f"cfg5_vessels_{'unique' if unique_meshes else 'shared'}", meshes, body_mesh, ocean, st)
 
 
+def config1_layout():
+    """The entities of the FluidDynamicsTest snapshot: (kind, [(mesh index, part offset)], quaternion, origin, v, omega) with
+    mesh indices 0 sphere, 1 box, 2 hull_hydro, 3 sphere_R=1 (FluidDynamicsTestManager.cpp:93-161)."""
+    I = (0.0, 0.0, 0.0, 1.0)
+    Z = (0.0, 0.0, 0.0)
+    out = [("solid", [(0, Z)], I, (0, 0, 0), (0, 0, 0.4), Z),                                       # Sphere, crossing the surface
+           ("solid", [(1, Z)], I, (2, 0, 0), (0.1, 0, 0.3), (0.0, 0.2, 0.0)),                        # Box, crossing
+           ("compound", [(0, (0, 0, 0)), (0, (2.0, 0, 0))], euler_zyx_quat(0.0, 0.5, 0.0), (6, 0, -5), Z, Z),   # in the air
+           ("solid", [(2, Z)], euler_zyx_quat(0.0, 0.5, 0.0), (8, 0, -5), Z, Z),                     # Hull, in the air
+           ("solid", [(3, Z)], euler_zyx_quat(0.0, 0.5, 0.0), (11, 0, -0.3), (0, 0, 1.0), Z),        # SphereR1M, dropped to the surface
+           ("solid", [(1, Z)], I, (4, 0, 0), (0, 0, 0.2), Z),                                        # Featherstone link
+           ("solid", [(1, Z)], I, (-7, 0, 1), (0.6, 0, 0), Z),                                       # Hull1 (thruster driven)
+           ("solid", [(1, Z)], euler_zyx_quat(math.pi / 2, 0, 0), (-5, 2, 1), (0, 0.6, 0), Z)]       # Hull2
+    for i in range(8):
+        yaw = math.pi / 4 * i
+        out.append(("compound", [(1, (0, 0.5, 0)), (1, (0, -0.5, 0))], euler_zyx_quat(yaw, 0, 0), (0, 0, 2 + 2 * i),
+                    (0.8 * math.cos(yaw), 0.8 * math.sin(yaw), 0.0), (0, 0, 0.05)))
+    return out
+
+
 def config1(real_meshes: dict | None = None) -> Scene:
     """FluidDynamicsTest scene (Tests/FluidDynamicsTest/FluidDynamicsTestManager.cpp:81-161) as a static snapshot:
     flat sea, SUBMERGED-mode buoyant bodies at their initial poses, full dispatcher (AUTO position from the AABB,
@@ -193,33 +213,11 @@ def config1(real_meshes: dict | None = None) -> Scene:
     sph1 = real_meshes.get("sphere_R=1") or M.uv_ellipsoid(1.0, 1.0, 1.0, 24, 21)     # 960 faces
     meshes = [sphere, boxm, hull, sph1]
     ocean = Ocean(1000.0, 9.81)
-    I = (0.0, 0.0, 0.0, 1.0)
     bodies = []  # (mesh idx, T_CG, T_C, v, omega)
-
-    def T(q, o):
-        return make_transform(quat_to_basis(q), o)
-
-    def solid(mi, q, o, v=(0, 0, 0), w=(0, 0, 0)):
-        t = T(q, o)
-        bodies.append((mi, t, t, v, w))
-
-    def compound(parts, q, o, v=(0, 0, 0), w=(0, 0, 0)):
-        t = T(q, o)
-        for mi, po in parts:
-            bodies.append((mi, t, transform_mul(t, make_transform(None, po)), v, w))
-
-    solid(0, I, (0, 0, 0), (0, 0, 0.4))                                   # Sphere, crossing the surface
-    solid(1, I, (2, 0, 0), (0.1, 0, 0.3), (0.0, 0.2, 0.0))                # Box, crossing
-    compound([(0, (0, 0, 0)), (0, (2.0, 0, 0))], euler_zyx_quat(0.0, 0.5, 0.0), (6, 0, -5))   # in the air
-    solid(2, euler_zyx_quat(0.0, 0.5, 0.0), (8, 0, -5))                   # Hull, in the air
-    solid(3, euler_zyx_quat(0.0, 0.5, 0.0), (11, 0, -0.3), (0, 0, 1.0))   # SphereR1M, dropped to the surface
-    solid(1, I, (4, 0, 0), (0, 0, 0.2))                                   # Featherstone link
-    solid(1, I, (-7, 0, 1), (0.6, 0, 0))                                  # Hull1 (thruster driven)
-    solid(1, euler_zyx_quat(math.pi / 2, 0, 0), (-5, 2, 1), (0, 0.6, 0))  # Hull2
-    for i in range(8):
-        yaw = math.pi / 4 * i
-        compound([(1, (0, 0.5, 0)), (1, (0, -0.5, 0))], euler_zyx_quat(yaw, 0, 0), (0, 0, 2 + 2 * i),
-                 (0.8 * math.cos(yaw), 0.8 * math.sin(yaw), 0.0), (0, 0, 0.05))
+    for kind, parts, q, o, v, w in config1_layout():
+        t = make_transform(quat_to_basis(q), o)
+        for mi, po in parts:  # a plain solid is one part at the origin of its own frame
+            bodies.append((mi, t, transform_mul(t, make_transform(None, po)) if kind == "compound" else t, v, w))
     st = new_body_states(len(bodies))
     body_mesh = np.zeros(len(bodies), dtype=np.int64)
     for k, (mi, tcg, tc, v, w) in enumerate(bodies):
