@@ -16,11 +16,16 @@
 #pragma once
 
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/sfh.h"
@@ -429,6 +434,11 @@ public:
     }
 
     sfh_ctx* raw() { return ctx; }
+    //! The raw records of the last ComputeHydrodynamicForces / ComputeAerodynamicForces (validation counters included)
+    const std::vector<sfh_info>& LastInfos() const { return infos; }
+    void ClearInfos() { infos.clear(); }
+    //! Feed a wave field this engine's Ocean mirror did not hand over itself (HydroEngineMulti shares one Ocean between engines)
+    void UploadWaves(const sfh_waves& w) { Check(sfh_waves_upload(ctx, &w), "sfh_waves_upload"); }
 
 private:
     static void Put(double* d, const Vector3& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
@@ -457,6 +467,148 @@ private:
     sfh_atmosphere atmosphere;
     std::vector<sfh_body_state> states;
     std::vector<sfh_info> infos;
+};
+
+// ------------------------------------------------------------------------------------------------ several GPUs
+//! Order-independent 64-bit checksum of a set of result records (= stonefish_b200/sharding.py:checksum): the wrapping sum of a
+//! per-record FNV-style hash. Equal sets of records give equal sums whatever their partition over devices.
+inline uint64_t Checksum(const std::vector<sfh_info>& infos)
+{
+    uint64_t sum = 0;
+    for (const sfh_info& r : infos) {
+        uint64_t w[sizeof(sfh_info) / 8], h = 0xCBF29CE484222325ull;
+        std::memcpy(w, &r, sizeof(w));
+        for (uint64_t x : w) { h = (h ^ x) * 0x100000001B3ull; h ^= h >> 29; }
+        sum += h;
+    }
+    return sum;
+}
+
+//! The bodies of one simulation spread over several GPUs of one node: ONE context and ONE host thread per device, bodies
+//! block-partitioned (sizes differ by at most one), every shard stepped concurrently, the results back in the caller's bodies.
+//! Bodies are independent: there is no traffic between the devices. Pass the same device twice ({0, 0}) to get
+//! two contexts on one GPU (tests on single-GPU machines).
+class HydroEngineMulti {
+public:
+    explicit HydroEngineMulti(const std::vector<int>& cudaDevices)
+    {
+        if (cudaDevices.empty()) throw std::runtime_error("HydroEngineMulti: no device given");
+        for (int d : cudaDevices) engines.emplace_back(new HydroEngine(d));
+        for (size_t r = 0; r < engines.size(); ++r) workers.emplace_back(new Worker());
+    }
+    size_t size() const { return engines.size(); }
+    HydroEngine& engine(size_t r) { return *engines.at(r); }
+
+    //! Contiguous block [first, last) of n units for shard `rank` of `world` (= sharding.py:shard_range)
+    static std::pair<size_t, size_t> ShardRange(size_t n, size_t rank, size_t world)
+    {
+        const size_t base = n / world, rem = n % world, lo = rank * base + (rank < rem ? rank : rem);
+        return {lo, lo + base + (rank < rem ? 1 : 0)};
+    }
+
+    //! Upload a mesh to EVERY device (a body may land on any of them); the id is valid on all.
+    uint32_t UploadMesh(const void* vertexData, size_t vertexSize, size_t numVertices, const void* faceData, size_t numFaces)
+    {
+        uint32_t id = 0;
+        for (size_t r = 0; r < engines.size(); ++r) {
+            const uint32_t got = engines[r]->UploadMesh(vertexData, vertexSize, numVertices, faceData, numFaces);
+            if (r && got != id) throw std::runtime_error("HydroEngineMulti: mesh ids diverged between devices (mix of UploadMesh and UploadMeshOn?)");
+            id = got;
+        }
+        return id;
+    }
+    //! Upload a mesh to ONE device only — batches of independent environments whose bodies never change shard (instance i of n
+    //! lives on ShardOf(i, n)). Ids are per device then: do not mix with UploadMesh.
+    uint32_t UploadMeshOn(size_t shard, const void* vertexData, size_t vertexSize, size_t numVertices, const void* faceData, size_t numFaces)
+    {
+        return engines.at(shard)->UploadMesh(vertexData, vertexSize, numVertices, faceData, numFaces);
+    }
+    size_t ShardOf(size_t body, size_t nBodies) const
+    {
+        for (size_t r = 0; r < engines.size(); ++r)
+            if (body < ShardRange(nBodies, r, engines.size()).second) return r;
+        return engines.size() - 1;
+    }
+
+    //! HydroEngine::ComputeHydrodynamicForces for bodies[ShardRange(r)] on device r, all r at once.
+    void ComputeHydrodynamicForces(const HydrodynamicsSettings& settings, Ocean& ocn, const std::vector<SolidBody*>& bodies)
+    {
+        sfh_waves w;
+        if (ocn.TakeWavesDirty(w))
+            for (auto& e : engines) e->UploadWaves(w);
+        const size_t G = engines.size();
+        for (size_t r = 0; r < G; ++r) {
+            const auto range = ShardRange(bodies.size(), r, G);
+            workers[r]->Run([this, r, range, &settings, &ocn, &bodies]() {
+                const std::vector<SolidBody*> mine(bodies.begin() + (ptrdiff_t)range.first, bodies.begin() + (ptrdiff_t)range.second);
+                if (!mine.empty()) engines[r]->ComputeHydrodynamicForces(settings, ocn, mine);
+                else engines[r]->ClearInfos();
+            });
+        }
+        std::string err;
+        for (size_t r = 0; r < G; ++r) {
+            const std::string e = workers[r]->Wait();
+            if (!e.empty() && err.empty()) err = "device shard " + std::to_string(r) + ": " + e;
+        }
+        if (!err.empty()) throw std::runtime_error(err);
+    }
+
+    //! Checksum of the last step's records over all shards (what bench.py gathers over NCCL, here inside one process)
+    uint64_t LastChecksum() const
+    {
+        uint64_t s = 0;
+        for (const auto& e : engines) s += Checksum(e->LastInfos());
+        return s;
+    }
+
+private:
+    struct Worker { // one host thread per device, alive as long as the engine
+        std::thread th;
+        std::mutex m;
+        std::condition_variable cv;
+        std::function<void()> job;
+        std::string error;
+        bool busy = false, quit = false;
+        Worker()
+        {
+            th = std::thread([this]() {
+                std::unique_lock<std::mutex> lk(m);
+                for (;;) {
+                    cv.wait(lk, [this]() { return busy || quit; });
+                    if (quit) return;
+                    std::function<void()> j = std::move(job);
+                    lk.unlock();
+                    std::string e;
+                    try { j(); } catch (const std::exception& ex) { e = ex.what(); }
+                    lk.lock();
+                    error = e;
+                    busy = false;
+                    cv.notify_all();
+                }
+            });
+        }
+        ~Worker()
+        {
+            { std::lock_guard<std::mutex> lk(m); quit = true; }
+            cv.notify_all();
+            th.join();
+        }
+        void Run(std::function<void()> j)
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = std::move(j);
+            busy = true;
+            cv.notify_all();
+        }
+        std::string Wait()
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [this]() { return !busy; });
+            return error;
+        }
+    };
+    std::vector<std::unique_ptr<HydroEngine>> engines;
+    std::vector<std::unique_ptr<Worker>> workers;
 };
 
 // ------------------------------------------------------------------------------------------------ compounds

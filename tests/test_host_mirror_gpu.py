@@ -138,3 +138,28 @@ def test_cpp_host_mirror_generated_waves(tmp_path, ctx):
     vel = np.stack([0.1 * s, np.full(40, -0.2), 0.05 * np.arange(40)], axis=1)
     cab = ctx.compute_cables(sc.ocean, [(0, 40, 0.02, 7)], pos, vel)
     assert np.array_equal(np.fromfile(outs[3], dtype=np.float64).reshape(40, 9), cab) and np.abs(cab[:, 2]).max() > 0
+
+
+@pytest.mark.parametrize("contexts", [2, 3])
+def test_cpp_host_mirror_several_contexts(tmp_path, oracle, contexts):
+    """sfb::HydroEngineMulti: one process, one host thread and one sfh context per shard, bodies block-partitioned (shard_range).
+    With one GPU the shards are contexts on the same device: what is checked is the host side — partition, concurrent steps, results
+    back in the caller's bodies, counters equal and sums equal to 1e-12 against ONE context, and against the oracle."""
+    import json
+
+    assert os.path.exists(DEMO), "build the host mirror demo first (make -C stonefish_b200/host)"
+    sc = scenes.config1()                      # 25 bodies: outside, inside and across the surface
+    sc.ocean.AddVelocityField(Uniform((0.2, -0.1, 0.0)))
+    sc.ocean.EnableCurrents()
+    scene, res = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(scene, sc)
+    txt = subprocess.check_output([DEMO, scene, res, "4", "--contexts", str(contexts)], text=True)
+    rec = json.loads(txt.strip().splitlines()[-1])
+    assert rec["scaling"] == "strong" and rec["contexts"] == contexts and rec["bodies_total"] == sc.n_bodies
+    assert rec["counts_equal"] is True and rec["max_rel_diff_vs_one_context"] <= 1e-12
+    got = read_results(res, sc.n_bodies)
+    ref, _ = oracle.OracleScene(sc.meshes, sc.body_mesh, sc.ocean, sc.states).step(1, n_threads=4)
+    for k in ("class_count", "n_degenerate", "n_quadratic", "n_skin", "n_faces", "position"):
+        assert np.array_equal(got[k], ref[k]), k
+    err, where = max_rel_err(got, ref)
+    assert err <= REL_TOL, (err, where)
