@@ -543,6 +543,9 @@ __device__ __forceinline__ void clip_vertices(const WavesDev& wv, const WaveCons
     }
 }
 
+// (Measured and rejected: a first pass that sorts the slots of a clip chunk into a class-7 list — sent through the pair code of the wet
+// role — and a list of cut faces for the general code: the clip role got 25 % SLOWER (0.102 -> 0.127 ms per 8212 chunks; twice the code,
+// 200-360 bytes of spills, list traffic), cfg 5 fell from 47.3 to 42.6 G tri-evals/s.)
 // One chunk the water line may cross: per-vertex depths were left in s_v[].w; the reference's eight classes, one face per lane
 // at a time (SolidEntity.cpp:1347-1687).
 template <bool WAVES, int CUR, bool DEBUG>
