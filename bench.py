@@ -366,8 +366,11 @@ def measure(rig: Rig, args, workload: str, n: int, first: int, keep_host: int, s
             launches = t.launches
             dominant = "k_submerged" if t.submerged_ms >= t.surface_ms else "surface path (k_classify + k_surface_wet + k_surface_clip)"
             split.append((t.classify_ms, t.wet_ms, t.clip_ms))
-            chunks = {"surface": int(t.chunks_surface), "wet": int(t.chunks_wet), "clip": int(t.chunks_clip),
-                      "dry": int(t.chunks_surface - t.chunks_wet - t.chunks_clip)}
+            if t.chunks_surface and not (t.chunks_wet or t.chunks_clip):  # direct mode: every warp classifies its own item, no lists
+                chunks = {"surface": int(t.chunks_surface), "mode": "direct (no lists: kinds not recorded)"}
+            else:
+                chunks = {"surface": int(t.chunks_surface), "wet": int(t.chunks_wet), "clip": int(t.chunks_clip),
+                          "dry": int(t.chunks_surface - t.chunks_wet - t.chunks_clip)}
         ctx.set_profiling(False)
         rig.barrier()
 

@@ -17,6 +17,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 # full captures: k_submerged on cfg4 (1024 bodies), the wet and the clip role of k_surface_lists and k_classify on cfg5 (16 bodies)
 ncu --set full --clock-control none --import-source on -k regex:k_submerged -s 3 -c 1 -o gpurun_out/sub_r02 -f \
     python bench.py --workload cfg4 --bodies 1024 --steps 3 --warmup 1 --no-cpu --no-validate > /dev/null 2>&1
-SFH_PROFILE_ROLES=1 ncu --set full --clock-control none --import-source on -k regex:"k_surface_lists|k_classify" -s 9 -c 3 -o gpurun_out/surf_r02 -f \
+SFH_PROFILE_ROLES=1 ncu --set full --clock-control none --import-source on -k regex:"k_surface_lists|k_classify" -s 10 -c 3 -o gpurun_out/surf_r02 -f \
     python bench.py --workload cfg5 --bodies 16 --steps 2 --warmup 3 --no-cpu --no-validate > /dev/null 2>&1
 tail -c 400 gpurun_out/bench_default_r02.json

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (one kernel) into the numbers DESIGN.md / profiles/ quote: duration, DRAM traffic, pipe
 utilisation, issue efficiency, stall reasons, dynamic instruction mix and the hottest SASS lines.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [faces_per_launch] [--traffic-json profiles/ncu_traffic_rNN.json] [--report-name profiles/x.txt]
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [faces_per_launch] [--traffic-json profiles/ncu_traffic_rNN.json] [--report-name profiles/x.txt] [--skip N]
 (--traffic-json also writes the per-face DRAM traffic and the pipe utilisations bench.py quotes as roofline.traffic / .secondary)"""
 import collections, csv, io, json, re, subprocess, sys
 
@@ -16,9 +16,14 @@ if "--report-name" in argv:
     i = argv.index("--report-name")
     report_name = argv[i + 1]
     del argv[i:i + 2]
+skip = []
+if "--skip" in argv:  # reports with several kernels: summarise launch number N of the report
+    i = argv.index("--skip")
+    skip = ["--launch-skip", argv[i + 1], "--launch-count", "1"]
+    del argv[i:i + 2]
 rep = argv[1]
 faces = float(argv[2]) if len(argv) > 2 else None
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep] + skip + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
@@ -60,7 +65,7 @@ print("stall reasons (warps stalled per issue-active cycle):")
 st = {h.split("issue_stalled_")[1].split("_per_issue")[0]: float(v) for h, (v, u) in m.items() if "issue_stalled_" in h and h.endswith("per_issue_active.ratio")}
 for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:9]:
     print(f"  {k:24s} {v:.3f}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep] + skip + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]; data = rows[2:]
 ia, isrc, isamp = h.index("Instructions Executed"), h.index("Source"), h.index("# Samples")
