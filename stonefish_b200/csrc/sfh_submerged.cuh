@@ -226,6 +226,9 @@ struct WarpStage { // shared memory private to one warp
     float4 v[SFH_CH_VERTS];
     BodyDev body;
 };
+struct WarpStageSurf : WarpStage { // the surface kernel's clip role: which vertex slots a sub-item's faces refer to
+    uint32_t need[8];
+};
 
 __device__ __forceinline__ PipeAddr warp_pipe_init(ChunkPipe& p, uint32_t lane)
 {

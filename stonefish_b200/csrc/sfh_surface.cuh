@@ -542,6 +542,35 @@ __device__ __forceinline__ void clip_vertices(const WavesDev& wv, const WaveCons
         s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z));
     }
 }
+// The same for a SUB-ITEM (faces [f0, f1) of the chunk): only the vertices those faces refer to. Vertex slots are handed out in the
+// order the faces first use them, so a quarter of the faces touches two or three of the eight groups of 32 slots: the other trips —
+// two wave lookups per vertex each — are skipped. `need`: 8 words of the warp's shared memory.
+template <bool WAVES>
+__device__ __forceinline__ void clip_vertices_of(const WavesDev& wv, const WaveConst& wc, const BodyDev& sb, const ChunkView& cv, float4* __restrict__ s_v,
+                                                 uint32_t lane, uint32_t f0, uint32_t f1, uint32_t* __restrict__ need)
+{
+    if (lane < 8u) need[lane] = 0u;
+    __syncwarp();
+    for (uint32_t slot = f0 + lane; slot < f1; slot += 32u) {
+        const uint32_t fp = cv.faces[slot];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t id = (fp >> (8 * k)) & 255u;
+            atomicOr(&need[id >> 5], 1u << (id & 31u));
+        }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t g = 0; g < 8u; ++g) {
+        const uint32_t m = need[g]; // warp-uniform
+        if (m == 0u) continue;
+        const uint32_t i = lane + 32u * g;
+        if ((m >> lane) & 1u) {
+            const F3 pw = xform(sb.R, sb.t, cv.x[i], cv.y[i], cv.z[i]);
+            s_v[i] = make_float4(pw.x, pw.y, pw.z, get_depth<WAVES>(wv, wc, pw.x, pw.y, pw.z));
+        }
+    }
+}
 
 // (Measured and rejected: a first pass that sorts the slots of a clip chunk into a class-7 list — sent through the pair code of the wet
 // role — and a list of cut faces for the general code: the clip role got 25 % SLOWER (0.102 -> 0.127 ms per 8212 chunks; twice the code,
@@ -648,7 +677,7 @@ __device__ __forceinline__ void clip_chunk(const SurfParams& P, const ChunkView&
 
 // One role of the consumer kernel: CLIP = false works through the wet list, CLIP = true through the clip list.
 template <bool CLIP, bool WAVES, int CUR, bool DEBUG>
-__device__ __forceinline__ void surface_role(const SurfParams& P, WarpStage& St, const sfh_current* s_cur, const CurGuard* s_guard, uint32_t n_cur,
+__device__ __forceinline__ void surface_role(const SurfParams& P, WarpStageSurf& St, const sfh_current* s_cur, const CurGuard* s_guard, uint32_t n_cur,
                                              uint32_t lane, uint32_t stream /* this warp's index among the role's warps */)
 {
     uint32_t* const ctrl = P.L.ctrl;
@@ -760,7 +789,8 @@ __device__ __forceinline__ void surface_role(const SurfParams& P, WarpStage& St,
                     if (cv.nv > 224u) xf(7u);
                 }
             } else { // ... and Ocean::GetDepth per vertex (SolidEntity.cpp:1349-1351): same bits for every incident face
-                clip_vertices<WAVES>(P.waves, wc, s_body, cv, s_v, lane);
+                if (split == 1u) clip_vertices<WAVES>(P.waves, wc, s_body, cv, s_v, lane);
+                else clip_vertices_of<WAVES>(P.waves, wc, s_body, cv, s_v, lane, q_cur * part, min(cv.nf, q_cur * part + part), St.need);
             }
             __syncwarp();
 
@@ -801,7 +831,7 @@ __device__ __forceinline__ void surface_role(const SurfParams& P, WarpStage& St,
 // Direct mode: sub-item u of the UNCLASSIFIED surface list, start to finish by this warp; one record at index u + body, zeros
 // for a dry chunk. Same per-face code as the roles, so the per-face terms are the same bits whichever mode ran.
 template <bool WAVES, int CUR, bool DEBUG>
-__device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStage& St, const sfh_current* s_cur, const CurGuard* s_guard, uint32_t n_cur,
+__device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStageSurf& St, const sfh_current* s_cur, const CurGuard* s_guard, uint32_t n_cur,
                                                uint32_t lane, uint32_t u, uint32_t split)
 {
     const uint32_t sh = 31u - __clz(split), part = SFH_CH_FACES >> sh;
@@ -848,7 +878,8 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStage& S
                 else        wet_chunk<WAVES, CUR, DEBUG, false, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
             }
         } else {
-            clip_vertices<WAVES>(P.waves, wc, s_body, cv, s_v, lane);
+            if (split == 1u) clip_vertices<WAVES>(P.waves, wc, s_body, cv, s_v, lane);
+            else clip_vertices_of<WAVES>(P.waves, wc, s_body, cv, s_v, lane, f0, f1, St.need);
             __syncwarp();
             clip_chunk<WAVES, CUR, DEBUG>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, cpack, body, orig, lane, f0, f1);
         }
@@ -879,7 +910,7 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStage& S
 template <bool WAVES, int CUR, bool DEBUG>
 __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SURF_MIN_BLOCKS) k_surface_lists(SurfParams P)
 {
-    __shared__ WarpStage s_stage[SFH_SUB_WPB];
+    __shared__ WarpStageSurf s_stage[SFH_SUB_WPB];
     __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
     __shared__ CurGuard s_guard[CUR ? SFH_MAX_CURRENTS : 1];
 
