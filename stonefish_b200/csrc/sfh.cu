@@ -434,7 +434,8 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     // Direct mode (sfh_surface.cuh): decided on the device from the number of surface items and T = the consumer's streams. Off
     // when the two roles are launched one by one to be timed (SFH_PROFILE_ROLES, tools/ablate_surface.py).
     const bool time_roles = prof && ctx->profile_roles;
-    const uint32_t direct_streams = time_roles ? 0u : (uint32_t)((g_wet + g_clip) * SFH_SUB_WPB);
+    const char* no_direct = getenv("SFH_NO_DIRECT"); // tests: small scenes through the LIST path too
+    const uint32_t direct_streams = (time_roles || (no_direct && no_direct[0] == '1')) ? 0u : (uint32_t)((g_wet + g_clip) * SFH_SUB_WPB);
     cp.direct_streams = direct_streams;
     // with host-side states the host knows when the step is certain to run in direct mode: k_classify is not even launched
     const bool surely_direct = direct_streams && plan.surf_ub && plan.surf_ub <= direct_streams;
@@ -611,7 +612,7 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
             out_target = static_cast<sfh_info*>(dp);
         }
         key.flags = (general ? 1u : 0u) | (ocean->has_waves ? 2u : 0u) | (plan.may_sub ? 4u : 0u) | (plan.may_surf ? 8u : 0u) | (aero ? 16u : 0u) |
-                    (zc ? 32u : 0u);
+                    (zc ? 32u : 0u) | ((getenv("SFH_NO_DIRECT") && getenv("SFH_NO_DIRECT")[0] == '1') ? 64u : 0u);
         key.chunks_ub = plan.chunks_ub; key.surf_ub = plan.surf_ub;
         key.d_states = ctx->d_states.p; key.d_info = ctx->d_info.p; key.h_states = ctx->h_states.p; key.h_info = ctx->h_info.p;
         key.h_ocean = ctx->h_ocean.p; key.d_ocean = ctx->d_ocean.p; key.d_meshes = ctx->d_meshes.p; key.d_bodies = ctx->d_bodies.p;

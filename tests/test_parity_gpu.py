@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("waves", [False, True])
 @pytest.mark.parametrize("currents", ["none", "uniform", "jetpipe"])
 @pytest.mark.parametrize("seed", [7, 8])
-def test_mixed_small_bit_exact_classes_and_forces(ctx, oracle, waves, currents, seed):
+def test_mixed_small_bit_exact_classes_and_forces(ctx, oracle, waves, currents, seed, surface_mode):
     sc = scenes.mixed_small(seed, waves, currents)
     gi, gc, ri, rc = run_both(ctx, oracle, sc)
     assert_counts_equal(gi, ri)
@@ -47,7 +47,7 @@ def test_config2_reduced_and_full(ctx, oracle):
 
 
 @pytest.mark.parametrize("waves", [False, True])
-def test_config3_reduced_and_full(ctx, oracle, waves):
+def test_config3_reduced_and_full(ctx, oracle, waves, surface_mode):
     for seg, st in ((100, 51), (400, 251)):
         sc = scenes.config3(seg, st, waves)
         gi, gc, ri, rc = run_both(ctx, oracle, sc)
@@ -60,7 +60,7 @@ def test_config3_reduced_and_full(ctx, oracle, waves):
             assert gi["Fb"][0][2] == -gi["Vsub"][0] * sc.ocean.density * sc.ocean.gravity
 
 
-def test_config1_scene_full_dispatch(ctx, oracle):
+def test_config1_scene_full_dispatch(ctx, oracle, surface_mode):
     sc = scenes.config1()
     gi, gc, ri, rc = run_both(ctx, oracle, sc)
     assert_counts_equal(gi, ri)
@@ -96,7 +96,7 @@ def test_config4_many_bodies_no_debug(ctx, oracle):
     assert err <= REL_TOL, (err, where)
 
 
-def test_config5_reduced(ctx, oracle):
+def test_config5_reduced(ctx, oracle, surface_mode):
     sc = scenes.config5(6, 120, 61, unique_meshes=True)
     gi, gc, ri, rc = run_both(ctx, oracle, sc)
     assert_counts_equal(gi, ri)
@@ -128,7 +128,7 @@ def test_keep_order_equals_morton_order(ctx, oracle):
     assert err <= 1e-12, (err, where)
 
 
-def test_edge_cases(ctx, oracle):
+def test_edge_cases(ctx, oracle, surface_mode):
     from stonefish_b200 import Mesh, Ocean, SfhError, new_body_states
 
     ocean = Ocean()
@@ -217,7 +217,7 @@ def test_graph_replay_of_small_steps_tracks_inputs(ctx, oracle):
 
 
 @pytest.mark.parametrize("depth,waves", [(0.05, False), (0.1, True), (4.0, False), (-6.0, False)])
-def test_compound_parts_sum_like_the_reference(ctx, oracle, depth, waves):
+def test_compound_parts_sum_like_the_reference(ctx, oracle, depth, waves, surface_mode):
     """Row a10, Compound::ComputeHydrodynamicForces (Compound.cpp:291-437): parts go through the C ABI as bodies sharing
     the compound's T_CG / velocities / AABB, the host sums them in part order (hydro.sum_compound) — against the oracle's
     restatement of the whole method, for crossing (flat and waves), inside and outside compounds, with an internal part,
@@ -269,7 +269,7 @@ def test_compound_parts_sum_like_the_reference(ctx, oracle, depth, waves):
     assert int(got["position"]) == expected
 
 
-def test_ragged_and_chunk_boundary_meshes(ctx, oracle):
+def test_ragged_and_chunk_boundary_meshes(ctx, oracle, surface_mode):
     """Mesh sizes around the 256-face / 256-vertex chunk limits, triangle soup (vertex-limited chunks), a single face,
     all in one step next to each other, crossing a wavy surface with Jet+Pipe currents."""
     from stonefish_b200 import meshes as M
@@ -307,7 +307,7 @@ def test_ragged_and_chunk_boundary_meshes(ctx, oracle):
 
 
 @pytest.mark.parametrize("waves", [False, True])
-def test_dry_chunk_skip_and_field_masks_are_exact(ctx, oracle, waves):
+def test_dry_chunk_skip_and_field_masks_are_exact(ctx, oracle, waves, surface_mode):
     """k_surface drops chunks whose bounding sphere lies above the highest possible surface and skips Jet/Pipe fields that
     cannot reach a chunk's sphere. Both are conservative tests, so codes and sums must stay what the oracle says — also for a
     NON-RIGID T_C (scaled, sheared basis: the sphere bound uses row / Frobenius norms, not |R| = 1), for hulls standing
@@ -407,7 +407,7 @@ def test_queued_device_steps_each_see_their_own_ocean(ctx):
     assert want[0].tobytes() != want[1].tobytes()
 
 
-def test_cuda_path_against_the_references_own_compiled_code(ctx, oracle):
+def test_cuda_path_against_the_references_own_compiled_code(ctx, oracle, surface_mode):
     """Directly against oracle/_ref/librefsrc.so — the reference's definitions compiled from its source text (shipped with the
     repository snapshot, built where the reference is mounted): resolved position and which outputs get assigned must be
     identical; the sums differ only by the reference's own fp32 sequential-summation noise (the oracle, which reproduces that

@@ -20,7 +20,7 @@ def unhex(v):
 
 
 @pytest.mark.parametrize("k", range(4))
-def test_cuda_path_on_the_references_meshes(ctx, oracle, k):
+def test_cuda_path_on_the_references_meshes(ctx, oracle, k, surface_mode):
     sc = rc.real_mesh_scenes(rc.load_real_meshes())[k]
     gi, gc, ri, rcodes = run_both(ctx, oracle, sc)
     # against the oracle in the CUDA path's own contract (identical fp32 per-face terms, fp64 sums): codes exact, sums 1e-9

@@ -67,7 +67,7 @@ for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:9]:
     print(f"  {k:24s} {v:.3f}")
 src = subprocess.run(["ncu", "-i", rep] + skip + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h = rows[1]; data = rows[2:]
+h = rows[1]; data = [r for r in rows[2:] if len(r) >= len(rows[1]) and r[rows[1].index("Instructions Executed")].strip().isdigit()]  # (functions that are not inlined start sections of their own)
 ia, isrc, isamp = h.index("Instructions Executed"), h.index("Source"), h.index("# Samples")
 by, samp = collections.Counter(), collections.Counter()
 for r in data:
