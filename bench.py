@@ -334,8 +334,12 @@ def measure(rig: Rig, args, workload: str, n: int, first: int, keep_host: int, s
     h_states[:] = states
     torch.cuda.synchronize(dev)
 
+    # what sfh_step derives from host-side states, the caller of a device-resident step says itself: which paths its bodies can take
+    modes = set(int(m) for m in np.unique(states["mode"]))
+    hints = (1 if modes <= {0, 1} else 0) | (2 if modes <= {0, 2} else 0)  # SFH_HINT_NO_SURFACE | SFH_HINT_NO_SUBMERGED
+
     def step_device():
-        ctx.compute_device(ostruct, d_states.data_ptr(), n, d_infos.data_ptr())
+        ctx.compute_device(ostruct, d_states.data_ptr(), n, d_infos.data_ptr(), hints)
 
     def step_host():
         ctx.lib.sfh_step(ctx.ctx, C.byref(ostruct), h_states.ctypes.data, n, h_infos.ctypes.data)

@@ -129,6 +129,15 @@ int sfh_step_debug(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* s
  * (sfh_sync after a device-resident step waits for the stream and fetches the step's status word). */
 int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies,
                     sfh_info* d_out);
+/* The same with what the caller knows about states the host cannot see (an environment batch knows its bodies' modes): the kernels of
+ * a path no body can take are not launched (sfh_step derives this itself from its host-side states). A body that takes an excluded
+ * path after all yields zero forces and makes the next sfh_sync return SFH_ERR_INVALID. */
+enum {
+    SFH_HINT_NO_SURFACE   = 1u << 0, /* no body crosses the surface: mode is SFH_POS_INSIDE or SFH_POS_OUTSIDE for all of them */
+    SFH_HINT_NO_SUBMERGED = 1u << 1  /* no body is entirely under water: mode is SFH_POS_CROSSING or SFH_POS_OUTSIDE           */
+};
+int sfh_step_device_hinted(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies,
+                           sfh_info* d_out, uint32_t hints);
 
 /* Aerodynamic twin: one recompute of the air drag of n_bodies bodies — replaces the
  * `for each atmosphere-ghost pair: atmosphere->ApplyFluidForces(...)` recompute, i.e.

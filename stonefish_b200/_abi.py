@@ -13,6 +13,7 @@ SFH_CURRENT_UNIFORM, SFH_CURRENT_JET, SFH_CURRENT_PIPE = 0, 1, 2
 SFH_POS_OUTSIDE, SFH_POS_INSIDE, SFH_POS_CROSSING, SFH_POS_AUTO = 0, 1, 2, 3
 SFH_F_DAMPING, SFH_F_BUOYANCY, SFH_F_BUOYANT, SFH_F_DISPATCH, SFH_F_AERO_CD = 1, 2, 4, 8, 16
 SFH_MESH_KEEP_ORDER = 1
+SFH_HINT_NO_SURFACE, SFH_HINT_NO_SUBMERGED = 1, 2
 SFH_FACE_CLASS_MASK, SFH_FACE_DEGENERATE, SFH_FACE_QUADRATIC, SFH_FACE_SKIN = 7, 8, 16, 32
 SFH_OK = 0
 
@@ -121,6 +122,7 @@ PROTOTYPES = {
     "sfh_step": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_step_debug": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sfh_step_device": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sfh_step_device_hinted": (C.c_int, [_ctx, _P(sfh_ocean), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]),
     "sfh_aero_step": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p]),
     "sfh_aero_step_debug": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sfh_aero_step_device": (C.c_int, [_ctx, _P(sfh_atmosphere), C.c_void_p, C.c_uint32, C.c_void_p]),

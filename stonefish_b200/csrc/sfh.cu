@@ -443,6 +443,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     pp.states = d_states; pp.meshes = ctx->d_meshes.p; pp.n_meshes = (uint32_t)ctx->meshes.size(); pp.n_bodies = n;
     pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;
     pp.off_sub = ctx->d_off_sub.p; pp.off_surf = ctx->d_off_surf.p; pp.status = ctx->d_status.p; pp.aero = plan.aero ? 1u : 0u;
+    pp.no_sub = plan.may_sub ? 0u : 1u; pp.no_surf = (plan.may_surf || plan.aero) ? 0u : 1u;
     uint32_t launches;
     if (n <= 1024) {
         k_prologue_scan<<<1, 1024, 0, ctx->stream>>>(pp);
@@ -1018,7 +1019,9 @@ int sfh_sync(sfh_ctx* ctx)
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         if (st != 0) {
             CU(ctx, cudaMemsetAsync(ctx->d_status.p, 0, sizeof(uint32_t), ctx->stream));
-            return fail(ctx, SFH_ERR_INVALID, "a body of a device-resident step referenced an unknown or released mesh id");
+            return fail(ctx, SFH_ERR_INVALID, (st & 4u) ? "a body of a device-resident step took a path its hints excluded" :
+                        ((st & 2u) ? "the surface work list of a device-resident step did not fit" :
+                                     "a body of a device-resident step referenced an unknown or released mesh id"));
         }
     }
     return SFH_OK;
@@ -1080,12 +1083,19 @@ int sfh_aero_step_debug(sfh_ctx* ctx, const sfh_atmosphere* atm, const sfh_body_
 
 int sfh_step_device(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies, sfh_info* d_out)
 {
+    return sfh_step_device_hinted(ctx, ocean, d_states, n_bodies, d_out, 0u);
+}
+
+int sfh_step_device_hinted(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n_bodies, sfh_info* d_out, uint32_t hints)
+{
     if (!ctx) return SFH_ERR_INVALID;
     if (!ocean || (!d_states && n_bodies) || (!d_out && n_bodies)) return fail(ctx, SFH_ERR_INVALID, "null argument");
     CU(ctx, cudaSetDevice(ctx->device));
     if (n_bodies == 0) return SFH_OK;
     StepPlan plan;
     plan.host_states = false;
+    plan.may_surf = !(hints & SFH_HINT_NO_SURFACE);
+    plan.may_sub = !(hints & SFH_HINT_NO_SUBMERGED);
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = run_step(ctx, ocean, d_states, n_bodies, d_out, plan);
     if (rc != SFH_OK) return rc;

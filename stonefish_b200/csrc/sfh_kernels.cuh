@@ -134,6 +134,7 @@ struct PrologueParams {
     uint32_t* off_surf; // n_bodies + 1
     uint32_t* status;   // [0] |= 1 if a body referenced an unknown mesh
     uint32_t aero;      // sfh_aero_step: every body runs the (aero variant of the) submerged face loop
+    uint32_t no_sub, no_surf; // the caller excluded the path (its kernels are not launched): a body that takes it is flagged, status |= 4
 };
 
 // SolidEntity::CheckBodyFluidPosition (SolidEntity.cpp:1239-1261); each corner narrowed to fp32 by
@@ -191,6 +192,10 @@ __device__ __forceinline__ void prologue_body(const PrologueParams& P, uint32_t 
     } else if (pos == SFH_POS_CROSSING) {
         if (dispatch && !(st.flags & SFH_F_BUOYANT)) buoyancy = false; // SolidEntity.cpp:1844
         kind = KIND_SURFACE;
+    }
+    if ((kind == KIND_SUBMERGED && P.no_sub) || (kind == KIND_SURFACE && P.no_surf)) {
+        atomicOr(P.status, 4u);
+        kind = KIND_NONE;
     }
     MeshDev m = {nullptr, nullptr, nullptr, nullptr, 0, 0};
     bool known = st.mesh_id < P.n_meshes;

@@ -460,9 +460,9 @@ class HydroContext:
                                             out.ctypes.data), "sfh_cable_step")
         return out
 
-    def compute_device(self, ocean_struct, d_states_ptr: int, n: int, d_out_ptr: int):
-        """Device-resident step (sfh_step_device): asynchronous on the context's stream."""
-        self._check(self.lib.sfh_step_device(self.ctx, C.byref(ocean_struct), d_states_ptr, n, d_out_ptr), "sfh_step_device")
+    def compute_device(self, ocean_struct, d_states_ptr: int, n: int, d_out_ptr: int, hints: int = 0):
+        """Device-resident step (sfh_step_device / sfh_step_device_hinted): asynchronous on the context's stream."""
+        self._check(self.lib.sfh_step_device_hinted(self.ctx, C.byref(ocean_struct), d_states_ptr, n, d_out_ptr, hints), "sfh_step_device_hinted")
 
     def GetDepth(self, ocean: Ocean, points: np.ndarray) -> np.ndarray:
         """Ocean::GetDepth(glm::vec3) for an [n,3] float32 array of world points."""

@@ -423,3 +423,35 @@ def test_cuda_path_against_the_references_own_compiled_code(ctx, oracle, surface
             assert np.array_equal(got[k], ref[k]), (sc.name, k)
         err, where = max_rel_err(got, ref)
         assert err <= 2e-4, (sc.name, err, where)
+
+
+def test_device_step_hints(ctx, oracle):
+    """sfh_step_device_hinted: the caller of a device-resident step says which paths its bodies can take (sfh_step sees that in its
+    host-side states); excluded paths launch nothing, results are the same, and a body that takes an excluded path after all is
+    reported by the next sfh_sync instead of silently getting zero forces."""
+    import torch
+
+    from stonefish_b200 import _abi
+    from stonefish_b200.hydro import BODY_STATE_DTYPE, INFO_DTYPE, SfhError
+
+    sc = scenes.config4(16, 50, 21, unique_meshes=True)          # all INSIDE
+    st = sc.bind(ctx)
+    dev = torch.device("cuda", 0)
+    d_st = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(dev)
+    d_out = torch.zeros(16 * INFO_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    o = sc.ocean.to_struct()
+
+    def run(hints):
+        d_out.zero_()
+        ctx.compute_device(o, d_st.data_ptr(), 16, d_out.data_ptr(), hints)
+        ctx.sync()
+        return d_out.cpu().numpy().view(INFO_DTYPE).copy()
+
+    plain, hinted = run(0), run(_abi.SFH_HINT_NO_SURFACE)
+    assert plain.tobytes() == hinted.tobytes() and np.abs(plain["Fdq"]).max() > 0
+    ref, _ = oracle.OracleScene(sc.meshes, sc.body_mesh, sc.ocean, sc.states).step(oracle.ORC_F64_ACC, n_threads=4)
+    assert_counts_equal(hinted, ref)
+    with pytest.raises(SfhError, match="excluded"):
+        run(_abi.SFH_HINT_NO_SUBMERGED)                          # every body IS submerged
+    again = run(_abi.SFH_HINT_NO_SURFACE)                        # the context is usable afterwards
+    assert again.tobytes() == plain.tobytes()
