@@ -799,6 +799,11 @@ __device__ __forceinline__ void surface_role(const SurfParams& P, WarpStageSurf&
             const uint32_t f0 = q_cur * part, f1 = min(cv.nf, f0 + part); // this sub-item's faces
             if (!CLIP) {
                 cls[7] += f1 > f0 ? f1 - f0 : 0u;
+#if defined(SFH_WET_ONLY_DAMP) /* timing probes of a split wet role (results are NOT the reference's): DESIGN.md 7b */
+                wet_chunk<WAVES, CUR, DEBUG, false, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
+#elif defined(SFH_WET_ONLY_BUOY)
+                wet_chunk<WAVES, CUR, DEBUG, true, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
+#else
                 if (S.buoy) {
                     if (S.damp) wet_chunk<WAVES, CUR, DEBUG, true, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
                     else        wet_chunk<WAVES, CUR, DEBUG, true, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
@@ -806,6 +811,7 @@ __device__ __forceinline__ void surface_role(const SurfParams& P, WarpStageSurf&
                     if (S.damp) wet_chunk<WAVES, CUR, DEBUG, false, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
                     else        wet_chunk<WAVES, CUR, DEBUG, false, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
                 }
+#endif
             } else {
                 clip_chunk<WAVES, CUR, DEBUG>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, cpack, body, orig, lane, f0, f1);
             }
