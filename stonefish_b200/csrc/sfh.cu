@@ -435,7 +435,9 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     // when the two roles are launched one by one to be timed (SFH_PROFILE_ROLES, tools/ablate_surface.py).
     const bool time_roles = prof && ctx->profile_roles;
     const char* no_direct = getenv("SFH_NO_DIRECT"); // tests: small scenes through the LIST path too
-    const uint32_t direct_streams = (time_roles || (no_direct && no_direct[0] == '1')) ? 0u : (uint32_t)((g_wet + g_clip) * SFH_SUB_WPB);
+    // T = the warps that are RESIDENT at once (the grid is twice that: wet blocks, then clip blocks): with more sub-items than that a
+    // second wave of blocks would pay the per-warp start-up (classification, descriptor and chunk round trips) a second time
+    const uint32_t direct_streams = (time_roles || (no_direct && no_direct[0] == '1')) ? 0u : (uint32_t)((g_wet > g_clip ? g_wet : g_clip) * SFH_SUB_WPB);
     cp.direct_streams = direct_streams;
     // with host-side states the host knows when the step is certain to run in direct mode: k_classify is not even launched
     const bool surely_direct = direct_streams && plan.surf_ub && plan.surf_ub <= direct_streams;

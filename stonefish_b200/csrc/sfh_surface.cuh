@@ -848,6 +848,9 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStageSur
     warp_load_body(&s_body, P.bodies + body, lane);
     const float4* rec = reinterpret_cast<const float4*>(s_body.bounds + c);
     const float4 b0 = __ldg(rec), b1 = __ldg(rec + 1);
+    // the chunk is fetched while it is being classified (a dry chunk's copy is wasted: direct mode is bound by latency, not traffic)
+    const PipeAddr pa = warp_pipe_init(St.pipe, lane);
+    if (lane == 0) pipe_issue(pa, 0, s_body.chunks + (size_t)__float_as_uint(b1.z) * 16u, __float_as_uint(b1.w));
     float hmax0 = 0.f, hmax1 = 0.f;
     if (WAVES) { hmax0 = __uint_as_float(__ldg(P.waves.hmax)); hmax1 = __uint_as_float(__ldg(P.waves.hmax + 1)); }
     const uint32_t kind = classify_chunk(s_body.R, s_body.t, b0, make_float2(b1.x, b1.y), WAVES, P.waves, hmax0, hmax1);
@@ -857,9 +860,8 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStageSur
     for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = 0.0;
     uint32_t epack = 0, cls7 = 0;
     uint64_t cpack = 0;
+    if (kind == CK_DRY) pipe_wait(pa, 0, 0u); // no warp leaves with a copy into its shared memory in flight
     if (kind != CK_DRY) {
-        const PipeAddr pa = warp_pipe_init(St.pipe, lane);
-        if (lane == 0) pipe_issue(pa, 0, s_body.chunks + (size_t)__float_as_uint(b1.z) * 16u, __float_as_uint(b1.w));
         const WaveConst wc = WAVES ? wave_const(P.waves) : WaveConst{};
         SurfBody S;
         surf_fetch_body(s_body, S);
