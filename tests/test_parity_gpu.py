@@ -455,3 +455,46 @@ def test_device_step_hints(ctx, oracle):
         run(_abi.SFH_HINT_NO_SUBMERGED)                          # every body IS submerged
     again = run(_abi.SFH_HINT_NO_SURFACE)                        # the context is usable afterwards
     assert again.tobytes() == plain.tobytes()
+
+
+@pytest.mark.parametrize("amplitude", [1.0, 0.05, 20.0])
+def test_chunk_classifier_is_conservative(ctx, oracle, surface_mode, amplitude):
+    """The surface path drops chunks it proves dry and skips the clipping code for chunks it proves wet, from the chunk's box and a LOCAL
+    bound of the wave lookup. A wrong proof changes per-face classes, which must stay bit-exact. Poses that stress the bound: on and next
+    to the period boundaries of both wave grids (893 m, 101 m: the reference's index quirk at i0f == 1.0f, OpenGLRealOcean.cpp:291-296,
+    negative coordinates), far from the origin (fp32 spacing of the coordinates grows), any orientation, CG within a few centimetres of
+    the surface; wave fields 20x smaller and 20x larger than the hull."""
+    from stonefish_b200 import meshes as M
+    from stonefish_b200._abi import SFH_POS_CROSSING
+    from stonefish_b200.hydro import Ocean, Uniform, make_transform, new_body_states, quat_to_basis, transform_mul
+    from stonefish_b200.scenes import CG2C, RAW, Scene, _fill_body, random_unit_quats, wave_field
+
+    mesh = M.uv_ellipsoid(1.5, 0.4, 0.3, 48, 25)      # 2304 faces: nine chunks with boxes of decimetres
+    ocean = Ocean(1000.0, 9.81)
+    f = wave_field()
+    f[0, :, :, :2] *= amplitude
+    ocean.setWaves(f)
+    ocean.AddVelocityField(Uniform((0.2, -0.1, 0.05)))
+    ocean.EnableCurrents()
+    gx, gy = 893.0, 101.0
+    spots = [(0.0, 0.0), (gx, 0.0), (0.0, gy), (-gx, -gy), (gx * 3, gy * 7), (0.3, -0.2), (-0.2, 0.4), (gy + 0.1, gy - 0.1), (-gy * 2 + 0.05, 0.0),
+             (gx - 0.2, -gx + 0.2), (gx / 256 * 0.5, gy / 256 * 0.5), (-gx / 256 * 0.5, -gy / 256 * 1.5), (1.0e4, -7.3e3), (-2.5e4 + 0.7, 3.1e4),
+             (123.456, -654.321), (50.5, 50.5)]
+    n = 3 * len(spots)
+    st = new_body_states(n)
+    quats = random_unit_quats(91, n)
+    u = M.splitmix_uniform(92, n)
+    for k in range(n):
+        x, y = spots[k % len(spots)]
+        tilt = quats[k] if k >= len(spots) else scenes.euler_zyx_quat(0.7 * k, 0.03, -0.05)
+        z = (-0.25 + 0.5 * u[k]) * (1.0 if amplitude < 5 else 8.0)
+        T_CG = make_transform(quat_to_basis(tilt), (x, y, z))
+        _fill_body(st, k, mesh, T_CG, transform_mul(T_CG, CG2C), (0.5, 0.1, -0.2), (0.05, -0.02, 0.1), SFH_POS_CROSSING, RAW)
+    sc = Scene("classifier_stress", [mesh], np.zeros(n, dtype=np.int64), ocean, st)
+    gi, gc, ri, rc = run_both(ctx, oracle, sc)
+    assert np.array_equal(gc, rc)
+    assert_counts_equal(gi, ri)
+    err, where = max_rel_err(gi, ri)
+    assert err <= REL_TOL, (err, where)
+    cls = gi["class_count"].sum(axis=0)
+    assert cls[0] > 0 and cls[7] > 0 and cls[1:7].sum() > 0     # dry, wet and cut faces all occur
