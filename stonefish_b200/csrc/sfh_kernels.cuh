@@ -65,6 +65,44 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Sums of N per-lane values over the warp, stored to out[0..N) and the per-lane values cleared. The values are FOLDED: at
+// every level a lane keeps one half of its values and sends the other half to its partner at xor distance 16, 8, 4, 2, 1 —
+// 2N double shuffles (N, N/2, ... per level) instead of 5N, and the 40 stores spread over the lanes. The pairing is the tree of
+// warp_sum ((l, l^16), then (l, l^8) ... on the partial sums; fp64 addition commutes), so every sum has the bits warp_sum gives.
+template <int N, int H>
+__device__ __forceinline__ void warp_fold(double* a, uint32_t lane, uint32_t bit)
+{
+    const bool upper = (lane & bit) != 0u;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        const double lo = a[k], hi = (k + H < N) ? a[k + H] : 0.0;
+        const double send = upper ? lo : hi, keep = upper ? hi : lo;
+        a[k] = dadd(keep, __shfl_xor_sync(SFH_FULL, send, bit));
+    }
+}
+template <int N>
+__device__ __forceinline__ void warp_sum_store(double* acc, double* out, uint32_t lane)
+{
+    constexpr int H1 = (N + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2, H4 = (H3 + 1) / 2, H5 = (H4 + 1) / 2;
+    warp_fold<N, H1>(acc, lane, 16u);
+    warp_fold<H1, H2>(acc, lane, 8u);
+    warp_fold<H2, H3>(acc, lane, 4u);
+    warp_fold<H3, H4>(acc, lane, 2u);
+    warp_fold<H4, H5>(acc, lane, 1u);
+#pragma unroll
+    for (int k = 0; k < H5; ++k) { // value k of this lane is the sum of which index? (an index past a level's size was padding)
+        uint32_t i = (uint32_t)k + ((lane & 1u) ? (uint32_t)H5 : 0u);
+        bool ok = i < (uint32_t)H4;
+        i += (lane & 2u) ? (uint32_t)H4 : 0u;  ok = ok && i < (uint32_t)H3;
+        i += (lane & 4u) ? (uint32_t)H3 : 0u;  ok = ok && i < (uint32_t)H2;
+        i += (lane & 8u) ? (uint32_t)H2 : 0u;  ok = ok && i < (uint32_t)H1;
+        i += (lane & 16u) ? (uint32_t)H1 : 0u; ok = ok && i < (uint32_t)N;
+        if (ok) out[i] = acc[k];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.0;
+}
+
 struct BodyRegs { // hot per-body constants
     F3 p, v, omega, cur;
 };

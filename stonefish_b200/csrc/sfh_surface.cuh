@@ -240,6 +240,9 @@ __device__ __forceinline__ void classify_tiles(const ClassifyParams& P, uint32_t
             const float4* rec = reinterpret_cast<const float4*>(bd.bounds + c);
             const float4 b0 = __ldg(rec), b1 = __ldg(rec + 1);
             kind = classify_chunk(bd.R, bd.t, b0, make_float2(b1.x, b1.y), waves, P.waves, hmax0, hmax1);
+            // the pair code of the wet role is compiled for the usual settings (buoyancy and damping, as Ocean::ApplyFluidForces sets
+            // them); the wet chunks of a body without one of them (a non-buoyant part, an internal part of a compound) take the general code
+            if (kind == CK_WET && (bd.flags & (BF_BUOYANCY | BF_DAMPING)) != (BF_BUOYANCY | BF_DAMPING)) kind = CK_CLIP;
             const unsigned long long addr = (unsigned long long)(bd.chunks + (size_t)__float_as_uint(b1.z) * 16u);
             desc = make_uint4((uint32_t)addr, (uint32_t)(addr >> 32), b, c | ((__float_as_uint(b1.w) >> 4) << 23));
         }
@@ -721,12 +724,7 @@ __device__ __forceinline__ void surface_role(const SurfParams& P, WarpStageSurf&
     auto flush = [&](uint32_t seg, uint32_t body) { // one partial record per (segment, body)
         spill();
         PartialSurf* rec = partials + (seg + body);
-#pragma unroll
-        for (int i = 0; i < SFH_NACC_SURF; ++i) {
-            const double v = warp_sum(acc[i]);
-            if (lane == 0) rec->a[i] = v;
-            acc[i] = 0.0;
-        }
+        warp_sum_store<SFH_NACC_SURF>(acc, rec->a, lane);
         if (lane == 0) {
             rec->n_degenerate = cnt[0]; rec->n_quadratic = cnt[1]; rec->n_skin = cnt[2];
 #pragma unroll
@@ -804,23 +802,18 @@ __device__ __forceinline__ void surface_role(const SurfParams& P, WarpStageSurf&
 #elif defined(SFH_WET_ONLY_BUOY)
                 wet_chunk<WAVES, CUR, DEBUG, true, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
 #else
-                if (S.buoy) {
-                    if (S.damp) wet_chunk<WAVES, CUR, DEBUG, true, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
-                    else        wet_chunk<WAVES, CUR, DEBUG, true, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
-                } else {
-                    if (S.damp) wet_chunk<WAVES, CUR, DEBUG, false, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
-                    else        wet_chunk<WAVES, CUR, DEBUG, false, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
-                }
+                wet_chunk<WAVES, CUR, DEBUG, true, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1); // k_classify only lists such bodies as wet
 #endif
             } else {
                 clip_chunk<WAVES, CUR, DEBUG>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, cpack, body, orig, lane, f0, f1);
             }
             if (++since_spill == SFH_LIST_SPILL_EVERY) spill(); // <= 8 faces per lane per sub-item: 10-bit / 8-bit fields stay in range
 
-            if (++R >= R1) break;
+            const bool last = ++R >= R1;
+            if (last || d_next.z != body) flush(seg, body); // the one flush site of the role
+            if (last) break;
             s ^= 1;
             if (d_next.z != body) {
-                flush(seg, body);
                 body = d_next.z;
                 __syncwarp();
                 warp_load_body(&s_body, P.bodies + body, lane);
@@ -830,7 +823,6 @@ __device__ __forceinline__ void surface_role(const SurfParams& P, WarpStageSurf&
             d_next = d_after; q_next = q_after;
         }
         s ^= 1; // the next segment's first copy goes to the other staging buffer
-        flush(seg, body);
     }
 }
 
@@ -853,7 +845,8 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStageSur
     if (lane == 0) pipe_issue(pa, 0, s_body.chunks + (size_t)__float_as_uint(b1.z) * 16u, __float_as_uint(b1.w));
     float hmax0 = 0.f, hmax1 = 0.f;
     if (WAVES) { hmax0 = __uint_as_float(__ldg(P.waves.hmax)); hmax1 = __uint_as_float(__ldg(P.waves.hmax + 1)); }
-    const uint32_t kind = classify_chunk(s_body.R, s_body.t, b0, make_float2(b1.x, b1.y), WAVES, P.waves, hmax0, hmax1);
+    uint32_t kind = classify_chunk(s_body.R, s_body.t, b0, make_float2(b1.x, b1.y), WAVES, P.waves, hmax0, hmax1);
+    if (kind == CK_WET && (s_body.flags & (BF_BUOYANCY | BF_DAMPING)) != (BF_BUOYANCY | BF_DAMPING)) kind = CK_CLIP; // as k_classify
 
     double acc[SFH_NACC_SURF];
 #pragma unroll
@@ -878,13 +871,7 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStageSur
             }
             __syncwarp();
             cls7 = f1 > f0 ? f1 - f0 : 0u;
-            if (S.buoy) {
-                if (S.damp) wet_chunk<WAVES, CUR, DEBUG, true, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
-                else        wet_chunk<WAVES, CUR, DEBUG, true, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
-            } else {
-                if (S.damp) wet_chunk<WAVES, CUR, DEBUG, false, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
-                else        wet_chunk<WAVES, CUR, DEBUG, false, false>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
-            }
+            wet_chunk<WAVES, CUR, DEBUG, true, true>(P, cv, s_v, S, s_cur, cur_may, n_cur, wc, acc, epack, body, orig, lane, f0, f1);
         } else {
             if (split == 1u) clip_vertices<WAVES>(P.waves, wc, s_body, cv, s_v, lane);
             else clip_vertices_of<WAVES>(P.waves, wc, s_body, cv, s_v, lane, f0, f1, St.need);
@@ -893,11 +880,7 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStageSur
         }
     }
     PartialSurf* out = P.part_wet + (u + body);
-#pragma unroll
-    for (int i = 0; i < SFH_NACC_SURF; ++i) {
-        const double v = warp_sum(acc[i]);
-        if (lane == 0) out->a[i] = v;
-    }
+    warp_sum_store<SFH_NACC_SURF>(acc, out->a, lane);
     uint32_t cnt[3], cl[8];
 #pragma unroll
     for (int k = 0; k < 3; ++k) cnt[k] = __reduce_add_sync(SFH_FULL, (epack >> (10 * k)) & 1023u);
