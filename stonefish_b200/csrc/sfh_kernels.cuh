@@ -492,18 +492,23 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
             add_records(P.part_clip, rank(P.L.clip_off, o0, 16) * cs, rank(P.L.clip_off, o1, 16) * cs, P.L.ctrl[SC_CLIP_SEG]);
         }
     }
-    const uint32_t lane = t & 31u;
+    // warp sums into shared memory (folded: sfh_kernels.cuh warp_sum_store), read back by the thread that goes on
+    const uint32_t lane = t & 31u, wp = threadIdx.x >> 5;
     if (kind != KIND_NONE) {
-#pragma unroll
-        for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = warp_sum(acc[i]);
+        warp_sum_store<SFH_NACC_SURF>(acc, s_red[wp], lane);
 #pragma unroll
         for (int i = 0; i < 11; ++i) cnt[i] = __reduce_add_sync(SFH_FULL, cnt[i]);
+    } else {
+        if (lane < (uint32_t)SFH_NACC_SURF) s_red[wp][lane] = 0.0;
     }
-    if (team == 128u) { // the four warps' sums, added in warp order
-        const uint32_t wp = t >> 5;
+    if (team == 32u) {
+        __syncwarp();
         if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < SFH_NACC_SURF; ++i) s_red[wp][i] = acc[i];
+            for (int i = 0; i < SFH_NACC_SURF; ++i) acc[i] = s_red[wp][i];
+        }
+    } else { // the four warps' sums, added in warp order
+        if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < 11; ++i) s_cnt[wp][i] = cnt[i];
         }
@@ -516,6 +521,8 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
         }
         if (S > 1u) { // second stage: slice totals, added in slice order by the block that finishes last
             __shared__ uint32_t s_last;
+            __shared__ double s_slice[16][SFH_NACC_SURF];
+            __shared__ uint32_t s_slice_cnt[16][11];
             PartialSurf* mine = P.slice_part + (size_t)b * S;
             if (t == 0) {
                 PartialSurf& o = mine[sl];
@@ -530,14 +537,24 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
             __syncthreads();
             if (!s_last) return;
             __threadfence();
+            // every slice total fetched at once (independent loads over the 128 threads), then added in slice order
+            for (uint32_t i = t; i < S * (uint32_t)SFH_NACC_SURF; i += 128u) {
+                const uint32_t k = i / (uint32_t)SFH_NACC_SURF, j = i % (uint32_t)SFH_NACC_SURF;
+                s_slice[k][j] = __ldcg(&mine[k].a[j]);
+            }
+            for (uint32_t i = t; i < S * 11u; i += 128u) {
+                const uint32_t k = i / 11u, f = i % 11u;
+                s_slice_cnt[k][f] = f < 3u ? __ldcg(&mine[k].n_degenerate + f) : __ldcg(&mine[k].cls[f - 3u]);
+            }
+            __syncthreads();
             if (t < (uint32_t)SFH_NACC_SURF) {
                 double v = 0.0;
-                for (uint32_t k = 0; k < S; ++k) v = dadd(v, __ldcg(&mine[k].a[t]));
+                for (uint32_t k = 0; k < S; ++k) v = dadd(v, s_slice[k][t]);
                 s_red[0][t] = v;
             } else if (t >= 32u && t < 43u) {
                 const uint32_t f = t - 32u;
                 uint32_t c = 0;
-                for (uint32_t k = 0; k < S; ++k) c += f < 3u ? __ldcg(&mine[k].n_degenerate + f) : __ldcg(&mine[k].cls[f - 3u]);
+                for (uint32_t k = 0; k < S; ++k) c += s_slice_cnt[k][f];
                 s_cnt[0][f] = c;
             }
             __syncthreads();
