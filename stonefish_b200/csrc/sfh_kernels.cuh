@@ -411,6 +411,82 @@ __device__ inline void correct_aero(double* Fda, double* Tda, const double* Cd, 
     for (int k = 0; k < 3; ++k) { Fda[k] = dmul(Fda[k], cor); Tda[k] = dmul(Tda[k], cor); }
 }
 
+// The per-body tail of the reference (SolidEntity.cpp:1689-1720, 1793-1850, 1920-1956) on the fp64 sums: one thread per body
+__device__ __forceinline__ void epilogue_finish(const EpilogueParams& P, uint32_t b, const BodyDev& bd, uint32_t kind, uint32_t pos,
+                                                const double* acc, const uint32_t* cnt, sfh_info& o)
+{
+    const sfh_body_state& st = P.states[b];
+    const OceanDev& oc = *P.ocean;
+    const bool dispatch = (st.flags & SFH_F_DISPATCH) != 0;
+    for (int k = 0; k < 3; ++k) { o.Fb[k] = 0; o.Tb[k] = 0; o.Fdq[k] = 0; o.Tdq[k] = 0; o.Fdf[k] = 0; o.Tdf[k] = 0; }
+    o.Swet = 0; o.Vsub = 0; o.wrote_buoyancy = 0; o.wrote_damping = 0; o.position = pos; o.reserved = 0;
+    o.n_faces = (kind != KIND_NONE) ? bd.n_faces : 0u;
+    o.n_degenerate = cnt[0]; o.n_quadratic = cnt[1]; o.n_skin = cnt[2];
+    for (int k = 0; k < 8; ++k) o.class_count[k] = cnt[3 + k];
+    if (kind == KIND_SURFACE) { // every face is in exactly one class; class 0 (all three vertices dry) is the one nobody counts
+        uint32_t others = 0;
+        for (int k = 1; k < 8; ++k) others += cnt[3 + k];
+        o.class_count[0] = bd.n_faces - others;
+    }
+
+    if (P.aero) { // SolidEntity.cpp:1920-1922, then CorrectAerodynamicForces
+        const double k = dmul(0.5, oc.density);
+        for (int c = 0; c < 3; ++c) { o.Fdq[c] = dmul(acc[c], k); o.Tdq[c] = dmul(acc[3 + c], k); }
+        o.wrote_damping = 1;
+        o.class_count[7] = o.n_faces;
+        if (dispatch) correct_aero(o.Fdq, o.Tdq, st.Cd, st.T_O_basis, (st.flags & SFH_F_AERO_CD) != 0);
+        return;
+    }
+    if (pos == SFH_POS_OUTSIDE) { // SolidEntity.cpp:1810-1821
+        o.wrote_buoyancy = 1; o.wrote_damping = 1;
+    } else if (pos == SFH_POS_INSIDE) {
+        if (kind == KIND_SUBMERGED) { // SolidEntity.cpp:1793-1796
+            for (int k = 0; k < 3; ++k) { o.Fdq[k] = acc[k]; o.Tdq[k] = acc[3 + k]; o.Fdf[k] = acc[6 + k]; o.Tdf[k] = acc[9 + k]; }
+            o.wrote_damping = 1;
+            o.class_count[7] = o.n_faces;
+        }
+        if (dispatch) { // SolidEntity.cpp:1828-1841
+            if (st.flags & SFH_F_BUOYANT) {
+                const double s = dmul(-st.volume, oc.density);
+                const D3 Fb = {dmul(0.0, s), dmul(0.0, s), dmul(oc.gravity_z, s)};
+                const double* T = st.T_CG;
+                const D3 pcb = {st.P_CB[0], st.P_CB[1], st.P_CB[2]}, org = {T[9], T[10], T[11]};
+                const D3 wcb = {dadd(ddot(D3{T[0], T[1], T[2]}, pcb), org.x), dadd(ddot(D3{T[3], T[4], T[5]}, pcb), org.y),
+                                dadd(ddot(D3{T[6], T[7], T[8]}, pcb), org.z)};
+                const D3 Tb = dcross(wcb - org, Fb);
+                o.Fb[0] = Fb.x; o.Fb[1] = Fb.y; o.Fb[2] = Fb.z; o.Tb[0] = Tb.x; o.Tb[1] = Tb.y; o.Tb[2] = Tb.z;
+                o.wrote_buoyancy = 1;
+            }
+            o.Swet = st.surface;
+        }
+    } else { // CROSSING: SolidEntity.cpp:1689-1720 on the fp64 sums (F64_ACC contract, DESIGN.md)
+        const bool buoy = (bd.flags & BF_BUOYANCY) != 0, damp = (bd.flags & BF_DAMPING) != 0;
+        const double Vsub = acc[19];
+        if (buoy && Vsub > (double)1e-9f) {
+            o.wrote_buoyancy = 1;
+            o.Vsub = ddiv(Vsub, (double)6.f);
+            if (oc.has_waves) {
+                const double kk = (double)(float)dmul(oc.density, oc.gravity_z);
+                for (int k = 0; k < 3; ++k) { o.Fb[k] = dmul(acc[12 + k], kk); o.Tb[k] = dmul(acc[15 + k], kk); }
+            } else {
+                const D3 cb = {dadd(ddiv(acc[20], Vsub), (double)bd.p[0]), dadd(ddiv(acc[21], Vsub), (double)bd.p[1]),
+                               dadd(ddiv(acc[22], Vsub), (double)0.f)};
+                const double s = dmul(-o.Vsub, oc.density);
+                const D3 Fb = {dmul(0.0, s), dmul(0.0, s), dmul(oc.gravity_z, s)};
+                const D3 Tb = dcross(cb - D3{st.T_CG[9], st.T_CG[10], st.T_CG[11]}, Fb);
+                o.Fb[0] = Fb.x; o.Fb[1] = Fb.y; o.Fb[2] = Fb.z; o.Tb[0] = Tb.x; o.Tb[1] = Tb.y; o.Tb[2] = Tb.z;
+            }
+        }
+        if (damp) {
+            o.wrote_damping = 1;
+            for (int k = 0; k < 3; ++k) { o.Fdq[k] = acc[k]; o.Tdq[k] = acc[3 + k]; o.Fdf[k] = acc[6 + k]; o.Tdf[k] = acc[9 + k]; }
+        }
+        o.Swet = acc[18];
+    }
+    if (dispatch && pos != SFH_POS_OUTSIDE && (st.flags & SFH_F_DAMPING)) // SolidEntity.cpp:1848-1849
+        correct_forces(oc.density, o.Fdq, o.Tdq, o.Fdf, o.Tdf, st.Cd, st.Cf, st.T_O_basis);
+}
+
 __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t b, uint32_t t, uint32_t team, double (*s_red)[SFH_NACC_SURF],
                                               uint32_t (*s_cnt)[11]);
 
@@ -567,81 +643,15 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
             }
         }
     }
-    if (t != 0) return;
-
-    const sfh_body_state& st = P.states[b];
-    const OceanDev& oc = *P.ocean;
-    const bool dispatch = (st.flags & SFH_F_DISPATCH) != 0;
-    sfh_info o;
-    for (int k = 0; k < 3; ++k) { o.Fb[k] = 0; o.Tb[k] = 0; o.Fdq[k] = 0; o.Tdq[k] = 0; o.Fdf[k] = 0; o.Tdf[k] = 0; }
-    o.Swet = 0; o.Vsub = 0; o.wrote_buoyancy = 0; o.wrote_damping = 0; o.position = pos; o.reserved = 0;
-    o.n_faces = (kind != KIND_NONE) ? bd.n_faces : 0u;
-    o.n_degenerate = cnt[0]; o.n_quadratic = cnt[1]; o.n_skin = cnt[2];
-    for (int k = 0; k < 8; ++k) o.class_count[k] = cnt[3 + k];
-    if (kind == KIND_SURFACE) { // every face is in exactly one class; class 0 (all three vertices dry) is the one nobody counts
-        uint32_t others = 0;
-        for (int k = 1; k < 8; ++k) others += cnt[3 + k];
-        o.class_count[0] = bd.n_faces - others;
-    }
-
-    if (P.aero) { // SolidEntity.cpp:1920-1922, then CorrectAerodynamicForces
-        const double k = dmul(0.5, oc.density);
-        for (int c = 0; c < 3; ++c) { o.Fdq[c] = dmul(acc[c], k); o.Tdq[c] = dmul(acc[3 + c], k); }
-        o.wrote_damping = 1;
-        o.class_count[7] = o.n_faces;
-        if (dispatch) correct_aero(o.Fdq, o.Tdq, st.Cd, st.T_O_basis, (st.flags & SFH_F_AERO_CD) != 0);
-        P.out[b] = o;
-        return;
-    }
-    if (pos == SFH_POS_OUTSIDE) { // SolidEntity.cpp:1810-1821
-        o.wrote_buoyancy = 1; o.wrote_damping = 1;
-    } else if (pos == SFH_POS_INSIDE) {
-        if (kind == KIND_SUBMERGED) { // SolidEntity.cpp:1793-1796
-            for (int k = 0; k < 3; ++k) { o.Fdq[k] = acc[k]; o.Tdq[k] = acc[3 + k]; o.Fdf[k] = acc[6 + k]; o.Tdf[k] = acc[9 + k]; }
-            o.wrote_damping = 1;
-            o.class_count[7] = o.n_faces;
-        }
-        if (dispatch) { // SolidEntity.cpp:1828-1841
-            if (st.flags & SFH_F_BUOYANT) {
-                const double s = dmul(-st.volume, oc.density);
-                const D3 Fb = {dmul(0.0, s), dmul(0.0, s), dmul(oc.gravity_z, s)};
-                const double* T = st.T_CG;
-                const D3 pcb = {st.P_CB[0], st.P_CB[1], st.P_CB[2]}, org = {T[9], T[10], T[11]};
-                const D3 wcb = {dadd(ddot(D3{T[0], T[1], T[2]}, pcb), org.x), dadd(ddot(D3{T[3], T[4], T[5]}, pcb), org.y),
-                                dadd(ddot(D3{T[6], T[7], T[8]}, pcb), org.z)};
-                const D3 Tb = dcross(wcb - org, Fb);
-                o.Fb[0] = Fb.x; o.Fb[1] = Fb.y; o.Fb[2] = Fb.z; o.Tb[0] = Tb.x; o.Tb[1] = Tb.y; o.Tb[2] = Tb.z;
-                o.wrote_buoyancy = 1;
-            }
-            o.Swet = st.surface;
-        }
-    } else { // CROSSING: SolidEntity.cpp:1689-1720 on the fp64 sums (F64_ACC contract, DESIGN.md)
-        const bool buoy = (bd.flags & BF_BUOYANCY) != 0, damp = (bd.flags & BF_DAMPING) != 0;
-        const double Vsub = acc[19];
-        if (buoy && Vsub > (double)1e-9f) {
-            o.wrote_buoyancy = 1;
-            o.Vsub = ddiv(Vsub, (double)6.f);
-            if (oc.has_waves) {
-                const double kk = (double)(float)dmul(oc.density, oc.gravity_z);
-                for (int k = 0; k < 3; ++k) { o.Fb[k] = dmul(acc[12 + k], kk); o.Tb[k] = dmul(acc[15 + k], kk); }
-            } else {
-                const D3 cb = {dadd(ddiv(acc[20], Vsub), (double)bd.p[0]), dadd(ddiv(acc[21], Vsub), (double)bd.p[1]),
-                               dadd(ddiv(acc[22], Vsub), (double)0.f)};
-                const double s = dmul(-o.Vsub, oc.density);
-                const D3 Fb = {dmul(0.0, s), dmul(0.0, s), dmul(oc.gravity_z, s)};
-                const D3 Tb = dcross(cb - D3{st.T_CG[9], st.T_CG[10], st.T_CG[11]}, Fb);
-                o.Fb[0] = Fb.x; o.Fb[1] = Fb.y; o.Fb[2] = Fb.z; o.Tb[0] = Tb.x; o.Tb[1] = Tb.y; o.Tb[2] = Tb.z;
-            }
-        }
-        if (damp) {
-            o.wrote_damping = 1;
-            for (int k = 0; k < 3; ++k) { o.Fdq[k] = acc[k]; o.Tdq[k] = acc[3 + k]; o.Fdf[k] = acc[6 + k]; o.Tdf[k] = acc[9 + k]; }
-        }
-        o.Swet = acc[18];
-    }
-    if (dispatch && pos != SFH_POS_OUTSIDE && (st.flags & SFH_F_DAMPING)) // SolidEntity.cpp:1848-1849
-        correct_forces(oc.density, o.Fdq, o.Tdq, o.Fdf, o.Tdf, st.Cd, st.Cf, st.T_O_basis);
-    P.out[b] = o;
+    if (t >= 32u) return;
+    // lane 0 of the body's first warp finishes the record in shared memory; the warp then writes it as fourteen 16-byte stores
+    // (one or two transactions — over PCIe when the record goes straight into the pinned result buffer)
+    static_assert(sizeof(sfh_info) % 16 == 0 && sizeof(sfh_info) / 16 <= 32, "record copy by one warp");
+    __shared__ __align__(16) sfh_info s_out[4];
+    if (lane == 0) epilogue_finish(P, b, bd, kind, pos, acc, cnt, s_out[wp]);
+    __syncwarp();
+    if (lane < (uint32_t)(sizeof(sfh_info) / 16))
+        reinterpret_cast<uint4*>(P.out + b)[lane] = reinterpret_cast<const uint4*>(&s_out[wp])[lane];
 }
 
 // point queries: Ocean::GetDepth(glm::vec3) / Ocean::GetFluidVelocity(glm::vec3) for n points
