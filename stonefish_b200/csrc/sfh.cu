@@ -145,6 +145,9 @@ struct sfh_ctx {
     bool profile_roles = false; // SFH_PROFILE_ROLES=1: while profiling, time the wet and the clip role in launches of their own
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [6], [7]: after k_classify, after the wet role of k_surface_lists
     bool ev_sub = false, ev_surf = false, ev_valid = false;
+    // small mixed steps: k_submerged runs beside the surface path on a stream of its own (fork / join by events)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t last_launches = 0;
     uint64_t last_faces = 0;
 };
@@ -462,17 +465,30 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     sp.codes = plan.debug ? ctx->d_codes.p : nullptr; sp.code_base = plan.debug ? ctx->d_code_base.p : nullptr;
 
     ctx->ev_sub = ctx->ev_surf = false;
+    // A small step that has both kinds of bodies (the FluidDynamicsTest scene): neither face kernel fills the machine and both are
+    // bound by latency, so k_submerged goes to a side stream and runs beside the surface path (two branches of the step's graph).
+    // Small = the surface path is certain to take direct mode and the submerged chunks do not outnumber the resident warps either.
+    const char* no_fork = getenv("SFH_NO_FORK"); // A/B measurements
+    const bool fork = !(no_fork && no_fork[0] == '1') && !prof && plan.may_sub && g_sub > 0 && surf && g_wet > 0 && g_clip > 0 && surely_direct && plan.chunks_ub &&
+                      plan.chunks_ub <= (uint64_t)direct_streams;
+    cudaStream_t sub_stream = ctx->stream;
+    if (fork) {
+        CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        sub_stream = ctx->side_stream;
+    }
     if (plan.may_sub && g_sub > 0) {
         sp.item_off = ctx->d_off_sub.p; sp.partials = ctx->d_part_sub.p;
         if (plan.aero) {
-            if (plan.debug) { if (general) launch_sub<1, true, true>(sp, (int)g_sub, ctx->stream); else launch_sub<0, true, true>(sp, (int)g_sub, ctx->stream); }
-            else            { if (general) launch_sub<1, false, true>(sp, (int)g_sub, ctx->stream); else launch_sub<0, false, true>(sp, (int)g_sub, ctx->stream); }
+            if (plan.debug) { if (general) launch_sub<1, true, true>(sp, (int)g_sub, sub_stream); else launch_sub<0, true, true>(sp, (int)g_sub, sub_stream); }
+            else            { if (general) launch_sub<1, false, true>(sp, (int)g_sub, sub_stream); else launch_sub<0, false, true>(sp, (int)g_sub, sub_stream); }
         } else {
-            if (plan.debug) { if (general) launch_sub<1, true>(sp, (int)g_sub, ctx->stream); else launch_sub<0, true>(sp, (int)g_sub, ctx->stream); }
-            else            { if (general) launch_sub<1, false>(sp, (int)g_sub, ctx->stream); else launch_sub<0, false>(sp, (int)g_sub, ctx->stream); }
+            if (plan.debug) { if (general) launch_sub<1, true>(sp, (int)g_sub, sub_stream); else launch_sub<0, true>(sp, (int)g_sub, sub_stream); }
+            else            { if (general) launch_sub<1, false>(sp, (int)g_sub, sub_stream); else launch_sub<0, false>(sp, (int)g_sub, sub_stream); }
         }
         ++launches;
         ctx->ev_sub = true;
+        if (fork) CU(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
     }
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
 
@@ -501,6 +517,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
         }
         ctx->ev_surf = true;
     }
+    if (fork) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
 
     EpilogueParams ep;
@@ -752,6 +769,9 @@ int sfh_create_on_stream(int cuda_device, void* cuda_stream, sfh_ctx** out)
     }
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     *out = ctx;
     return SFH_OK;
 }
@@ -778,6 +798,9 @@ void sfh_destroy(sfh_ctx* ctx)
         if (b->p) cudaFreeHost(b->p);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
