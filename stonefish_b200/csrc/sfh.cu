@@ -340,18 +340,31 @@ struct StepPlan {
     uint64_t faces = 0;
 };
 
+// A kernel launch that may overlap the tail of its predecessor in the stream (programmatic dependent launch, see pdl_wait() in
+// sfh_device.cuh); pdl = false: an ordinary launch.
+template <typename P>
+void launch_k(void (*kernel)(P), unsigned grid, unsigned block, cudaStream_t s, bool pdl, const P& params)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(block, 1, 1); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, params); // errors are picked up by cudaGetLastError at the end of run_step
+}
 template <int CUR, bool DEBUG, bool AERO = false>
-void launch_sub(const StepParams& P, int grid, cudaStream_t s) { k_submerged<CUR, DEBUG, AERO><<<grid, SFH_SUB_THREADS, 0, s>>>(P); }
+void launch_sub(const StepParams& P, int grid, cudaStream_t s, bool pdl) { launch_k(k_submerged<CUR, DEBUG, AERO>, (unsigned)grid, SFH_SUB_THREADS, s, pdl, P); }
 template <bool WAVES, int CUR, bool DEBUG>
-void launch_lists(const SurfParams& P, int grid, cudaStream_t s) { k_surface_lists<WAVES, CUR, DEBUG><<<grid, SFH_SUB_THREADS, 0, s>>>(P); }
-void launch_lists_variant(const SurfParams& P, int grid, cudaStream_t s, bool waves, bool general, bool debug)
+void launch_lists(const SurfParams& P, int grid, cudaStream_t s, bool pdl) { launch_k(k_surface_lists<WAVES, CUR, DEBUG>, (unsigned)grid, SFH_SUB_THREADS, s, pdl, P); }
+void launch_lists_variant(const SurfParams& P, int grid, cudaStream_t s, bool waves, bool general, bool debug, bool pdl)
 {
     if (debug) {
-        if (waves) { if (general) launch_lists<true, 1, true>(P, grid, s); else launch_lists<true, 0, true>(P, grid, s); }
-        else       { if (general) launch_lists<false, 1, true>(P, grid, s); else launch_lists<false, 0, true>(P, grid, s); }
+        if (waves) { if (general) launch_lists<true, 1, true>(P, grid, s, pdl); else launch_lists<true, 0, true>(P, grid, s, pdl); }
+        else       { if (general) launch_lists<false, 1, true>(P, grid, s, pdl); else launch_lists<false, 0, true>(P, grid, s, pdl); }
     } else {
-        if (waves) { if (general) launch_lists<true, 1, false>(P, grid, s); else launch_lists<true, 0, false>(P, grid, s); }
-        else       { if (general) launch_lists<false, 1, false>(P, grid, s); else launch_lists<false, 0, false>(P, grid, s); }
+        if (waves) { if (general) launch_lists<true, 1, false>(P, grid, s, pdl); else launch_lists<true, 0, false>(P, grid, s, pdl); }
+        else       { if (general) launch_lists<false, 1, false>(P, grid, s, pdl); else launch_lists<false, 0, false>(P, grid, s, pdl); }
     }
 }
 
@@ -468,7 +481,11 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     // A small step that has both kinds of bodies (the FluidDynamicsTest scene): neither face kernel fills the machine and both are
     // bound by latency, so k_submerged goes to a side stream and runs beside the surface path (two branches of the step's graph).
     // Small = the surface path is certain to take direct mode and the submerged chunks do not outnumber the resident warps either.
-    const char* no_fork = getenv("SFH_NO_FORK"); // A/B measurements
+    const char* no_pdl = getenv("SFH_NO_PDL");   // A/B measurements
+    // Device-resident steps only (back-to-back launches: cfg 3 34.9 -> 30.8 us per step). The replayed graphs of host-side small steps
+    // gain nothing from programmatic edges (host to host 50.3 vs 51.8 us for cfg 3, +-0.5 us elsewhere; measured).
+    const bool pdl = !plan.host_states && !(no_pdl && no_pdl[0] == '1') && !prof;
+    const char* no_fork = getenv("SFH_NO_FORK");
     const bool fork = !(no_fork && no_fork[0] == '1') && !prof && plan.may_sub && g_sub > 0 && surf && g_wet > 0 && g_clip > 0 && surely_direct && plan.chunks_ub &&
                       plan.chunks_ub <= (uint64_t)direct_streams;
     cudaStream_t sub_stream = ctx->stream;
@@ -480,11 +497,11 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     if (plan.may_sub && g_sub > 0) {
         sp.item_off = ctx->d_off_sub.p; sp.partials = ctx->d_part_sub.p;
         if (plan.aero) {
-            if (plan.debug) { if (general) launch_sub<1, true, true>(sp, (int)g_sub, sub_stream); else launch_sub<0, true, true>(sp, (int)g_sub, sub_stream); }
-            else            { if (general) launch_sub<1, false, true>(sp, (int)g_sub, sub_stream); else launch_sub<0, false, true>(sp, (int)g_sub, sub_stream); }
+            if (plan.debug) { if (general) launch_sub<1, true, true>(sp, (int)g_sub, sub_stream, pdl && !fork); else launch_sub<0, true, true>(sp, (int)g_sub, sub_stream, pdl && !fork); }
+            else            { if (general) launch_sub<1, false, true>(sp, (int)g_sub, sub_stream, pdl && !fork); else launch_sub<0, false, true>(sp, (int)g_sub, sub_stream, pdl && !fork); }
         } else {
-            if (plan.debug) { if (general) launch_sub<1, true>(sp, (int)g_sub, sub_stream); else launch_sub<0, true>(sp, (int)g_sub, sub_stream); }
-            else            { if (general) launch_sub<1, false>(sp, (int)g_sub, sub_stream); else launch_sub<0, false>(sp, (int)g_sub, sub_stream); }
+            if (plan.debug) { if (general) launch_sub<1, true>(sp, (int)g_sub, sub_stream, pdl && !fork); else launch_sub<0, true>(sp, (int)g_sub, sub_stream, pdl && !fork); }
+            else            { if (general) launch_sub<1, false>(sp, (int)g_sub, sub_stream, pdl && !fork); else launch_sub<0, false>(sp, (int)g_sub, sub_stream, pdl && !fork); }
         }
         ++launches;
         ctx->ev_sub = true;
@@ -494,7 +511,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
 
     if (surf && g_wet > 0 && g_clip > 0) {
         if (!surely_direct) {
-            k_classify<<<(unsigned)g_cls, SFH_TILE, 0, ctx->stream>>>(cp);
+            launch_k(k_classify, (unsigned)g_cls, SFH_TILE, ctx->stream, pdl && !(plan.may_sub && g_sub > 0 && !fork), cp);
             ++launches;
         }
         if (prof) CU(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
@@ -504,14 +521,14 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
         up.part_wet = ctx->d_part_wet.p; up.part_clip = ctx->d_part_clip.p; up.direct_streams = direct_streams;
         if (time_roles) { // one launch per role, so that each can be timed
             up.wet_blocks = (uint32_t)g_wet;
-            launch_lists_variant(up, (int)g_wet, ctx->stream, waves, general, plan.debug);
+            launch_lists_variant(up, (int)g_wet, ctx->stream, waves, general, plan.debug, pdl);
             CU(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
             up.wet_blocks = 0;
-            launch_lists_variant(up, (int)g_clip, ctx->stream, waves, general, plan.debug);
+            launch_lists_variant(up, (int)g_clip, ctx->stream, waves, general, plan.debug, pdl);
             launches += 2;
         } else {
             up.wet_blocks = (uint32_t)g_wet;
-            launch_lists_variant(up, (int)(g_wet + g_clip), ctx->stream, waves, general, plan.debug);
+            launch_lists_variant(up, (int)(g_wet + g_clip), ctx->stream, waves, general, plan.debug, pdl);
             if (prof) CU(ctx, cudaEventRecord(ctx->ev[7], ctx->stream)); // wet_ms = the whole consumer, clip_ms = 0
             ++launches;
         }
@@ -550,7 +567,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
         CU(ctx, cudaHostGetDevicePointer(&dp, ctx->h_status.p, 0));
         ep.zc_host = static_cast<uint32_t*>(dp);
     }
-    k_epilogue<<<ep.team == 128u ? n * ep.slices : (n + 3) / 4, 128, 0, ctx->stream>>>(ep);
+    launch_k(k_epilogue, ep.team == 128u ? n * ep.slices : (n + 3) / 4, 128u, ctx->stream, pdl && !fork, ep);
     ++launches;
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     CU(ctx, cudaGetLastError());

@@ -84,6 +84,14 @@ struct PartialSurf {
     uint32_t n_degenerate, n_quadratic, n_skin, pad;
 };
 
+// Programmatic dependent launch (griddepcontrol): the kernels of a step are launched with programmatic stream serialization, so
+// the next kernel's blocks are scheduled — launch latency, shared-memory set-up — while its predecessor still runs. pdl_wait()
+// returns when the predecessor grid has COMPLETED and its writes are visible; every kernel of the chain executes it on every path
+// before it reads anything a kernel of the same step wrote (and before it exits: completion of a grid that never waited would say
+// nothing about ITS predecessor). Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // fp32 chain: glm::vec3 semantics, one rounding per operator, nothing fused
 // ---------------------------------------------------------------------------------------------

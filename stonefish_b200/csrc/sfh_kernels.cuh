@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t
 // Steps of at most 1024 bodies: prologue and scan in one launch (single-body steps are launch-latency bound)
 __global__ void __launch_bounds__(1024) k_prologue_scan(PrologueParams P)
 {
+    pdl_trigger(); // the face kernels may be scheduled now; they wait for this grid before they read its lists
     if (threadIdx.x < P.n_bodies) prologue_body(P, threadIdx.x);
     __syncthreads();
     scan_items(P.off_sub, P.off_surf, P.n_bodies);
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueParams P)
 {
     __shared__ double s_red[4][SFH_NACC_SURF];
     __shared__ uint32_t s_cnt[4][11];
+    pdl_wait();
     const uint32_t per_block = 128u / P.team;
     const uint32_t b = P.team == 128u ? blockIdx.x / P.slices : blockIdx.x * per_block + threadIdx.x / P.team;
     if (b < P.n_bodies) epilogue_body(P, b, threadIdx.x % P.team, P.team, s_red, s_cnt);

@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
         stage_currents(s_cur, s_guard, P.ocean, n_cur);
         __syncthreads(); // the only block barrier of the kernel, before any warp can leave
     }
+    pdl_trigger();
+    pdl_wait(); // the prologue's work lists and body records
     const uint64_t W = P.item_off[P.n_bodies], G = min((uint64_t)gridDim.x * SFH_SUB_WPB, W);
     const uint32_t wg = blockIdx.x * SFH_SUB_WPB + warp;
     if (wg >= G) return;

@@ -364,6 +364,8 @@ __device__ __forceinline__ uint32_t surface_items(const ClassifyParams& P)
 __global__ void __launch_bounds__(SFH_TILE, 4) k_classify(ClassifyParams P)
 {
     __shared__ uint32_t s_last;
+    pdl_trigger();
+    pdl_wait();
     const uint32_t W = surface_items(P);
     if (direct_split(W, P.direct_streams)) return; // the consumers classify for themselves
     classify_tiles(P, W, blockIdx.x, gridDim.x);
@@ -911,6 +913,8 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SURF_MIN_BLOCKS) k_surfac
         stage_currents(s_cur, s_guard, P.ocean, n_cur);
         __syncthreads(); // the only block barrier of the kernel, before any warp can leave
     }
+    pdl_trigger();
+    pdl_wait(); // the prologue's (and k_classify's) results
     const uint32_t W = P.off_surf[P.n_bodies], dsplit = direct_split(W <= P.L.items_cap ? W : 0u, P.direct_streams);
     if (dsplit) { // small step: every (sub-)item has a warp of its own, no lists
         const uint32_t u = blockIdx.x * SFH_SUB_WPB + warp;
