@@ -368,7 +368,7 @@ def measure(rig: Rig, args, workload: str, n: int, first: int, keep_host: int, s
             k_ms.append(max(t.submerged_ms, t.surface_ms))
             pro_ms.append(t.prologue_ms); epi_ms.append(t.epilogue_ms)
             launches = t.launches
-            dominant = "k_submerged" if t.submerged_ms >= t.surface_ms else "surface path (k_classify + k_surface_wet + k_surface_clip)"
+            dominant = "k_submerged" if t.submerged_ms >= t.surface_ms else "surface path (k_classify + k_surface_lists: wet and clip roles)"
             split.append((t.classify_ms, t.wet_ms, t.clip_ms))
             if t.chunks_surface and not (t.chunks_wet or t.chunks_clip):  # direct mode: every warp classifies its own item, no lists
                 chunks = {"surface": int(t.chunks_surface), "mode": "direct (no lists: kinds not recorded)"}

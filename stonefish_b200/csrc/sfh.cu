@@ -455,8 +455,9 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     // second wave of blocks would pay the per-warp start-up (classification, descriptor and chunk round trips) a second time
     const uint32_t direct_streams = (time_roles || (no_direct && no_direct[0] == '1')) ? 0u : (uint32_t)((g_wet > g_clip ? g_wet : g_clip) * SFH_SUB_WPB);
     cp.direct_streams = direct_streams;
-    // with host-side states the host knows when the step is certain to run in direct mode: k_classify is not even launched
-    const bool surely_direct = direct_streams && plan.surf_ub && plan.surf_ub <= direct_streams;
+    // the host often knows that the step is certain to run in direct mode (exactly, with host-side states): k_classify is not even launched
+    // (device-resident states: when even bodies x largest mesh fits)
+    const bool surely_direct = direct_streams && items_ub <= direct_streams;
     PrologueParams pp;
     pp.states = d_states; pp.meshes = ctx->d_meshes.p; pp.n_meshes = (uint32_t)ctx->meshes.size(); pp.n_bodies = n;
     pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;

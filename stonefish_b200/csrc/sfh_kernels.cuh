@@ -556,7 +556,7 @@ __device__ __forceinline__ void epilogue_body(const EpilogueParams& P, uint32_t 
                 for (int i = 1; i < 8; ++i) cnt[3 + i] += r.cls[i];
             }
         };
-        const uint32_t dsplit = direct_split(Wall <= P.L.items_cap ? Wall : 0u, P.direct_streams);
+        const uint32_t dsplit = Wall <= P.L.items_cap ? direct_split(Wall, P.direct_streams) : 0u;
         if (dsplit) { // direct mode: one record per sub-item, `dsplit` consecutive ones per chunk
             add_records(P.part_wet, o0 * dsplit, o1 * dsplit, 1u);
         } else if (o1 > o0 && o1 <= P.L.ctrl[SC_ITEMS]) { // SC_ITEMS = 0: the lists did not fit (status flag)

@@ -58,7 +58,8 @@ __device__ __forceinline__ int floor_div(int a, int n) { return a >= 0 ? a / n :
 // items) and T (consumer streams): 0 = list mode, else the number of sub-items per item.
 __device__ __forceinline__ uint32_t direct_split(uint32_t W, uint32_t T)
 {
-    if (W == 0u || W > T) return 0u;
+    if (W > T) return 0u;
+    if (W == 0u) return 1u; // nothing to do: no lists either (k_classify may not even have been launched)
     return (uint64_t)W * 4u <= T ? 4u : ((uint64_t)W * 2u <= T ? 2u : 1u);
 }
 
@@ -366,8 +367,9 @@ __global__ void __launch_bounds__(SFH_TILE, 4) k_classify(ClassifyParams P)
     __shared__ uint32_t s_last;
     pdl_trigger();
     pdl_wait();
-    const uint32_t W = surface_items(P);
-    if (direct_split(W, P.direct_streams)) return; // the consumers classify for themselves
+    const bool fits = P.off_surf[P.n_bodies] <= P.L.items_cap;
+    const uint32_t W = surface_items(P); // 0 (and a status flag) when the items do not fit: empty lists are built
+    if (fits && direct_split(W, P.direct_streams)) return; // the consumers classify for themselves
     classify_tiles(P, W, blockIdx.x, gridDim.x);
     // the last block to finish turns the tile counts into offsets and sizes the consumers' segments
     __threadfence();
@@ -915,7 +917,7 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SURF_MIN_BLOCKS) k_surfac
     }
     pdl_trigger();
     pdl_wait(); // the prologue's (and k_classify's) results
-    const uint32_t W = P.off_surf[P.n_bodies], dsplit = direct_split(W <= P.L.items_cap ? W : 0u, P.direct_streams);
+    const uint32_t W = P.off_surf[P.n_bodies], dsplit = W <= P.L.items_cap ? direct_split(W, P.direct_streams) : 0u;
     if (dsplit) { // small step: every (sub-)item has a warp of its own, no lists
         const uint32_t u = blockIdx.x * SFH_SUB_WPB + warp;
         if (u < W * dsplit) surface_direct<WAVES, CUR, DEBUG>(P, s_stage[warp], s_cur, s_guard, n_cur, lane, u, dsplit);

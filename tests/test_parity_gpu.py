@@ -498,3 +498,39 @@ def test_chunk_classifier_is_conservative(ctx, oracle, surface_mode, amplitude):
     assert err <= REL_TOL, (err, where)
     cls = gi["class_count"].sum(axis=0)
     assert cls[0] > 0 and cls[7] > 0 and cls[1:7].sum() > 0     # dry, wet and cut faces all occur
+
+
+def test_step_without_surface_items_between_surface_steps(ctx, oracle, surface_mode):
+    """AUTO bodies that all turn out INSIDE leave the surface path with NO items although the host had to allow for some: the
+    consumers of that step must not walk the lists (or the control words) an earlier step left behind, and the next surface step must
+    not see anything of the empty one. Both ways through the surface path, host-side and device-resident states."""
+    import torch
+
+    from stonefish_b200._abi import SFH_POS_AUTO
+    from stonefish_b200.hydro import INFO_DTYPE
+
+    crossing = scenes.mixed_small(5, True, "none")
+    deep = scenes.config4(12, 50, 21, unique_meshes=True)         # far below the surface ...
+    deep.ocean = crossing.ocean
+    deep.states["mode"] = SFH_POS_AUTO                             # ... but the gate decides that on the device
+    for round_ in range(2):
+        for sc in (crossing, deep, crossing):
+            gi, gc, ri, rc = run_both(ctx, oracle, sc)
+            assert_counts_equal(gi, ri)
+            err, where = max_rel_err(gi, ri)
+            assert err <= REL_TOL, (sc.name, round_, err, where)
+        assert (gi["position"] == 2).any()
+    gi, _, ri, _ = run_both(ctx, oracle, deep)
+    assert (gi["position"] == 1).all() and np.abs(gi["Fdq"]).max() > 0
+    # device-resident states: the host knows nothing about the bodies
+    st = deep.bind(ctx)
+    dev = torch.device("cuda", 0)
+    d_st = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(dev)
+    d_out = torch.zeros(len(st) * INFO_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    run_both(ctx, oracle, crossing)
+    ctx.compute_device(deep.ocean.to_struct(), d_st.data_ptr(), len(st), d_out.data_ptr())
+    ctx.sync()
+    got = d_out.cpu().numpy().view(INFO_DTYPE)
+    assert_counts_equal(got, ri)
+    err, where = max_rel_err(got, ri)
+    assert err <= REL_TOL, (err, where)
