@@ -326,7 +326,17 @@ __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SUB_MIN_BLOCKS) k_submerg
         for (int i = 0; i < SFH_NACC_SUB; ++i) { acc[i] = (double)accf[i]; accf[i] = 0.f; }
 #endif
         PartialSub* rec = reinterpret_cast<PartialSub*>(P.partials) + (wg + body);
+#ifdef SFH_SUB_FOLD_FLUSH /* the folded flush of the surface roles (warp_sum_store): 20 KB less code here, but the face loop around
+                             it is scheduled differently and cfg 4 loses 2.2 % (127.2 against 130.0 G, A/B on one box) */
         warp_sum_store<SFH_NACC_SUB>(acc, rec->a, lane);
+#else
+#pragma unroll
+        for (int i = 0; i < SFH_NACC_SUB; ++i) {
+            const double v = warp_sum(acc[i]);
+            if (lane == 0) rec->a[i] = v;
+            acc[i] = 0.0;
+        }
+#endif
         if (lane == 0) { rec->n_degenerate = cnt0; rec->n_quadratic = cnt1; rec->n_skin = cnt2; }
         cnt0 = cnt1 = cnt2 = 0;
     };
