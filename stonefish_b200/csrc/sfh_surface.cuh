@@ -170,7 +170,7 @@ __device__ __forceinline__ void chan_reduce(const ChanWin& w, const float (&v)[1
 
 // Kind of one chunk of a crossing body. R, t: T_C as fp32 (BodyDev); b0, b1: the chunk's box in the mesh frame (ChunkBounds).
 __device__ __forceinline__ uint32_t classify_chunk(const float* __restrict__ R, const float* __restrict__ t, float4 b0, float2 b1, bool waves,
-                                                   const WavesDev& wv, float hmax0, float hmax1)
+                                                   const WavesDev& wv, float hmax0, float hmax1, int local = 2)
 {
     const float cx = b0.x, cy = b0.y, cz = b0.z, hx = b0.w, hy = b1.x, hz = b1.y;
     float cw[3], ext[3], M = 0.f;
@@ -191,7 +191,7 @@ __device__ __forceinline__ uint32_t classify_chunk(const float* __restrict__ R, 
     const float H = __fadd_ru(hmax0, hmax1), E = e + 1e-5f * H;
     if (zmax + H + E < 0.f) return CK_DRY;
     if (zmin - H - E > 0.f) return CK_WET;
-    if (!(zmax + H + E >= 0.f)) return CK_CLIP; // NaN somewhere: the general path
+    if (!(zmax + H + E >= 0.f) || local == 0) return CK_CLIP; // NaN somewhere: the general path
     float lo0 = -hmax0, hi0 = hmax0, lo1 = -hmax1, hi1 = hmax1;
     const ChanWin w0 = chan_window(wv.N, wv.gx, cw[0], cw[1], ext[0] + e, ext[1] + e);
     const ChanWin w1 = chan_window(wv.N, wv.gy, cw[0], cw[1], ext[0] + e, ext[1] + e);
@@ -200,10 +200,12 @@ __device__ __forceinline__ uint32_t classify_chunk(const float* __restrict__ R, 
     for (int k = 0; k < 16; ++k) { v0[k] = __ldg(wv.ch0 + w0.idx[k]); v1[k] = __ldg(wv.ch1 + w1.idx[k]); }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { c0[k] = __ldg(wv.ch0 + w0.cen[k]); c1[k] = __ldg(wv.ch1 + w1.cen[k]); }
+    // local = 2 (k_classify, one thread per chunk): the full local bound; local = 1: a channel whose footprint does not fit the
+    // 4 x 4 window keeps its global bound instead of walking up to 8 x 8 texels row by row; local = 0 returned above
     if (w0.fast) chan_reduce(w0, v0, c0, lo0, hi0);
-    else wave_channel_bounds(wv.ch0, wv.N, wv.gx, hmax0, cw[0], cw[1], ext[0] + e, ext[1] + e, lo0, hi0);
+    else if (local == 2) wave_channel_bounds(wv.ch0, wv.N, wv.gx, hmax0, cw[0], cw[1], ext[0] + e, ext[1] + e, lo0, hi0);
     if (w1.fast) chan_reduce(w1, v1, c1, lo1, hi1);
-    else wave_channel_bounds(wv.ch1, wv.N, wv.gy, hmax1, cw[0], cw[1], ext[0] + e, ext[1] + e, lo1, hi1);
+    else if (local == 2) wave_channel_bounds(wv.ch1, wv.N, wv.gy, hmax1, cw[0], cw[1], ext[0] + e, ext[1] + e, lo1, hi1);
     if (zmax + (hi0 + hi1) + E < 0.f) return CK_DRY;
     if (zmin + (lo0 + lo1) - E > 0.f) return CK_WET;
     return CK_CLIP;
@@ -849,7 +851,14 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStageSur
     if (lane == 0) pipe_issue(pa, 0, s_body.chunks + (size_t)__float_as_uint(b1.z) * 16u, __float_as_uint(b1.w));
     float hmax0 = 0.f, hmax1 = 0.f;
     if (WAVES) { hmax0 = __uint_as_float(__ldg(P.waves.hmax)); hmax1 = __uint_as_float(__ldg(P.waves.hmax + 1)); }
-    uint32_t kind = classify_chunk(s_body.R, s_body.t, b0, make_float2(b1.x, b1.y), WAVES, P.waves, hmax0, hmax1);
+    // Direct mode keeps the GLOBAL wave bound (local = 0): the step waits for its slowest warp, and that warp is one with a cut chunk
+    // whatever the others are spared; the local bound costs every warp its texel round trips. Measured host to host (5k-face hull /
+    // 200k-face hull crossing waves, nearly every chunk inside the global band): full local bound 40.7 / 50.3 us, 4 x 4 window only
+    // 36.5 / 46.6 us, global bound 34.6 / 45.3 us (r01, no classification at all: 33.5 / 54.5 us).
+#ifndef SFH_DIRECT_LOCAL
+#define SFH_DIRECT_LOCAL 0
+#endif
+    uint32_t kind = classify_chunk(s_body.R, s_body.t, b0, make_float2(b1.x, b1.y), WAVES, P.waves, hmax0, hmax1, SFH_DIRECT_LOCAL);
     if (kind == CK_WET && (s_body.flags & (BF_BUOYANCY | BF_DAMPING)) != (BF_BUOYANCY | BF_DAMPING)) kind = CK_CLIP; // as k_classify
 
     double acc[SFH_NACC_SURF];
