@@ -544,10 +544,12 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     ep.part_sub = ctx->d_part_sub.p; ep.part_wet = ctx->d_part_wet.p; ep.part_clip = ctx->d_part_clip.p;
     ep.grid_sub = (uint32_t)(g_sub * SFH_SUB_WPB); ep.L = L; ep.aero = plan.aero ? 1u : 0u; ep.out = d_out;
     ep.direct_streams = surf ? direct_streams : 0u;
-    ep.team = n <= 256 ? 128u : 32u;
     // slices of >= 256 records: a body has at most one record per stream (or sub-item) that touched it
     uint64_t rec_ub = (uint64_t)ctx->num_sms * 16 * SFH_SUB_WPB;
     if (plan.chunks_ub && 4 * plan.chunks_ub < rec_ub) rec_ub = 4 * plan.chunks_ub;
+    // a block of 128 threads per body pays a block barrier and a four-way sum: only where a body can have more records than a warp
+    // reads in two or three rounds
+    ep.team = (n <= 256 && rec_ub / n > 96) ? 128u : 32u;
     ep.slices = 1;
     if (ep.team == 128u) {
         const uint64_t want = rec_ub / n / 256, room = 512u / n;
