@@ -912,7 +912,11 @@ __device__ __forceinline__ void surface_direct(const SurfParams& P, WarpStageSur
 // step the wet blocks fill the machine first and clip blocks move in as they leave — no kernel boundary in between; on a small
 // step both roles are resident together and their latencies overlap.
 template <bool WAVES, int CUR, bool DEBUG>
+#ifdef SFH_SURF_MAXNREG /* experiments: a register cap between the steps __launch_bounds__ offers */
+__global__ void __maxnreg__(SFH_SURF_MAXNREG) k_surface_lists(SurfParams P)
+#else
 __global__ void __launch_bounds__(SFH_SUB_THREADS, SFH_SURF_MIN_BLOCKS) k_surface_lists(SurfParams P)
+#endif
 {
     __shared__ WarpStageSurf s_stage[SFH_SUB_WPB];
     __shared__ sfh_current s_cur[CUR ? SFH_MAX_CURRENTS : 1];
