@@ -308,7 +308,7 @@ def test_ragged_and_chunk_boundary_meshes(ctx, oracle, surface_mode):
 
 @pytest.mark.parametrize("waves", [False, True])
 def test_dry_chunk_skip_and_field_masks_are_exact(ctx, oracle, waves, surface_mode):
-    """k_surface drops chunks whose bounding sphere lies above the highest possible surface and skips Jet/Pipe fields that
+    """The surface path drops chunks whose box lies above the highest possible surface and skips Jet/Pipe fields that
     cannot reach a chunk's sphere. Both are conservative tests, so codes and sums must stay what the oracle says — also for a
     NON-RIGID T_C (scaled, sheared basis: the sphere bound uses row / Frobenius norms, not |R| = 1), for hulls standing
     several wave heights out of the water (most chunks dropped) and for bodies straddling the edge of a jet cone and a pipe."""

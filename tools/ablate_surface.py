@@ -1,4 +1,4 @@
-"""Where does k_surface spend its time? Same 16 x 1M-face vessels with waves / Jet+Pipe currents switched off in turn."""
+"""Where does the surface path (k_classify + k_surface_lists) spend its time? Same 16 x 1M-face vessels with waves / Jet+Pipe currents switched off in turn."""
 import os, sys, numpy as np
 os.environ["SFH_PROFILE_ROLES"] = "1"  # time the wet and the clip role of k_surface_lists in launches of their own
 sys.path.insert(0, ".")
