@@ -457,7 +457,7 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     cp.direct_streams = direct_streams;
     // the host often knows that the step is certain to run in direct mode (exactly, with host-side states): k_classify is not even launched
     // (device-resident states: when even bodies x largest mesh fits)
-    const bool surely_direct = direct_streams && items_ub <= direct_streams;
+    const bool surely_direct = direct_streams && items_ub <= 2 * (uint64_t)direct_streams; // direct_split(): up to two waves
     PrologueParams pp;
     pp.states = d_states; pp.meshes = ctx->d_meshes.p; pp.n_meshes = (uint32_t)ctx->meshes.size(); pp.n_bodies = n;
     pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;

@@ -55,10 +55,13 @@ __device__ __forceinline__ int floor_div(int a, int n) { return a >= 0 ? a / n :
 // DIRECT MODE: a step with no more surface items than consumer streams (a single hull, a small scene) is bound by latency, and
 // every kernel of the chain costs 5-15 us of dependent round trips whatever it computes. Such a step skips the lists: warp u of
 // k_surface_lists classifies its own (sub-)item, works on it and writes one record. Every kernel decides alike from W (surface
-// items) and T (consumer streams): 0 = list mode, else the number of sub-items per item.
+// items) and T (the consumer's RESIDENT streams; the launch has twice as many warps): 0 = list mode, else the number of sub-items
+// per item. Sub-items only while they all fit the resident warps (a second wave pays the per-warp start-up again: 400k faces
+// 50.8 us with one sub-item per chunk in one wave, 57.7 us with two in two waves); whole chunks up to two waves (455k-900k-face
+// hulls crossing waves: 53-66 us against 61-72 us through the lists).
 __device__ __forceinline__ uint32_t direct_split(uint32_t W, uint32_t T)
 {
-    if (W > T) return 0u;
+    if (W > 2u * (uint64_t)T) return 0u; // up to two waves of warps (the launch always has 2 T of them): measured against the lists
     if (W == 0u) return 1u; // nothing to do: no lists either (k_classify may not even have been launched)
     return (uint64_t)W * 4u <= T ? 4u : ((uint64_t)W * 2u <= T ? 2u : 1u);
 }

@@ -48,7 +48,9 @@ def test_config2_reduced_and_full(ctx, oracle):
 
 @pytest.mark.parametrize("waves", [False, True])
 def test_config3_reduced_and_full(ctx, oracle, waves, surface_mode):
-    for seg, st in ((100, 51), (400, 251)):
+    # 10k and 200k faces (direct mode: 4 and 2 sub-items per chunk), 455k faces (1777 chunks: one more than the resident warps —
+    # whole chunks in a second wave of warps), 1M faces (more chunks than two waves: the lists whatever the mode)
+    for seg, st in ((100, 51), (400, 251), (600, 380), (1000, 501)):
         sc = scenes.config3(seg, st, waves)
         gi, gc, ri, rc = run_both(ctx, oracle, sc)
         assert_counts_equal(gi, ri)
