@@ -25,3 +25,5 @@ done
 done
 echo "== compute-sanitizer --tool memcheck python -m pytest tests/test_parity_gpu.py tests/test_real_meshes_gpu.py tests/test_aero_gpu.py -m gpu -k 'not full and not large'"
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py tests/test_real_meshes_gpu.py tests/test_aero_gpu.py -m gpu -q -x -k 'not full and not large' 2>&1 | tail -4
+echo "== compute-sanitizer --tool memcheck python -m pytest tests/test_parity_gpu.py -m gpu -k config3   (10k .. 1M-face hulls: sub-items, second wave of direct mode, lists)"
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -m gpu -q -x -k config3 2>&1 | tail -4
