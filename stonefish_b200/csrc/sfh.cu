@@ -597,6 +597,15 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
     std::vector<uint64_t> code_base;
     if (debug) code_base.resize(n);
     uint64_t total_codes = 0;
+    // Large steps from pinned buffers: the state copy is started BEFORE the host walks the records (validation and work bounds read
+    // every 464-byte record once: tens of microseconds for thousands of bodies), so the two overlap. A record that then fails
+    // validation only means the copy was for nothing.
+    bool states_copied = false;
+    if (n > SFH_GRAPH_MAX_BODIES && n <= ctx->d_states.cap && n <= ctx->d_info.cap && is_pinned_host(states)) {
+        if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->d_states.p, states, (size_t)n * sizeof(sfh_body_state), cudaMemcpyHostToDevice, ctx->stream));
+        states_copied = true;
+    }
     {
         std::lock_guard<std::mutex> lock(ctx->mesh_mutex);
         for (uint32_t i = 0; i < n; ++i) {
@@ -704,14 +713,16 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
         return SFH_OK;
     }
 
-    if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    const void* src = states;
-    if (!is_pinned_host(states)) {
-        if ((rc = ensure_pin(ctx, ctx->h_states, sbytes)) != SFH_OK) return rc;
-        std::memcpy(ctx->h_states.p, states, sbytes);
-        src = ctx->h_states.p;
+    if (!states_copied) {
+        if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        const void* src = states;
+        if (!is_pinned_host(states)) {
+            if ((rc = ensure_pin(ctx, ctx->h_states, sbytes)) != SFH_OK) return rc;
+            std::memcpy(ctx->h_states.p, states, sbytes);
+            src = ctx->h_states.p;
+        }
+        CU(ctx, cudaMemcpyAsync(ctx->d_states.p, src, sbytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    CU(ctx, cudaMemcpyAsync(ctx->d_states.p, src, sbytes, cudaMemcpyHostToDevice, ctx->stream));
 
     if (debug) {
         if ((rc = ensure_dev(ctx, ctx->d_codes, total_codes ? total_codes : 1)) != SFH_OK) return rc;
