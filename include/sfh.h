@@ -74,7 +74,9 @@ int sfh_abi_version(void);
 /* Context = one GPU: stream, pinned staging, device arenas.
  * Replaces: the ThreadPool the reference creates for hydrodynamics (SimulationApp.cpp:132-142). */
 int sfh_create(int cuda_device, sfh_ctx** out);
-/* Same, but enqueue on a caller-owned cudaStream_t (e.g. torch's current stream) instead of a private one. */
+/* Same, but enqueue on a caller-owned cudaStream_t (e.g. torch's current stream) instead of a private one. Everything a step does
+ * is ordered with that stream: a small step with both submerged and surface-crossing bodies runs one of its kernels on a private side
+ * stream, forked after the step's first kernel and joined before its last by events (two branches inside the step, invisible outside). */
 int sfh_create_on_stream(int cuda_device, void* cuda_stream, sfh_ctx** out);
 void sfh_destroy(sfh_ctx* ctx);
 /* Text of the last error on ctx (ctx == NULL: last error of sfh_create on this thread). Never NULL. */
