@@ -342,8 +342,8 @@ struct StepPlan {
 
 // A kernel launch that may overlap the tail of its predecessor in the stream (programmatic dependent launch, see pdl_wait() in
 // sfh_device.cuh); pdl = false: an ordinary launch.
-template <typename P>
-void launch_k(void (*kernel)(P), unsigned grid, unsigned block, cudaStream_t s, bool pdl, const P& params)
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t s, bool pdl, Args... params)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(block, 1, 1); cfg.dynamicSmemBytes = 0; cfg.stream = s;
@@ -351,7 +351,7 @@ void launch_k(void (*kernel)(P), unsigned grid, unsigned block, cudaStream_t s, 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
-    cudaLaunchKernelEx(&cfg, kernel, params); // errors are picked up by cudaGetLastError at the end of run_step
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(params)...); // errors are picked up by cudaGetLastError at the end of run_step
 }
 template <int CUR, bool DEBUG, bool AERO = false>
 void launch_sub(const StepParams& P, int grid, cudaStream_t s, bool pdl) { launch_k(k_submerged<CUR, DEBUG, AERO>, (unsigned)grid, SFH_SUB_THREADS, s, pdl, P); }
@@ -463,13 +463,19 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     pp.ocean = ctx->d_ocean.p; pp.waves = ctx->waves; pp.bodies = ctx->d_bodies.p;
     pp.off_sub = ctx->d_off_sub.p; pp.off_surf = ctx->d_off_surf.p; pp.status = ctx->d_status.p; pp.aero = plan.aero ? 1u : 0u;
     pp.no_sub = plan.may_sub ? 0u : 1u; pp.no_surf = (plan.may_surf || plan.aero) ? 0u : 1u;
+    const char* no_pdl = getenv("SFH_NO_PDL");   // A/B measurements
+    // Device-resident steps only (back-to-back launches: cfg 3 34.9 -> 30.8 us per step). The replayed graphs of host-side small steps
+    // gain nothing from programmatic edges (host to host 50.3 vs 51.8 us for cfg 3, +-0.5 us elsewhere; measured, DESIGN.md 7b).
+    const bool pdl = !plan.host_states && !(no_pdl && no_pdl[0] == '1') && !prof;
+    const bool pdl_chain = pdl; // k_prologue -> k_scan_items of a large step
     uint32_t launches;
     if (n <= 1024) {
         k_prologue_scan<<<1, 1024, 0, ctx->stream>>>(pp);
         launches = 1;
     } else {
-        k_prologue<<<(n + 127) / 128, 128, 0, ctx->stream>>>(pp);
-        k_scan_items<<<1, 1024, 0, ctx->stream>>>(ctx->d_off_sub.p, ctx->d_off_surf.p, n);
+        const unsigned pt = SFH_PROLOGUE_THREADS; // bodies per block: few, so that the records' round trips spread over the SMs
+        k_prologue<<<(n + pt - 1) / pt, pt, 0, ctx->stream>>>(pp);
+        launch_k(k_scan_items, 1u, 1024u, ctx->stream, pdl_chain, ctx->d_off_sub.p, ctx->d_off_surf.p, n);
         launches = 2;
     }
     if (prof) CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -482,10 +488,6 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     // A small step that has both kinds of bodies (the FluidDynamicsTest scene): neither face kernel fills the machine and both are
     // bound by latency, so k_submerged goes to a side stream and runs beside the surface path (two branches of the step's graph).
     // Small = the surface path is certain to take direct mode and the submerged chunks do not outnumber the resident warps either.
-    const char* no_pdl = getenv("SFH_NO_PDL");   // A/B measurements
-    // Device-resident steps only (back-to-back launches: cfg 3 34.9 -> 30.8 us per step). The replayed graphs of host-side small steps
-    // gain nothing from programmatic edges (host to host 50.3 vs 51.8 us for cfg 3, +-0.5 us elsewhere; measured, DESIGN.md 7b).
-    const bool pdl = !plan.host_states && !(no_pdl && no_pdl[0] == '1') && !prof;
     const char* no_fork = getenv("SFH_NO_FORK");
     const bool fork = !(no_fork && no_fork[0] == '1') && !prof && plan.may_sub && g_sub > 0 && surf && g_wet > 0 && g_clip > 0 && surely_direct && plan.chunks_ub &&
                       plan.chunks_ub <= (uint64_t)direct_streams;

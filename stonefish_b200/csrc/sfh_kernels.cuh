@@ -268,8 +268,12 @@ __device__ __forceinline__ void prologue_body(const PrologueParams& P, uint32_t 
     P.off_surf[i] = (kind == KIND_SURFACE) ? bd.n_chunks : 0u;
 }
 
+#ifndef SFH_PROLOGUE_THREADS
+#define SFH_PROLOGUE_THREADS 32 /* bodies per block of k_prologue: few, so that the records' round trips spread over the SMs */
+#endif
 __global__ void __launch_bounds__(128) k_prologue(PrologueParams P)
 {
+    pdl_trigger();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.n_bodies) prologue_body(P, i);
 }
@@ -317,6 +321,8 @@ __device__ __forceinline__ void scan_items(uint32_t* off_sub, uint32_t* off_surf
 }
 __global__ void __launch_bounds__(1024) k_scan_items(uint32_t* off_sub, uint32_t* off_surf, uint32_t n_bodies)
 {
+    pdl_trigger();
+    pdl_wait(); // k_prologue's chunk counts
     scan_items(off_sub, off_surf, n_bodies);
 }
 // Steps of at most 1024 bodies: prologue and scan in one launch (single-body steps are launch-latency bound)
