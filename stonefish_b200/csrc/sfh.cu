@@ -469,7 +469,12 @@ int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_state
     const bool pdl = !plan.host_states && !(no_pdl && no_pdl[0] == '1') && !prof;
     const bool pdl_chain = pdl; // k_prologue -> k_scan_items of a large step
     uint32_t launches;
-    if (n <= 1024) {
+    // One block does gates and scans for a small step (one launch less); from a few hundred bodies on, its single SM is the slower
+    // way: 512 bodies 218.2 -> 213.1 us per step with k_prologue spread over the SMs, 1024 bodies 420.5 -> 405.4 us, 192 equal.
+#ifndef SFH_PROLOGUE_SCAN_MAX
+#define SFH_PROLOGUE_SCAN_MAX 192u
+#endif
+    if (n <= SFH_PROLOGUE_SCAN_MAX) {
         k_prologue_scan<<<1, 1024, 0, ctx->stream>>>(pp);
         launches = 1;
     } else {
