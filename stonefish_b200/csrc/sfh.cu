@@ -368,6 +368,9 @@ void launch_lists_variant(const SurfParams& P, int grid, cudaStream_t s, bool wa
     }
 }
 
+#ifndef SFH_GRAPH_MAX_FACES
+#define SFH_GRAPH_MAX_FACES 2500000ull
+#endif
 int run_step(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* d_states, uint32_t n, sfh_info* d_out, const StepPlan& plan)
 {
     int rc;
@@ -644,7 +647,14 @@ int step_host(sfh_ctx* ctx, const sfh_ocean* ocean, const sfh_body_state* states
     // Small steps are launch-latency bound (2 copies in, 5 kernels, 2 copies out): once the same step shape has been
     // seen twice in a row it is captured into a CUDA graph and replayed with one launch. Everything a graph node
     // reads is at a fixed address: states/results/ocean go through the context's pinned staging buffers.
-    const bool graphable = !debug && !ctx->profiling && n <= SFH_GRAPH_MAX_BODIES;
+    // From PINNED caller buffers a graph costs the two copies through the staging buffers (0.03 us per body), and a step with
+    // millions of faces hides its launches behind its own kernels anyway: such steps are launched one by one, the copies straight
+    // from / to the caller's buffers. Measured end to end, 50k-face hulls: 32 bodies 54.5 (graph) vs 57.5 us, 64 bodies 75.1 vs
+    // 73.6 us, 128 bodies 104 vs 98.3 us, 512 bodies 266 vs 251.5 us, 1024 bodies 482 vs 450.5 us.
+    const char* gmf = getenv("SFH_GRAPH_MAX_FACES"); // A/B measurements
+    const uint64_t graph_max_faces = gmf ? strtoull(gmf, nullptr, 10) : SFH_GRAPH_MAX_FACES;
+    bool graphable = !debug && !ctx->profiling && n <= SFH_GRAPH_MAX_BODIES;
+    if (graphable && (plan.faces > graph_max_faces || n > 256u) && is_pinned_host(states) && is_pinned_host(out)) graphable = false;
     if (graphable) {
         if ((rc = ensure_pin(ctx, ctx->h_states, sbytes)) != SFH_OK) return rc;
         if ((rc = ensure_pin(ctx, ctx->h_info, obytes)) != SFH_OK) return rc;
