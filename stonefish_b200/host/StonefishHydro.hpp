@@ -297,13 +297,63 @@ struct CableBody {
 
 //! One GPU worth of hydrodynamics: replaces the ThreadPool-driven loop of SimulationManager::SimulationTickCallback
 //! (SimulationManager.cpp:1619-1655). Not copyable; one per GPU.
+//! Array of trivially copyable records in page-locked host memory (sfh_host_alloc): sfh_step copies straight from / to it — no
+//! staging copy inside the library, and the state copy of a large step overlaps the library's host-side validation. Contents are
+//! NOT kept when it grows (the engine rewrites every record each step).
+template <typename T>
+class PinnedArray {
+public:
+    PinnedArray() = default;
+    PinnedArray(const PinnedArray&) = delete;
+    PinnedArray& operator=(const PinnedArray&) = delete;
+    ~PinnedArray() { release(); }
+    void bind(sfh_ctx* c) { ctx = c; }
+    void release()
+    {
+        if (p) sfh_host_free(ctx, p);
+        p = nullptr; n = cap = 0;
+    }
+    void resize(size_t count)
+    {
+        if (count > cap) {
+            const size_t want = count > cap + cap / 2 ? count : cap + cap / 2;
+            void* q = nullptr;
+            if (sfh_host_alloc(ctx, want * sizeof(T), &q) != SFH_OK) throw std::runtime_error(std::string("sfh_host_alloc: ") + sfh_last_error(ctx));
+            if (p) sfh_host_free(ctx, p);
+            p = static_cast<T*>(q);
+            cap = want;
+        }
+        n = count;
+    }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    const T* begin() const { return p; }
+    const T* end() const { return p + n; }
+
+private:
+    sfh_ctx* ctx = nullptr;
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+};
+
 class HydroEngine {
 public:
     explicit HydroEngine(int cudaDevice = 0)
     {
         if (sfh_create(cudaDevice, &ctx) != SFH_OK) throw std::runtime_error(std::string("sfh_create: ") + sfh_last_error(nullptr));
+        states.bind(ctx);
+        infos.bind(ctx);
     }
-    ~HydroEngine() { sfh_destroy(ctx); }
+    ~HydroEngine()
+    {
+        states.release(); // before the context they were allocated through goes away
+        infos.release();
+        sfh_destroy(ctx);
+    }
     HydroEngine(const HydroEngine&) = delete;
     HydroEngine& operator=(const HydroEngine&) = delete;
 
@@ -435,7 +485,7 @@ public:
 
     sfh_ctx* raw() { return ctx; }
     //! The raw records of the last ComputeHydrodynamicForces / ComputeAerodynamicForces (validation counters included)
-    const std::vector<sfh_info>& LastInfos() const { return infos; }
+    std::vector<sfh_info> LastInfos() const { return std::vector<sfh_info>(infos.begin(), infos.end()); }
     void ClearInfos() { infos.clear(); }
     //! Feed a wave field this engine's Ocean mirror did not hand over itself (HydroEngineMulti shares one Ocean between engines)
     void UploadWaves(const sfh_waves& w) { Check(sfh_waves_upload(ctx, &w), "sfh_waves_upload"); }
@@ -465,8 +515,8 @@ private:
     sfh_ctx* ctx = nullptr;
     sfh_ocean ocean;
     sfh_atmosphere atmosphere;
-    std::vector<sfh_body_state> states;
-    std::vector<sfh_info> infos;
+    PinnedArray<sfh_body_state> states; // gathered / scattered in place: page-locked, see PinnedArray
+    PinnedArray<sfh_info> infos;
 };
 
 // ------------------------------------------------------------------------------------------------ several GPUs
