@@ -31,7 +31,9 @@ namespace sfh {
 
 #define SFH_TILE 128u         /* items per classification tile = threads of a k_classify block. Small: the classifier of a single
                                  hull (783 chunks) then runs on 7 SMs instead of one, whose L1 miss path its ~40 texel loads per item saturated */
+#ifndef SFH_SEG_PER_STREAM
 #define SFH_SEG_PER_STREAM 16u /* at most this many segments per resident stream (warp) */
+#endif
 enum { CK_DRY = 0, CK_WET = 1, CK_CLIP = 2 };
 // control words of the surface path (device, zeroed once): the classifier's last block fills them in for the consumers
 // (totals and segment sizes count SUB-ITEMS: entries x split, see finish_lists)
