@@ -341,8 +341,11 @@ def measure(rig: Rig, args, workload: str, n: int, first: int, keep_host: int, s
     def step_device():
         ctx.compute_device(ostruct, d_states.data_ptr(), n, d_infos.data_ptr(), hints)
 
-    def step_host():
-        ctx.lib.sfh_step(ctx.ctx, C.byref(ostruct), h_states.ctypes.data, n, h_infos.ctypes.data)
+    sfh_step, ocean_ref, p_states, p_infos = ctx.lib.sfh_step, C.byref(ostruct), h_states.ctypes.data, h_infos.ctypes.data
+
+    def step_host():  # the C call a host makes per step: pointers and the ocean record are the caller's, prepared once
+        if sfh_step(ctx.ctx, ocean_ref, p_states, n, p_infos) != 0:
+            raise RuntimeError("sfh_step: " + ctx.lib.sfh_last_error(ctx.ctx).decode())
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
